@@ -1,0 +1,292 @@
+"""entropy_coders_b200 -- B200 (sm_100a) FSE / tANS coder behind the public API of the Rust crate
+Cognoscan/entropy_coders.
+
+Layers (all arithmetic runs in libfse_b200.so; this package is host plumbing only):
+
+* `_capi`        ctypes binding of include/fse_b200.h (the drop-in C ABI).
+* `Context`      device-pointer API over torch CUDA tensors: stage entry points
+                 (histogram, normalise, NCount header, table builds) and the fused block pipelines.
+* crate mirror   `Histogram`, `NormHistogram`, `fse.EncodeTable`, `fse.DecodeTable`,
+                 `fse_compress`, `fse_compress2`, `fse_decompress`, `fse_decompress2` with the crate's
+                 names, argument meaning and error behaviour (src/lib.rs:7, :112-248), each backed by
+                 the CUDA path with the whole input as one block.
+
+There is no CPU fallback: without the built library or without a CUDA device every call raises.
+"""
+import ctypes as C
+
+from . import _capi
+from ._capi import FseError, Params
+
+TABLE_LOG_MIN, TABLE_LOG_MAX, TABLE_LOG_DEFAULT = 5, 15, 11  # src/lib.rs:9-12
+TABLE_PER_BLOCK, TABLE_GLOBAL = 0, 1
+GEN_KINDS = {"geo": 0, "text": 1, "few": 2, "uniform": 3}
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("entropy_coders_b200 needs a CUDA device (no CPU fallback)")
+    return torch
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class Context:
+    """One fse_b200_ctx: a device, a stream and reusable device workspaces."""
+
+    def __init__(self, device=0, stream=None):
+        torch = _torch()
+        self._L = _capi.lib()
+        self.device = torch.device("cuda", device)
+        self._h = C.c_void_p()
+        s = C.c_void_p(stream) if stream else None
+        rc = self._L.fse_b200_create(device, s, C.byref(self._h))
+        if rc != 0:
+            raise FseError(rc, "fse_b200_create")
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._L.fse_b200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise FseError(rc, self._L.fse_b200_last_error(self._h).decode())
+
+    @property
+    def launches(self):
+        return int(self._L.fse_b200_launch_count(self._h))
+
+    def sync(self):
+        self._ck(self._L.fse_b200_sync(self._h))
+
+    KERNELS = ("hist", "encode", "scan", "gather", "decode")
+
+    def set_timing(self, enable=True):
+        self._ck(self._L.fse_b200_set_timing(self._h, 1 if enable else 0))
+
+    def get_timing(self):
+        """-> {kernel: (total ms, launches)} from CUDA events around each launch"""
+        ms = (C.c_double * 5)()
+        cnt = (C.c_uint64 * 5)()
+        self._ck(self._L.fse_b200_get_timing(self._h, ms, cnt))
+        return {k: (ms[i], int(cnt[i])) for i, k in enumerate(self.KERNELS)}
+
+    # ------------------------------------------------------------------ helpers
+    def _u8(self, n):
+        return _torch().empty(max(int(n), 1), dtype=_torch().uint8, device=self.device)
+
+    def params(self, block_size, table_log=0, n_states=32, table_mode=TABLE_PER_BLOCK):
+        return Params(int(block_size), int(table_log), int(n_states), int(table_mode))
+
+    def num_blocks(self, n, block_size):
+        return int(self._L.fse_b200_num_blocks(n, block_size))
+
+    def bound(self, n, p):
+        return int(self._L.fse_b200_compress_blocks_bound(n, C.byref(p)))
+
+    def generate(self, kind, seed, n, first_index=0):
+        """Synthetic bytes of SURVEY.md 8(d), generated on the device."""
+        out = self._u8(n)
+        self._ck(self._L.fse_b200_generate(self._h, GEN_KINDS[kind], seed, first_index, _ptr(out), n))
+        return out[:n]
+
+    # ------------------------------------------------------------------ stages
+    def histogram_blocks(self, src, block_size):
+        """Histogram::new per block (src/histogram.rs:18-66) -> (counts int32[nb,256] holding u32, table_len[nb])"""
+        torch = _torch()
+        nb = self.num_blocks(src.numel(), block_size)
+        counts = torch.empty((nb, 256), dtype=torch.int32, device=self.device)
+        tlen = torch.empty(nb, dtype=torch.int32, device=self.device)
+        self._ck(self._L.fse_b200_histogram_blocks(self._h, _ptr(src), src.numel(), block_size, _ptr(counts), _ptr(tlen)))
+        return counts, tlen
+
+    def histogram_global(self, src):
+        torch = _torch()
+        counts = torch.empty(256, dtype=torch.int64, device=self.device)
+        self._ck(self._L.fse_b200_histogram_global(self._h, _ptr(src), src.numel(), _ptr(counts)))
+        return counts
+
+    def normalize(self, counts64, table_log=0):
+        """Histogram::normalize (+optimal_log2 when table_log == 0), src/histogram.rs:95-277.
+        counts64: int64[nt,256] -> (norm int32[nt,256], log2[nt], table_len[nt], status[nt])"""
+        torch = _torch()
+        counts64 = counts64.reshape(-1, 256).contiguous()
+        nt = counts64.shape[0]
+        norm = torch.empty((nt, 256), dtype=torch.int32, device=self.device)
+        log2 = torch.empty(nt, dtype=torch.int32, device=self.device)
+        tlen = torch.empty(nt, dtype=torch.int32, device=self.device)
+        st = torch.empty(nt, dtype=torch.int32, device=self.device)
+        self._ck(self._L.fse_b200_normalize(self._h, _ptr(counts64), nt, table_log, _ptr(norm), _ptr(log2), _ptr(tlen), _ptr(st)))
+        return norm, log2, tlen, st
+
+    def ncount_write(self, norm, log2, tlen):
+        """NormHistogram::write, src/histogram.rs:376-431 -> (rows uint8[nt,512], bytes[nt], bits[nt])"""
+        torch = _torch()
+        nt = norm.shape[0]
+        out = torch.zeros((nt, 512), dtype=torch.uint8, device=self.device)
+        nbytes = torch.empty(nt, dtype=torch.int32, device=self.device)
+        nbits = torch.empty(nt, dtype=torch.int32, device=self.device)
+        self._ck(self._L.fse_b200_ncount_write(self._h, _ptr(norm), _ptr(log2), _ptr(tlen), nt, _ptr(out), 512, _ptr(nbytes), _ptr(nbits)))
+        return out, nbytes, nbits
+
+    def ncount_read(self, rows, lens):
+        """NormHistogram::read, src/histogram.rs:436-505 -> (norm, log2, table_len, consumed, status)"""
+        torch = _torch()
+        nt, stride = rows.shape
+        norm = torch.empty((nt, 256), dtype=torch.int32, device=self.device)
+        log2 = torch.empty(nt, dtype=torch.int32, device=self.device)
+        tlen = torch.empty(nt, dtype=torch.int32, device=self.device)
+        cons = torch.empty(nt, dtype=torch.int32, device=self.device)
+        st = torch.empty(nt, dtype=torch.int32, device=self.device)
+        self._ck(self._L.fse_b200_ncount_read(self._h, _ptr(rows), stride, _ptr(lens), nt, _ptr(norm), _ptr(log2), _ptr(tlen), _ptr(cons), _ptr(st)))
+        return norm, log2, tlen, cons, st
+
+    def build_encode_tables(self, norm, log2, tlen, max_table_log):
+        """EncodeTable::update, src/fse.rs:101-189 -> (table int16[nt,S] holding u16, symbol_tt int32[nt,256,2], symbols uint8[nt,S], status)"""
+        torch = _torch()
+        nt, S = norm.shape[0], 1 << max_table_log
+        table = torch.zeros((nt, S), dtype=torch.int16, device=self.device)
+        tt = torch.zeros((nt, 256, 2), dtype=torch.int32, device=self.device)
+        sym = torch.zeros((nt, S), dtype=torch.uint8, device=self.device)
+        st = torch.empty(nt, dtype=torch.int32, device=self.device)
+        self._ck(self._L.fse_b200_build_encode_tables(self._h, _ptr(norm), _ptr(log2), _ptr(tlen), nt, max_table_log,
+                                                      _ptr(table), _ptr(tt), _ptr(sym), _ptr(st)))
+        return table, tt, sym, st
+
+    def build_decode_tables(self, norm, log2, tlen, max_table_log):
+        """DecodeTable::update, src/fse.rs:280-338 -> (table int32[nt,S] = new_state | symbol<<16 | num_bits<<24, status)"""
+        torch = _torch()
+        nt, S = norm.shape[0], 1 << max_table_log
+        table = torch.zeros((nt, S), dtype=torch.int32, device=self.device)
+        st = torch.empty(nt, dtype=torch.int32, device=self.device)
+        self._ck(self._L.fse_b200_build_decode_tables(self._h, _ptr(norm), _ptr(log2), _ptr(tlen), nt, max_table_log, _ptr(table), _ptr(st)))
+        return table, st
+
+    # ------------------------------------------------------------------ fused pipelines (device tensors)
+    def compress_blocks(self, src, block_size, table_log=0, n_states=32, table_mode=TABLE_PER_BLOCK, out=None):
+        """-> (dst uint8[cap] (first `total` bytes valid), offsets int64[nb+1], status int32[nb], total)"""
+        torch = _torch()
+        p = self.params(block_size, table_log, n_states, table_mode)
+        n = src.numel()
+        nb = self.num_blocks(n, block_size)
+        cap = self.bound(n, p)
+        if out is None:
+            dst = self._u8(cap)
+            offsets = torch.empty(nb + 1, dtype=torch.int64, device=self.device)
+            status = torch.empty(max(nb, 1), dtype=torch.int32, device=self.device)
+        else:
+            dst, offsets, status = out
+        total = C.c_uint64()
+        self._ck(self._L.fse_b200_compress_blocks(self._h, _ptr(src), n, C.byref(p), _ptr(dst), dst.numel(), _ptr(offsets),
+                                                  _ptr(status), C.byref(total)))
+        return dst, offsets, status[:nb], int(total.value)
+
+    def compress_blocks_async(self, src, p, dst, offsets, status):
+        self._ck(self._L.fse_b200_compress_blocks_async(self._h, _ptr(src), src.numel(), C.byref(p), _ptr(dst), dst.numel(),
+                                                        _ptr(offsets), _ptr(status)))
+
+    def decompress_blocks(self, comp, total, offsets, n, block_size, table_log=0, n_states=32, table_mode=TABLE_PER_BLOCK, out=None):
+        """-> (dst uint8[n], status int32[nb])"""
+        torch = _torch()
+        p = self.params(block_size, table_log, n_states, table_mode)
+        nb = self.num_blocks(n, block_size)
+        if out is None:
+            dst = self._u8(n)
+            status = torch.empty(max(nb, 1), dtype=torch.int32, device=self.device)
+        else:
+            dst, status = out
+        self._ck(self._L.fse_b200_decompress_blocks(self._h, _ptr(comp), total, _ptr(offsets), nb, C.byref(p), _ptr(dst), n, _ptr(status)))
+        return dst[:n], status[:nb]
+
+    def decompress_blocks_async(self, comp, total, offsets, nb, p, dst, n, status):
+        self._ck(self._L.fse_b200_decompress_blocks_async(self._h, _ptr(comp), total, _ptr(offsets), nb, C.byref(p), _ptr(dst), n, _ptr(status)))
+
+    def decompress_exhaust(self, comp, total, offsets, nblocks, capacity, max_table_log=0, n_states=2):
+        """The reference's termination rule (no stored length).  -> (dst uint8[nb, capacity], out_len[nb], status[nb])"""
+        torch = _torch()
+        p = self.params(capacity, max_table_log, n_states, TABLE_PER_BLOCK)
+        dst = torch.empty((nblocks, capacity), dtype=torch.uint8, device=self.device)
+        out_len = torch.zeros(nblocks, dtype=torch.int32, device=self.device)
+        status = torch.empty(nblocks, dtype=torch.int32, device=self.device)
+        self._ck(self._L.fse_b200_decompress_exhaust(self._h, _ptr(comp), total, _ptr(offsets), nblocks, C.byref(p), _ptr(dst),
+                                                     _ptr(out_len), _ptr(status)))
+        return dst, out_len, status
+
+    def set_global_table(self, counts64, table_log=0):
+        """-> (header bytes, effective log2)"""
+        hdr = (C.c_uint8 * 512)()
+        hb = C.c_size_t(512)
+        l2 = C.c_uint32()
+        self._ck(self._L.fse_b200_set_global_table(self._h, _ptr(counts64), table_log, hdr, C.byref(hb), C.byref(l2)))
+        return bytes(hdr[: hb.value]), int(l2.value)
+
+    def set_global_table_from_header(self, header):
+        buf = (C.c_uint8 * len(header)).from_buffer_copy(header)
+        l2 = C.c_uint32()
+        self._ck(self._L.fse_b200_set_global_table_from_header(self._h, buf, len(header), C.byref(l2)))
+        return int(l2.value)
+
+    # ------------------------------------------------------------------ host buffers (numpy / pinned torch)
+    def compress_host(self, src, block_size, table_log=0, n_states=32, table_mode=TABLE_PER_BLOCK, dst=None):
+        """src, dst: host uint8 arrays (numpy or CPU torch).  -> (dst, offsets, status, total)"""
+        import numpy as np
+        p = self.params(block_size, table_log, n_states, table_mode)
+        n = int(src.size if hasattr(src, "size") and not callable(src.size) else src.numel())
+        nb = self.num_blocks(n, block_size)
+        if dst is None:
+            dst = np.empty(self.bound(n, p), dtype=np.uint8)
+        offsets = np.zeros(nb + 1, dtype=np.uint64)
+        status = np.zeros(max(nb, 1), dtype=np.int32)
+        total = C.c_uint64()
+        rc = self._L.fse_b200_compress_host(self._h, _host_ptr(src), n, C.byref(p), _host_ptr(dst), _host_len(dst),
+                                            _host_ptr(offsets), _host_ptr(status), C.byref(total))
+        if rc not in (0, -11):
+            self._ck(rc)
+        return dst, offsets, status[:nb], int(total.value)
+
+    def decompress_host(self, comp, total, offsets, n, block_size, table_log=0, n_states=32, table_mode=TABLE_PER_BLOCK, dst=None):
+        import numpy as np
+        p = self.params(block_size, table_log, n_states, table_mode)
+        nb = self.num_blocks(n, block_size)
+        if dst is None:
+            dst = np.empty(max(n, 1), dtype=np.uint8)
+        status = np.zeros(max(nb, 1), dtype=np.int32)
+        rc = self._L.fse_b200_decompress_host(self._h, _host_ptr(comp), total, _host_ptr(offsets), nb, C.byref(p),
+                                              _host_ptr(dst), n, _host_ptr(status))
+        if rc not in (0, -11):
+            self._ck(rc)
+        return dst[:n], status[:nb]
+
+
+def _host_ptr(a):
+    if hasattr(a, "ctypes"):
+        return C.c_void_p(a.ctypes.data)
+    return C.c_void_p(a.data_ptr())
+
+
+def _host_len(a):
+    return int(a.nbytes) if hasattr(a, "nbytes") else int(a.numel() * a.element_size())
+
+
+_default_ctx = None
+
+
+def default_context():
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(0)
+    return _default_ctx
+
+
+from .crate import (Histogram, NormHistogram, HistError, fse, fse_compress, fse_compress2,  # noqa: E402,F401
+                    fse_decompress, fse_decompress2)

@@ -1,0 +1,35 @@
+"""Builds entropy_coders_b200/libfse_b200.so in-tree with nvcc for sm_100a (no JIT cache, no CPU path)."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+SRC = os.path.join(HERE, "csrc", "fse_b200.cu")
+DEPS = [SRC, os.path.join(HERE, "csrc", "fse_kernels.cuh"), os.path.join(HERE, "csrc", "fse_device.cuh"),
+        os.path.join(ROOT, "include", "fse_b200.h")]
+OUT = os.path.join(HERE, "libfse_b200.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+
+
+def needs_build():
+    if not os.path.exists(OUT):
+        return True
+    t = os.path.getmtime(OUT)
+    return any(os.path.getmtime(d) > t for d in DEPS)
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return OUT
+    cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+           "-Xcompiler", "-fPIC", "-shared", "-o", OUT, SRC, "-lcudart"]
+    if verbose:
+        cmd.insert(1, "-Xptxas")
+        cmd.insert(2, "-v")
+    subprocess.check_call(cmd)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

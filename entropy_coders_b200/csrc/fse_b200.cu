@@ -1,0 +1,728 @@
+// fse_b200.cu -- C ABI of libfse_b200.so (see include/fse_b200.h).  Host orchestration only;
+// all arithmetic runs in the kernels of fse_kernels.cuh.  There is no CPU fallback.
+#include "../../include/fse_b200.h"
+#include "fse_kernels.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace fsed;
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = std::max(bytes, cap + cap / 2);
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T *as() { return reinterpret_cast<T *>(p); }
+};
+
+struct HostBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+        cudaError_t e = cudaMallocHost(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct fse_b200_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int num_sms = 148;
+    size_t smem_optin = 0;
+    uint64_t launches = 0;
+    std::string err;
+    // workspaces
+    DevBuf counts, hlen, plen, scratch, offsets_tmp, status_tmp, misc;
+    DevBuf stage_in, stage_out, stage_off, stage_status;  // host-buffer conveniences
+    HostBuf pin;
+    // global table
+    DevBuf g_enc_table, g_enc_tt, g_dec_table, g_norm, g_meta, g_hdr;
+    uint32_t g_log2 = 0, g_table_len = 0;
+    bool g_valid = false;
+    // optional per-kernel timing (bench.py's roofline figures): events on the launching stream
+    bool timing = false;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    struct Span { int kernel; size_t e0, e1; };
+    std::vector<Span> spans;
+    double t_ms[FSE_B200_NUM_KERNELS] = {0};
+    uint64_t t_count[FSE_B200_NUM_KERNELS] = {0};
+    // generator LUTs
+    DevBuf lut[4];
+    uint32_t lut_len[4] = {0, 0, 0, 0};
+};
+
+namespace {
+
+int fail(fse_b200_ctx *c, int code, const char *what, cudaError_t e = cudaSuccess)
+{
+    if (c) {
+        c->err = what;
+        if (e != cudaSuccess) { c->err += ": "; c->err += cudaGetErrorString(e); }
+    }
+    return code;
+}
+
+#define CK(call)                                                             \
+    do {                                                                     \
+        cudaError_t e_ = (call);                                             \
+        if (e_ != cudaSuccess) return fail(ctx, FSE_B200_ERR_CUDA, #call, e_); \
+    } while (0)
+
+// RAII-less span helper: records an event pair around one kernel launch when timing is on
+size_t ev_get(fse_b200_ctx *c)
+{
+    if (c->ev_used == c->ev_pool.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        c->ev_pool.push_back(e);
+    }
+    return c->ev_used++;
+}
+struct Timed {
+    fse_b200_ctx *c; int k; size_t e0 = 0;
+    Timed(fse_b200_ctx *ctx, int kernel) : c(ctx), k(kernel)
+    {
+        if (c->timing) { e0 = ev_get(c); cudaEventRecord(c->ev_pool[e0], c->stream); }
+    }
+    ~Timed()
+    {
+        c->launches++;
+        if (c->timing) {
+            size_t e1 = ev_get(c);
+            cudaEventRecord(c->ev_pool[e1], c->stream);
+            c->spans.push_back({k, e0, e1});
+        }
+    }
+};
+
+bool pow2(uint32_t v) { return v && !(v & (v - 1)); }
+
+int check_params(fse_b200_ctx *ctx, const fse_b200_params *p)
+{
+    if (!ctx || !p) return FSE_B200_ERR_ARG;
+    if (p->block_size == 0 || p->block_size > (1u << 30)) return fail(ctx, FSE_B200_ERR_ARG, "block_size must be in 1..2^30");
+    if (!pow2(p->n_states) || p->n_states > 32) return fail(ctx, FSE_B200_ERR_ARG, "n_states must be 1, 2, 4, 8, 16 or 32");
+    if (p->table_log != 0 && (p->table_log < 5 || p->table_log > 15)) return fail(ctx, FSE_B200_ERR_ARG, "table_log must be 0 or 5..15");
+    if (p->table_mode > 1) return fail(ctx, FSE_B200_ERR_ARG, "table_mode");
+    return 0;
+}
+
+// largest table_log a per-block launch can meet: the request (or optimal_log2 <= 11), raised to
+// ilog2(table_len-1)+2 <= 9 (src/histogram.rs:96-98)
+uint32_t tlmax_for(const fse_b200_params *p) { return p->table_log == 0 ? 11u : std::max(p->table_log, 9u); }
+
+size_t pay_cap_bytes(uint32_t block_size, uint32_t n_states)
+{
+    size_t v = (size_t)block_size + (block_size >> 7) + 2 * (size_t)n_states + 64;
+    return (v + 15) & ~(size_t)15;
+}
+size_t scratch_stride(uint32_t block_size, uint32_t n_states) { return HDR_RESERVE + pay_cap_bytes(block_size, n_states); }
+
+// pick warps per CTA so that the last wave of blocks is as full as possible
+int pick_warps(size_t nblocks, int num_sms, size_t per_warp_smem, size_t smem_limit, int max_warps)
+{
+    int wmax = (int)std::min<size_t>((size_t)max_warps, smem_limit / per_warp_smem);
+    if (wmax < 1) return 0;
+    int best = wmax;
+    double best_eff = -1;
+    for (int w = wmax; w >= std::max(1, (wmax * 3) / 4); w--) {
+        size_t slots = (size_t)num_sms * w;
+        size_t waves = (nblocks + slots - 1) / slots;
+        double eff = (double)nblocks / (double)(waves * slots);
+        if (eff > best_eff + 1e-9) { best_eff = eff; best = w; }
+    }
+    return best;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *fse_b200_version(void) { return "fse_b200 0.1 (sm_100a)"; }
+
+int fse_b200_create(int device, void *stream, fse_b200_ctx **out)
+{
+    if (!out) return FSE_B200_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return FSE_B200_ERR_CUDA;
+    fse_b200_ctx *ctx = new (std::nothrow) fse_b200_ctx();
+    if (!ctx) return FSE_B200_ERR_CUDA;
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return FSE_B200_ERR_CUDA; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return FSE_B200_ERR_CUDA; }
+    ctx->num_sms = prop.multiProcessorCount;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    if (stream) ctx->stream = (cudaStream_t)stream;
+    else {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return FSE_B200_ERR_CUDA; }
+        ctx->own_stream = true;
+    }
+    cudaFuncSetAttribute(k_hist_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, HIST_SMEM);
+    cudaFuncSetAttribute(k_encode_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
+    cudaFuncSetAttribute(k_decode_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
+    cudaFuncSetAttribute(k_build_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { fse_b200_destroy(ctx); return FSE_B200_ERR_CUDA; }
+    *out = ctx;
+    return FSE_B200_OK;
+}
+
+void fse_b200_destroy(fse_b200_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf *bufs[] = {&ctx->counts, &ctx->hlen, &ctx->plen, &ctx->scratch, &ctx->offsets_tmp, &ctx->status_tmp, &ctx->misc,
+                      &ctx->stage_in, &ctx->stage_out, &ctx->stage_off, &ctx->stage_status, &ctx->g_enc_table,
+                      &ctx->g_enc_tt, &ctx->g_dec_table, &ctx->g_norm, &ctx->g_meta, &ctx->g_hdr,
+                      &ctx->lut[0], &ctx->lut[1], &ctx->lut[2], &ctx->lut[3]};
+    for (DevBuf *b : bufs) b->release();
+    ctx->pin.release();
+    for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *fse_b200_last_error(const fse_b200_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+uint64_t fse_b200_launch_count(const fse_b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int fse_b200_set_timing(fse_b200_ctx *ctx, int enable)
+{
+    if (!ctx) return FSE_B200_ERR_ARG;
+    ctx->timing = enable != 0;
+    ctx->spans.clear();
+    ctx->ev_used = 0;
+    for (int k = 0; k < FSE_B200_NUM_KERNELS; k++) { ctx->t_ms[k] = 0; ctx->t_count[k] = 0; }
+    return FSE_B200_OK;
+}
+
+int fse_b200_get_timing(fse_b200_ctx *ctx, double *ms_total, uint64_t *count)
+{
+    if (!ctx || !ms_total || !count) return FSE_B200_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (const auto &sp : ctx->spans) {
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, ctx->ev_pool[sp.e0], ctx->ev_pool[sp.e1]));
+        ctx->t_ms[sp.kernel] += ms;
+        ctx->t_count[sp.kernel] += 1;
+    }
+    ctx->spans.clear();
+    ctx->ev_used = 0;
+    for (int k = 0; k < FSE_B200_NUM_KERNELS; k++) { ms_total[k] = ctx->t_ms[k]; count[k] = ctx->t_count[k]; }
+    return FSE_B200_OK;
+}
+
+int fse_b200_sync(fse_b200_ctx *ctx)
+{
+    if (!ctx) return FSE_B200_ERR_ARG;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return FSE_B200_OK;
+}
+
+size_t fse_b200_compress_bound(size_t size) { return 512 + size + (size >> 7) + 4 + 8; }
+size_t fse_b200_num_blocks(size_t n, uint32_t block_size) { return block_size ? (n + block_size - 1) / block_size : 0; }
+size_t fse_b200_compress_blocks_bound(size_t n, const fse_b200_params *p)
+{
+    if (!p || !p->block_size) return 0;
+    size_t nb = fse_b200_num_blocks(n, p->block_size);
+    return nb * scratch_stride(p->block_size, p->n_states ? p->n_states : 32) + 16;
+}
+
+// ---------------------------------------------------------------------------------- stages
+
+int fse_b200_histogram_blocks(fse_b200_ctx *ctx, const uint8_t *d_src, size_t n, uint32_t block_size,
+                              uint32_t *d_counts, uint32_t *d_table_len)
+{
+    if (!ctx || !d_src || !d_counts || block_size == 0) return fail(ctx, FSE_B200_ERR_ARG, "histogram_blocks: bad argument");
+    CK(cudaSetDevice(ctx->device));
+    size_t nb = fse_b200_num_blocks(n, block_size);
+    if (nb == 0) return FSE_B200_OK;
+    if (nb > 0xffffffffull) return fail(ctx, FSE_B200_ERR_ARG, "too many blocks");
+    int grid = (int)std::min<size_t>(nb, (size_t)ctx->num_sms * 3);
+    k_hist_blocks<<<grid, HIST_WARPS * 32, HIST_SMEM, ctx->stream>>>(d_src, n, block_size, (uint32_t)nb, d_counts, d_table_len);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    return FSE_B200_OK;
+}
+
+static int hist_global_async(fse_b200_ctx *ctx, const uint8_t *d_src, size_t n, uint64_t *d_counts64)
+{
+    // fixed 1 MiB pieces: counts per piece fit uint32 and the result does not depend on the caller's block size
+    const uint32_t piece = 1u << 20;
+    size_t nb = fse_b200_num_blocks(n, piece);
+    CK(cudaMemsetAsync(d_counts64, 0, 256 * sizeof(uint64_t), ctx->stream));
+    if (nb == 0) return FSE_B200_OK;
+    CK(ctx->counts.reserve(nb * 256 * sizeof(uint32_t)));
+    int grid = (int)std::min<size_t>(nb, (size_t)ctx->num_sms * 3);
+    k_hist_blocks<<<grid, HIST_WARPS * 32, HIST_SMEM, ctx->stream>>>(d_src, n, piece, (uint32_t)nb, ctx->counts.as<uint32_t>(), nullptr);
+    ctx->launches++;
+    k_hist_reduce<<<(int)std::min<size_t>(nb, 64), 256, 0, ctx->stream>>>(ctx->counts.as<uint32_t>(), (uint32_t)nb,
+                                                                          reinterpret_cast<unsigned long long *>(d_counts64));
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return FSE_B200_OK;
+}
+
+int fse_b200_histogram_global(fse_b200_ctx *ctx, const uint8_t *d_src, size_t n, uint64_t *d_counts64)
+{
+    if (!ctx || (!d_src && n) || !d_counts64) return fail(ctx, FSE_B200_ERR_ARG, "histogram_global: bad argument");
+    CK(cudaSetDevice(ctx->device));
+    int rc = hist_global_async(ctx, d_src, n, d_counts64);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return FSE_B200_OK;
+}
+
+int fse_b200_normalize(fse_b200_ctx *ctx, const uint64_t *d_counts64, size_t ntables, uint32_t table_log,
+                       int32_t *d_norm, uint32_t *d_log2, uint32_t *d_table_len, int32_t *d_status)
+{
+    if (!ctx || !d_counts64 || !d_norm || !d_log2 || !d_table_len || !d_status) return fail(ctx, FSE_B200_ERR_ARG, "normalize: bad argument");
+    if (table_log != 0 && (table_log < 5 || table_log > 15)) return fail(ctx, FSE_B200_ERR_ARG, "table_log must be 0 or 5..15");
+    CK(cudaSetDevice(ctx->device));
+    if (ntables == 0) return FSE_B200_OK;
+    int grid = (int)std::min<size_t>(ntables, (size_t)ctx->num_sms * 16);
+    k_normalize<<<grid, 32, 0, ctx->stream>>>(reinterpret_cast<const unsigned long long *>(d_counts64), (uint32_t)ntables,
+                                              table_log, d_norm, d_log2, d_table_len, d_status);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    return FSE_B200_OK;
+}
+
+int fse_b200_ncount_write(fse_b200_ctx *ctx, const int32_t *d_norm, const uint32_t *d_log2, const uint32_t *d_table_len,
+                          size_t ntables, uint8_t *d_out, size_t stride, uint32_t *d_bytes, uint32_t *d_bits)
+{
+    if (!ctx || !d_norm || !d_log2 || !d_table_len || !d_out || !d_bytes || !d_bits) return fail(ctx, FSE_B200_ERR_ARG, "ncount_write: bad argument");
+    if (stride < 512) return fail(ctx, FSE_B200_ERR_CAPACITY, "ncount_write: stride must be >= 512");
+    CK(cudaSetDevice(ctx->device));
+    if (ntables == 0) return FSE_B200_OK;
+    int grid = (int)std::min<size_t>(ntables, (size_t)ctx->num_sms * 16);
+    k_ncount_write<<<grid, 32, 0, ctx->stream>>>(d_norm, d_log2, d_table_len, (uint32_t)ntables, d_out, stride, d_bytes, d_bits);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    return FSE_B200_OK;
+}
+
+int fse_b200_ncount_read(fse_b200_ctx *ctx, const uint8_t *d_in, size_t stride, const uint32_t *d_len, size_t ntables,
+                         int32_t *d_norm, uint32_t *d_log2, uint32_t *d_table_len, uint32_t *d_consumed, int32_t *d_status)
+{
+    if (!ctx || !d_in || !d_len || !d_norm || !d_log2 || !d_table_len || !d_consumed || !d_status)
+        return fail(ctx, FSE_B200_ERR_ARG, "ncount_read: bad argument");
+    CK(cudaSetDevice(ctx->device));
+    if (ntables == 0) return FSE_B200_OK;
+    int grid = (int)std::min<size_t>(ntables, (size_t)ctx->num_sms * 16);
+    k_ncount_read<<<grid, 32, 0, ctx->stream>>>(d_in, stride, d_len, (uint32_t)ntables, d_norm, d_log2, d_table_len, d_consumed, d_status);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    return FSE_B200_OK;
+}
+
+static int build_tables(fse_b200_ctx *ctx, const int32_t *d_norm, const uint32_t *d_log2, const uint32_t *d_table_len,
+                        size_t ntables, uint32_t max_log2, int decode, uint16_t *enc, uint2 *tt, uint8_t *sym,
+                        uint32_t *dec, int32_t *d_status, bool sync)
+{
+    if (max_log2 < 5 || max_log2 > 15) return fail(ctx, FSE_B200_ERR_ARG, "max_table_log must be 5..15");
+    CK(cudaSetDevice(ctx->device));
+    if (ntables == 0) return FSE_B200_OK;
+    size_t smem = 4096 + 5 * ((size_t)1 << max_log2);
+    if (smem > ctx->smem_optin) return fail(ctx, FSE_B200_ERR_UNSUPPORTED, "table too large for shared memory");
+    int grid = (int)std::min<size_t>(ntables, (size_t)ctx->num_sms * 8);
+    k_build_tables<<<grid, 32, smem, ctx->stream>>>(d_norm, d_log2, d_table_len, (uint32_t)ntables, max_log2, decode, enc, tt, sym, dec, d_status);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    if (sync) CK(cudaStreamSynchronize(ctx->stream));
+    return FSE_B200_OK;
+}
+
+int fse_b200_build_encode_tables(fse_b200_ctx *ctx, const int32_t *d_norm, const uint32_t *d_log2, const uint32_t *d_table_len,
+                                 size_t ntables, uint32_t max_table_log, uint16_t *d_table,
+                                 fse_b200_symbol_transform *d_symbol_tt, uint8_t *d_symbols, int32_t *d_status)
+{
+    if (!ctx || !d_norm || !d_log2 || !d_table_len || !d_table || !d_symbol_tt || !d_status)
+        return fail(ctx, FSE_B200_ERR_ARG, "build_encode_tables: bad argument");
+    return build_tables(ctx, d_norm, d_log2, d_table_len, ntables, max_table_log, 0, d_table,
+                        reinterpret_cast<uint2 *>(d_symbol_tt), d_symbols, nullptr, d_status, true);
+}
+
+int fse_b200_build_decode_tables(fse_b200_ctx *ctx, const int32_t *d_norm, const uint32_t *d_log2, const uint32_t *d_table_len,
+                                 size_t ntables, uint32_t max_table_log, fse_b200_decode_transform *d_table, int32_t *d_status)
+{
+    if (!ctx || !d_norm || !d_log2 || !d_table_len || !d_table || !d_status)
+        return fail(ctx, FSE_B200_ERR_ARG, "build_decode_tables: bad argument");
+    return build_tables(ctx, d_norm, d_log2, d_table_len, ntables, max_table_log, 1, nullptr, nullptr, nullptr,
+                        reinterpret_cast<uint32_t *>(d_table), d_status, true);
+}
+
+// ---------------------------------------------------------------------------------- global table
+
+static int install_global(fse_b200_ctx *ctx, uint32_t *h_log2)
+{
+    // g_norm / g_meta (log2, table_len, status) are on the device; build both tables at the effective log2
+    uint32_t meta[4];
+    CK(cudaMemcpyAsync(meta, ctx->g_meta.p, sizeof(meta), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    int32_t st = (int32_t)meta[2];
+    if (st < 0) return fail(ctx, st, "global table: normalisation failed");
+    uint32_t log2 = meta[0];
+    size_t size = (size_t)1 << log2;
+    CK(ctx->g_enc_table.reserve(size * 2));
+    CK(ctx->g_enc_tt.reserve(256 * 8));
+    CK(ctx->g_dec_table.reserve(size * 4));
+    uint32_t *m = ctx->g_meta.as<uint32_t>();
+    int rc = build_tables(ctx, ctx->g_norm.as<int32_t>(), m, m + 1, 1, log2, 0, ctx->g_enc_table.as<uint16_t>(),
+                          ctx->g_enc_tt.as<uint2>(), nullptr, nullptr, reinterpret_cast<int32_t *>(m + 3), false);
+    if (rc) return rc;
+    rc = build_tables(ctx, ctx->g_norm.as<int32_t>(), m, m + 1, 1, log2, 1, nullptr, nullptr, nullptr,
+                      ctx->g_dec_table.as<uint32_t>(), reinterpret_cast<int32_t *>(m + 3), true);
+    if (rc) return rc;
+    ctx->g_log2 = log2;
+    ctx->g_table_len = meta[1];
+    ctx->g_valid = true;
+    if (h_log2) *h_log2 = log2;
+    return FSE_B200_OK;
+}
+
+int fse_b200_set_global_table(fse_b200_ctx *ctx, const uint64_t *d_counts64, uint32_t table_log,
+                              uint8_t *h_header, size_t *h_header_bytes, uint32_t *h_log2)
+{
+    if (!ctx || !d_counts64) return fail(ctx, FSE_B200_ERR_ARG, "set_global_table: bad argument");
+    if (table_log != 0 && (table_log < 5 || table_log > 15)) return fail(ctx, FSE_B200_ERR_ARG, "table_log must be 0 or 5..15");
+    CK(cudaSetDevice(ctx->device));
+    ctx->g_valid = false;
+    CK(ctx->g_norm.reserve(1024));
+    CK(ctx->g_meta.reserve(64));
+    CK(ctx->g_hdr.reserve(512));
+    uint32_t *m = ctx->g_meta.as<uint32_t>();
+    k_normalize<<<1, 32, 0, ctx->stream>>>(reinterpret_cast<const unsigned long long *>(d_counts64), 1, table_log,
+                                           ctx->g_norm.as<int32_t>(), m, m + 1, reinterpret_cast<int32_t *>(m + 2));
+    ctx->launches++;
+    CK(cudaGetLastError());
+    int rc = install_global(ctx, h_log2);
+    if (rc) return rc;
+    if (h_header && h_header_bytes) {
+        k_ncount_write<<<1, 32, 0, ctx->stream>>>(ctx->g_norm.as<int32_t>(), m, m + 1, 1, ctx->g_hdr.as<uint8_t>(), 512, m + 4, m + 5);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        uint32_t hb[2];
+        CK(cudaMemcpyAsync(hb, m + 4, sizeof(hb), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (hb[0] > *h_header_bytes) return fail(ctx, FSE_B200_ERR_CAPACITY, "header buffer too small");
+        CK(cudaMemcpy(h_header, ctx->g_hdr.p, hb[0], cudaMemcpyDeviceToHost));
+        *h_header_bytes = hb[0];
+    }
+    return FSE_B200_OK;
+}
+
+int fse_b200_set_global_table_from_header(fse_b200_ctx *ctx, const uint8_t *h_header, size_t header_bytes, uint32_t *h_log2)
+{
+    if (!ctx || !h_header || header_bytes == 0 || header_bytes > 512) return fail(ctx, FSE_B200_ERR_ARG, "set_global_table_from_header: bad argument");
+    CK(cudaSetDevice(ctx->device));
+    ctx->g_valid = false;
+    CK(ctx->g_norm.reserve(1024));
+    CK(ctx->g_meta.reserve(64));
+    CK(ctx->g_hdr.reserve(512));
+    uint32_t *m = ctx->g_meta.as<uint32_t>();
+    uint32_t len = (uint32_t)header_bytes;
+    CK(cudaMemcpyAsync(ctx->g_hdr.p, h_header, header_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(m + 6, &len, 4, cudaMemcpyHostToDevice, ctx->stream));
+    k_ncount_read<<<1, 32, 0, ctx->stream>>>(ctx->g_hdr.as<uint8_t>(), 512, m + 6, 1, ctx->g_norm.as<int32_t>(), m, m + 1, m + 7,
+                                             reinterpret_cast<int32_t *>(m + 2));
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return install_global(ctx, h_log2);
+}
+
+// ---------------------------------------------------------------------------------- pipelines
+
+int fse_b200_compress_blocks_async(fse_b200_ctx *ctx, const uint8_t *d_src, size_t n, const fse_b200_params *p,
+                                   uint8_t *d_dst, size_t dst_cap, uint64_t *d_offsets, int32_t *d_status)
+{
+    int rc = check_params(ctx, p);
+    if (rc) return rc;
+    if ((!d_src && n) || !d_dst || !d_offsets || !d_status) return fail(ctx, FSE_B200_ERR_ARG, "compress_blocks: null pointer");
+    CK(cudaSetDevice(ctx->device));
+    const size_t nb = fse_b200_num_blocks(n, p->block_size);
+    if (nb > 0x7fffffffull) return fail(ctx, FSE_B200_ERR_ARG, "too many blocks");
+    if (dst_cap < fse_b200_compress_blocks_bound(n, p)) return fail(ctx, FSE_B200_ERR_CAPACITY, "dst_cap < fse_b200_compress_blocks_bound");
+    const bool global = p->table_mode == FSE_B200_TABLE_GLOBAL;
+    if (global && !ctx->g_valid) return fail(ctx, FSE_B200_ERR_ARG, "global table not installed");
+    if (nb == 0) {
+        CK(cudaMemsetAsync(d_offsets, 0, sizeof(uint64_t), ctx->stream));
+        return FSE_B200_OK;
+    }
+    const uint32_t tlmax = global ? ctx->g_log2 : tlmax_for(p);
+    const size_t stride = scratch_stride(p->block_size, p->n_states);
+    CK(ctx->hlen.reserve(nb * 4));
+    CK(ctx->plen.reserve(nb * 4));
+    CK(ctx->scratch.reserve(nb * stride));
+    if (!global) {
+        CK(ctx->counts.reserve(nb * 256 * sizeof(uint32_t)));
+        int grid = (int)std::min<size_t>(nb, (size_t)ctx->num_sms * 3);
+        Timed t(ctx, FSE_B200_K_HIST);
+        k_hist_blocks<<<grid, HIST_WARPS * 32, HIST_SMEM, ctx->stream>>>(d_src, n, p->block_size, (uint32_t)nb,
+                                                                       ctx->counts.as<uint32_t>(), nullptr);
+    }
+    EncArgs a;
+    a.src = d_src; a.n = n; a.block_size = p->block_size; a.nblocks = (uint32_t)nb;
+    a.req_log2 = p->table_log; a.n_states = p->n_states; a.tlmax = tlmax;
+    a.counts = ctx->counts.as<uint32_t>();
+    a.scratch = ctx->scratch.as<uint8_t>(); a.stride = stride;
+    a.pay_cap_words = (uint32_t)(pay_cap_bytes(p->block_size, p->n_states) / 4);
+    a.hlen = ctx->hlen.as<uint32_t>(); a.plen = ctx->plen.as<uint32_t>(); a.status = d_status;
+    a.global_mode = global ? 1 : 0;
+    a.g.log2 = ctx->g_log2; a.g.table_len = ctx->g_table_len;
+    a.g.enc_table = ctx->g_enc_table.as<uint16_t>(); a.g.enc_tt = ctx->g_enc_tt.as<uint2>(); a.g.dec_table = ctx->g_dec_table.as<uint32_t>();
+    const EncLayout lay = enc_layout(tlmax);
+    int wpc = pick_warps(nb, ctx->num_sms, lay.total, ctx->smem_optin, 16);
+    if (wpc < 1) return fail(ctx, FSE_B200_ERR_UNSUPPORTED, "table_log too large for shared memory");
+    int grid = (int)std::min<size_t>((nb + wpc - 1) / wpc, (size_t)ctx->num_sms);
+    {
+        Timed t(ctx, FSE_B200_K_ENCODE);
+        k_encode_blocks<<<grid, wpc * 32, (size_t)wpc * lay.total, ctx->stream>>>(a);
+    }
+    {
+        Timed t(ctx, FSE_B200_K_SCAN);
+        k_scan_sizes<<<1, 1024, 0, ctx->stream>>>(a.hlen, a.plen, (uint32_t)nb, reinterpret_cast<unsigned long long *>(d_offsets));
+    }
+    {
+        Timed t(ctx, FSE_B200_K_GATHER);
+        k_gather<<<(int)std::min<size_t>(nb, (size_t)ctx->num_sms * 8), 256, 0, ctx->stream>>>(
+            a.scratch, stride, a.hlen, a.plen, reinterpret_cast<const unsigned long long *>(d_offsets), (uint32_t)nb, d_dst);
+    }
+    CK(cudaGetLastError());
+    return FSE_B200_OK;
+}
+
+int fse_b200_compress_blocks(fse_b200_ctx *ctx, const uint8_t *d_src, size_t n, const fse_b200_params *p,
+                             uint8_t *d_dst, size_t dst_cap, uint64_t *d_offsets, int32_t *d_status, uint64_t *h_total)
+{
+    int rc = fse_b200_compress_blocks_async(ctx, d_src, n, p, d_dst, dst_cap, d_offsets, d_status);
+    if (rc) return rc;
+    const size_t nb = fse_b200_num_blocks(n, p->block_size);
+    uint64_t total = 0;
+    CK(cudaMemcpyAsync(&total, d_offsets + nb, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (h_total) *h_total = total;
+    return FSE_B200_OK;
+}
+
+int fse_b200_decompress_blocks_async(fse_b200_ctx *ctx, const uint8_t *d_comp, size_t comp_bytes, const uint64_t *d_offsets,
+                                     size_t nblocks, const fse_b200_params *p, uint8_t *d_dst, size_t n, int32_t *d_status)
+{
+    int rc = check_params(ctx, p);
+    if (rc) return rc;
+    if (!d_comp || !d_offsets || (!d_dst && n) || !d_status) return fail(ctx, FSE_B200_ERR_ARG, "decompress_blocks: null pointer");
+    if (nblocks != fse_b200_num_blocks(n, p->block_size)) return fail(ctx, FSE_B200_ERR_ARG, "nblocks does not match n / block_size");
+    if (nblocks > 0x7fffffffull) return fail(ctx, FSE_B200_ERR_ARG, "too many blocks");
+    CK(cudaSetDevice(ctx->device));
+    if (nblocks == 0) return FSE_B200_OK;
+    const bool global = p->table_mode == FSE_B200_TABLE_GLOBAL;
+    if (global && !ctx->g_valid) return fail(ctx, FSE_B200_ERR_ARG, "global table not installed");
+    const uint32_t tlmax = global ? ctx->g_log2 : tlmax_for(p);
+    DecArgs a;
+    a.comp = d_comp; a.comp_bytes = comp_bytes; a.offsets = reinterpret_cast<const unsigned long long *>(d_offsets);
+    a.nblocks = (uint32_t)nblocks; a.block_size = p->block_size; a.n = n; a.n_states = p->n_states; a.tlmax = tlmax;
+    a.dst = d_dst; a.status = d_status; a.global_mode = global ? 1 : 0;
+    a.exhaust = 0; a.out_len = nullptr;
+    a.g.log2 = ctx->g_log2; a.g.table_len = ctx->g_table_len;
+    a.g.enc_table = ctx->g_enc_table.as<uint16_t>(); a.g.enc_tt = ctx->g_enc_tt.as<uint2>(); a.g.dec_table = ctx->g_dec_table.as<uint32_t>();
+    const DecLayout lay = dec_layout(tlmax);
+    int wpc = pick_warps(nblocks, ctx->num_sms, lay.total, ctx->smem_optin, 16);
+    if (wpc < 1) return fail(ctx, FSE_B200_ERR_UNSUPPORTED, "table_log too large for shared memory");
+    int grid = (int)std::min<size_t>((nblocks + wpc - 1) / wpc, (size_t)ctx->num_sms);
+    {
+        Timed t(ctx, FSE_B200_K_DECODE);
+        k_decode_blocks<<<grid, wpc * 32, (size_t)wpc * lay.total, ctx->stream>>>(a);
+    }
+    CK(cudaGetLastError());
+    return FSE_B200_OK;
+}
+
+int fse_b200_decompress_blocks(fse_b200_ctx *ctx, const uint8_t *d_comp, size_t comp_bytes, const uint64_t *d_offsets,
+                               size_t nblocks, const fse_b200_params *p, uint8_t *d_dst, size_t n, int32_t *d_status)
+{
+    int rc = fse_b200_decompress_blocks_async(ctx, d_comp, comp_bytes, d_offsets, nblocks, p, d_dst, n, d_status);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return FSE_B200_OK;
+}
+
+int fse_b200_decompress_exhaust(fse_b200_ctx *ctx, const uint8_t *d_comp, size_t comp_bytes, const uint64_t *d_offsets,
+                                size_t nblocks, const fse_b200_params *p, uint8_t *d_dst, uint32_t *d_out_len, int32_t *d_status)
+{
+    int rc = check_params(ctx, p);
+    if (rc) return rc;
+    if (!d_comp || !d_offsets || !d_dst || !d_out_len || !d_status) return fail(ctx, FSE_B200_ERR_ARG, "decompress_exhaust: null pointer");
+    if (p->table_mode != FSE_B200_TABLE_PER_BLOCK) return fail(ctx, FSE_B200_ERR_ARG, "decompress_exhaust: per-block tables only");
+    if (nblocks > 0x7fffffffull) return fail(ctx, FSE_B200_ERR_ARG, "too many blocks");
+    CK(cudaSetDevice(ctx->device));
+    if (nblocks == 0) return FSE_B200_OK;
+    const uint32_t tlmax = p->table_log ? p->table_log : 11u;
+    DecArgs a;
+    a.comp = d_comp; a.comp_bytes = comp_bytes; a.offsets = reinterpret_cast<const unsigned long long *>(d_offsets);
+    a.nblocks = (uint32_t)nblocks; a.block_size = p->block_size; a.n = nblocks * (size_t)p->block_size;
+    a.n_states = p->n_states; a.tlmax = tlmax;
+    a.dst = d_dst; a.status = d_status; a.global_mode = 0; a.exhaust = 1; a.out_len = d_out_len;
+    a.g.log2 = 0; a.g.table_len = 0; a.g.enc_table = nullptr; a.g.enc_tt = nullptr; a.g.dec_table = nullptr;
+    const DecLayout lay = dec_layout(tlmax);
+    int wpc = pick_warps(nblocks, ctx->num_sms, lay.total, ctx->smem_optin, 16);
+    if (wpc < 1) return fail(ctx, FSE_B200_ERR_UNSUPPORTED, "table_log too large for shared memory");
+    int grid = (int)std::min<size_t>((nblocks + wpc - 1) / wpc, (size_t)ctx->num_sms);
+    k_decode_blocks<<<grid, wpc * 32, (size_t)wpc * lay.total, ctx->stream>>>(a);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    return FSE_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------- host buffers
+
+static int worst_status(const int32_t *st, size_t nb)
+{
+    for (size_t i = 0; i < nb; i++) if (st[i] < 0) return FSE_B200_ERR_BLOCK;
+    return FSE_B200_OK;
+}
+
+int fse_b200_compress_host(fse_b200_ctx *ctx, const uint8_t *h_src, size_t n, const fse_b200_params *p, uint8_t *h_dst,
+                           size_t dst_cap, uint64_t *h_offsets, int32_t *h_status, uint64_t *h_total)
+{
+    int rc = check_params(ctx, p);
+    if (rc) return rc;
+    if ((!h_src && n) || !h_dst || !h_total) return fail(ctx, FSE_B200_ERR_ARG, "compress_host: null pointer");
+    CK(cudaSetDevice(ctx->device));
+    const size_t nb = fse_b200_num_blocks(n, p->block_size);
+    const size_t bound = fse_b200_compress_blocks_bound(n, p);
+    CK(ctx->stage_in.reserve(n + 16));
+    CK(ctx->stage_out.reserve(bound));
+    CK(ctx->stage_off.reserve((nb + 1) * 8));
+    CK(ctx->stage_status.reserve((nb + 1) * 4));
+    CK(cudaMemcpyAsync(ctx->stage_in.p, h_src, n, cudaMemcpyHostToDevice, ctx->stream));
+    rc = fse_b200_compress_blocks_async(ctx, ctx->stage_in.as<uint8_t>(), n, p, ctx->stage_out.as<uint8_t>(), bound,
+                                        ctx->stage_off.as<uint64_t>(), ctx->stage_status.as<int32_t>());
+    if (rc) return rc;
+    std::vector<uint64_t> off(nb + 1);
+    std::vector<int32_t> st(nb);
+    CK(cudaMemcpyAsync(off.data(), ctx->stage_off.p, (nb + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (nb) CK(cudaMemcpyAsync(st.data(), ctx->stage_status.p, nb * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    uint64_t total = off[nb];
+    *h_total = total;
+    if (h_offsets) memcpy(h_offsets, off.data(), (nb + 1) * 8);
+    if (h_status && nb) memcpy(h_status, st.data(), nb * 4);
+    if (total > dst_cap) return fail(ctx, FSE_B200_ERR_CAPACITY, "compress_host: dst_cap too small");
+    CK(cudaMemcpyAsync(h_dst, ctx->stage_out.p, total, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return worst_status(st.data(), nb);
+}
+
+int fse_b200_decompress_host(fse_b200_ctx *ctx, const uint8_t *h_comp, size_t comp_bytes, const uint64_t *h_offsets,
+                             size_t nblocks, const fse_b200_params *p, uint8_t *h_dst, size_t n, int32_t *h_status)
+{
+    int rc = check_params(ctx, p);
+    if (rc) return rc;
+    if (!h_comp || !h_offsets || (!h_dst && n)) return fail(ctx, FSE_B200_ERR_ARG, "decompress_host: null pointer");
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->stage_out.reserve(comp_bytes + 16));
+    CK(ctx->stage_in.reserve(n + 16));
+    CK(ctx->stage_off.reserve((nblocks + 1) * 8));
+    CK(ctx->stage_status.reserve((nblocks + 1) * 4));
+    CK(cudaMemcpyAsync(ctx->stage_out.p, h_comp, comp_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->stage_off.p, h_offsets, (nblocks + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    rc = fse_b200_decompress_blocks_async(ctx, ctx->stage_out.as<uint8_t>(), comp_bytes, ctx->stage_off.as<uint64_t>(), nblocks, p,
+                                          ctx->stage_in.as<uint8_t>(), n, ctx->stage_status.as<int32_t>());
+    if (rc) return rc;
+    std::vector<int32_t> st(nblocks);
+    if (n) CK(cudaMemcpyAsync(h_dst, ctx->stage_in.p, n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (nblocks) CK(cudaMemcpyAsync(st.data(), ctx->stage_status.p, nblocks * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (h_status && nblocks) memcpy(h_status, st.data(), nblocks * 4);
+    return worst_status(st.data(), nblocks);
+}
+
+// ---------------------------------------------------------------------------------- generators
+
+static uint32_t build_lut(int kind, std::vector<uint8_t> &lut)
+{
+    static const uint8_t TEXT_RANKS[96] = {
+        0x20,0x65,0x74,0x61,0x6f,0x69,0x6e,0x73,0x68,0x72,0x64,0x6c,0x63,0x75,0x6d,0x77,
+        0x66,0x67,0x79,0x70,0x62,0x76,0x6b,0x6a,0x78,0x71,0x7a,0x45,0x54,0x41,0x4f,0x49,
+        0x4e,0x53,0x48,0x52,0x44,0x4c,0x43,0x55,0x4d,0x57,0x46,0x47,0x59,0x50,0x42,0x56,
+        0x4b,0x4a,0x58,0x51,0x5a,0x30,0x31,0x32,0x33,0x34,0x35,0x36,0x37,0x38,0x39,0x2e,
+        0x2c,0x3b,0x3a,0x27,0x22,0x21,0x3f,0x2d,0x28,0x29,0x0a,0x09,0x2f,0x26,0x25,0x24,
+        0x23,0x40,0x2a,0x2b,0x3c,0x3d,0x3e,0x5b,0x5d,0x5f,0x7b,0x7d,0x7c,0x7e,0x5e,0x60};
+    lut.clear();
+    if (kind == 0) {        // the crate's gen_sequence(0.2) LUT, src/lib.rs:255-270
+        size_t remaining = 4096;
+        uint8_t s = 0;
+        while (remaining > 0) {
+            size_t k = (size_t)((double)remaining * 0.2);
+            if (k < 1) k = 1;
+            lut.insert(lut.end(), k, s);
+            s++;
+            remaining -= k;
+        }
+    } else if (kind == 1) { // Zipf(1) over 96 printable bytes
+        uint64_t w[96], W = 0, cnt[96], used = 0;
+        for (int r = 0; r < 96; r++) { w[r] = (1ull << 20) / (uint64_t)(r + 1); W += w[r]; }
+        for (int r = 0; r < 96; r++) { cnt[r] = (65536ull * w[r]) / W; used += cnt[r]; }
+        cnt[0] += 65536 - used;
+        for (int r = 0; r < 96; r++) lut.insert(lut.end(), (size_t)cnt[r], TEXT_RANKS[r]);
+    } else if (kind == 2) { // four symbols, ~.90/.05/.03/.02
+        const unsigned c[4] = {3686, 205, 123, 82};
+        for (int s = 0; s < 4; s++) lut.insert(lut.end(), c[s], (uint8_t)s);
+    } else {
+        for (int i = 0; i < 256; i++) lut.push_back((uint8_t)i);
+    }
+    return (uint32_t)lut.size();
+}
+
+int fse_b200_generate(fse_b200_ctx *ctx, int kind, uint64_t seed, uint64_t first_index, uint8_t *d_dst, size_t n)
+{
+    if (!ctx || kind < 0 || kind > 3 || (!d_dst && n)) return fail(ctx, FSE_B200_ERR_ARG, "generate: bad argument");
+    CK(cudaSetDevice(ctx->device));
+    if (n == 0) return FSE_B200_OK;
+    if (!ctx->lut_len[kind]) {
+        std::vector<uint8_t> lut;
+        uint32_t len = build_lut(kind, lut);
+        CK(ctx->lut[kind].reserve(len));
+        CK(cudaMemcpy(ctx->lut[kind].p, lut.data(), len, cudaMemcpyHostToDevice));
+        ctx->lut_len[kind] = len;
+    }
+    k_generate<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(ctx->lut[kind].as<uint8_t>(), ctx->lut_len[kind] - 1, seed, first_index, d_dst, n);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    return FSE_B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,684 @@
+// fse_kernels.cuh -- the sm_100a kernels of the FSE path.  One warp per block / per table.
+#pragma once
+#include "fse_device.cuh"
+
+namespace fsed {
+
+// ------------------------------------------------------------------------------------------
+// Per-warp shared-memory slices
+// ------------------------------------------------------------------------------------------
+struct EncLayout {
+    uint32_t tab;    // uint16[size]      next-state table (also the posmap scratch of warp_spread)
+    uint32_t tt;     // uint2[256]        symbol transforms
+    uint32_t work;   // build: counts u32[256] | norm i32[256] | cum u32[256] | spread u8[size]
+                     // encode: fld u32[32*32]
+    uint32_t rows;   // uint32[32*17]     lane bit strings
+    uint32_t total;
+};
+__host__ __device__ inline EncLayout enc_layout(uint32_t tlmax)
+{
+    EncLayout l;
+    uint32_t size = 1u << tlmax;
+    l.tab = 0;
+    l.tt = l.tab + size * 2;
+    l.work = l.tt + 2048;
+    uint32_t build = 3072 + size, enc = 4096;
+    l.rows = l.work + (build > enc ? build : enc);
+    l.total = (l.rows + ROWS_WORDS * 4 + 15u) & ~15u;
+    return l;
+}
+
+struct DecLayout {
+    uint32_t tab;    // uint32[size]      decode entries (also the posmap scratch)
+    uint32_t norm;   // int32[256]
+    uint32_t ctr;    // uint32[256]       cum (unused output of warp_spread) then symbol_next
+    uint32_t spread; // uint8[size]
+    uint32_t total;
+};
+__host__ __device__ inline DecLayout dec_layout(uint32_t tlmax)
+{
+    DecLayout l;
+    uint32_t size = 1u << tlmax;
+    l.tab = 0;
+    l.norm = size * 4;
+    l.ctr = l.norm + 1024;
+    l.spread = l.ctr + 1024;
+    l.total = (l.spread + size + 15u) & ~15u;
+    return l;
+}
+
+// A table shared by every block (FSE_B200_TABLE_GLOBAL)
+struct GlobalTable {
+    uint32_t log2;
+    uint32_t table_len;
+    const uint16_t *enc_table;  // [1 << log2]
+    const uint2 *enc_tt;        // [256]
+    const uint32_t *dec_table;  // [1 << log2]
+};
+
+// ------------------------------------------------------------------------------------------
+// K1: Histogram::new per block (src/histogram.rs:18-66).  One CTA of 2 warps per block; every
+// lane owns a private column of 256 32-bit counters (bank == lane: no conflicts, no atomics);
+// four bytes are counted per step with the duplicate increments resolved in registers.
+// ------------------------------------------------------------------------------------------
+constexpr int HIST_WARPS = 2;
+constexpr int HIST_SMEM = HIST_WARPS * 256 * 32 * 4;
+
+__device__ __forceinline__ void hist_word(uint32_t *cnt, uint32_t w)
+{
+    uint32_t b0 = w & 0xff, b1 = (w >> 8) & 0xff, b2 = (w >> 16) & 0xff, b3 = w >> 24;
+    uint32_t c0 = cnt[b0 << 5], c1 = cnt[b1 << 5], c2 = cnt[b2 << 5], c3 = cnt[b3 << 5];
+    uint32_t i1 = (b1 == b0), i2 = (b2 == b0) + (b2 == b1), i3 = (b3 == b0) + (b3 == b1) + (b3 == b2);
+    cnt[b0 << 5] = c0 + 1;  // later stores win: program order is ascending multiplicity
+    cnt[b1 << 5] = c1 + 1 + i1;
+    cnt[b2 << 5] = c2 + 1 + i2;
+    cnt[b3 << 5] = c3 + 1 + i3;
+}
+
+__global__ void __launch_bounds__(HIST_WARPS * 32)
+k_hist_blocks(const uint8_t *__restrict__ src, size_t n, uint32_t block_size, uint32_t nblocks,
+              uint32_t *__restrict__ counts, uint32_t *__restrict__ table_len)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint32_t *cnt_all = reinterpret_cast<uint32_t *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t *cnt = cnt_all + warp * 8192 + lane;  // counter(bin) = cnt[bin << 5]
+    for (uint32_t b = blockIdx.x; b < nblocks; b += gridDim.x) {
+        for (int i = 0; i < 256; i++) cnt[i << 5] = 0;
+        const size_t off = (size_t)b * block_size;
+        const uint32_t bn = (uint32_t)min((size_t)block_size, n - off);
+        const uint8_t *p = src + off;
+        // bytes before the first 16-byte boundary and after the last one go one at a time
+        uint32_t head = (uint32_t)((16 - ((uintptr_t)p & 15)) & 15);
+        if (head > bn) head = bn;
+        uint32_t nvec = (bn - head) >> 4;
+        uint32_t tail0 = head + (nvec << 4);
+        if (tid < (int)head) cnt[(uint32_t)p[tid] << 5] += 1;
+        if (tail0 + tid < bn) cnt[(uint32_t)p[tail0 + tid] << 5] += 1;  // tail < 16 <= 64 threads
+        const uint4 *v = reinterpret_cast<const uint4 *>(p + head);
+        uint32_t i = tid;
+        for (; i + 3 * HIST_WARPS * 32 < nvec; i += 4 * HIST_WARPS * 32) {  // 4 loads in flight
+            uint4 x0 = __ldg(v + i), x1 = __ldg(v + i + HIST_WARPS * 32);
+            uint4 x2 = __ldg(v + i + 2 * HIST_WARPS * 32), x3 = __ldg(v + i + 3 * HIST_WARPS * 32);
+            hist_word(cnt, x0.x); hist_word(cnt, x0.y); hist_word(cnt, x0.z); hist_word(cnt, x0.w);
+            hist_word(cnt, x1.x); hist_word(cnt, x1.y); hist_word(cnt, x1.z); hist_word(cnt, x1.w);
+            hist_word(cnt, x2.x); hist_word(cnt, x2.y); hist_word(cnt, x2.z); hist_word(cnt, x2.w);
+            hist_word(cnt, x3.x); hist_word(cnt, x3.y); hist_word(cnt, x3.z); hist_word(cnt, x3.w);
+        }
+        for (; i < nvec; i += HIST_WARPS * 32) {
+            uint4 x = __ldg(v + i);
+            hist_word(cnt, x.x); hist_word(cnt, x.y); hist_word(cnt, x.z); hist_word(cnt, x.w);
+        }
+        __syncthreads();
+        // merge: thread t sums bins 4t..4t+3 over all 64 private columns (rotated => bank == lane)
+        uint32_t s[4] = {0, 0, 0, 0};
+        for (int w = 0; w < HIST_WARPS; w++)
+            for (int l = 0; l < 32; l++) {
+                int col = (l + tid) & 31;
+#pragma unroll
+                for (int q = 0; q < 4; q++) s[q] += cnt_all[w * 8192 + ((tid * 4 + q) << 5) + col];
+            }
+        *reinterpret_cast<uint4 *>(counts + (size_t)b * 256 + tid * 4) = make_uint4(s[0], s[1], s[2], s[3]);
+        if (table_len) {
+            int hi = -1;
+#pragma unroll
+            for (int q = 0; q < 4; q++) if (s[q]) hi = tid * 4 + q;
+#pragma unroll
+            for (int d = 16; d; d >>= 1) hi = max(hi, __shfl_xor_sync(FULL, hi, d));
+            __shared__ int hiw[HIST_WARPS];
+            if (lane == 0) hiw[warp] = hi;
+            __syncthreads();
+            if (tid == 0) {
+                int h = hiw[0];
+                for (int w = 1; w < HIST_WARPS; w++) h = max(h, hiw[w]);
+                table_len[b] = (uint32_t)(h < 0 ? 0 : h) + 1;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// sum of per-block histograms into uint64[256] (global-table mode)
+__global__ void k_hist_reduce(const uint32_t *__restrict__ counts, uint32_t nblocks, unsigned long long *out)
+{
+    uint32_t bin = threadIdx.x;  // 256 threads
+    unsigned long long s = 0;
+    for (uint32_t b = blockIdx.x; b < nblocks; b += gridDim.x) s += counts[(size_t)b * 256 + bin];
+    if (s) atomicAdd(out + bin, s);
+}
+
+// ------------------------------------------------------------------------------------------
+// K2-K4 fused: per block  normalise -> header -> encode table -> reverse-order N-state encode.
+// One warp per block; CTAs are just containers of independent warps.
+// Block scratch (stride bytes, 16-aligned): [0, HDR_RESERVE) header, [HDR_RESERVE, ...) payload words.
+// ------------------------------------------------------------------------------------------
+struct EncArgs {
+    const uint8_t *src;
+    size_t n;
+    uint32_t block_size, nblocks;
+    uint32_t req_log2, n_states, tlmax;
+    const uint32_t *counts;  // [nblocks*256] (per-block mode)
+    uint8_t *scratch;
+    size_t stride;
+    uint32_t pay_cap_words;
+    uint32_t *hlen, *plen;   // [nblocks] header / payload bytes
+    int32_t *status;
+    GlobalTable g;
+    int global_mode;
+};
+
+// fse.rs:210-218
+__device__ __forceinline__ uint32_t enc_first(const uint16_t *tab, const uint2 *tt, uint32_t sym)
+{
+    uint2 t = tt[sym];
+    uint32_t bo = (t.x + (1u << 15)) >> 16;
+    uint32_t value = (bo << 16) - t.x;
+    return tab[(int32_t)(value >> bo) + (int32_t)t.y];
+}
+
+__device__ void encode_payload_warp(const uint8_t *__restrict__ bsrc, uint32_t bn, uint32_t N, uint32_t log2,
+                                    const uint16_t *tab, const uint2 *tt, uint32_t *fld, uint32_t *rows,
+                                    uint32_t *pay, uint32_t cap_words, int lane, uint32_t &bits_out, bool &overflow)
+{
+    const bool act = (uint32_t)lane < N;
+    const uint32_t c = (bn - 1) & (N - 1);
+    const uint32_t kcol = act ? ((c - (uint32_t)lane) & (N - 1)) : (uint32_t)lane;  // stream position in a round
+    // swizzled field address: row r, 16-byte chunk (kcol>>2) ^ (r&7)
+    uint32_t state = 0;
+    int32_t i0 = (int32_t)bn - 1 - (int32_t)kcol;  // my highest symbol (costs no bits, lib.rs:123,155-165)
+    if (act) state = enc_first(tab, tt, __ldg(bsrc + i0));
+    i0 -= (int32_t)N;
+    const uint32_t G = (bn - N + N - 1) / N;  // rounds of N transitions
+    uint32_t cw = 0, cb = 0, wdone = 0;
+    uint32_t *myrow = rows + lane * ROW_STRIDE;
+    overflow = false;
+    for (uint32_t g0 = 0; g0 < G; g0 += 32) {
+        // pass 1: 32 rounds of the state transform (fse.rs:227-239); fields go to fld in stream order
+#pragma unroll 8
+        for (int r = 0; r < 32; r++) {
+            int32_t ii = i0 - (int32_t)((g0 + r) * N);
+            uint32_t f = 0;
+            if (act && ii >= 0) {
+                uint32_t sym = __ldg(bsrc + ii);
+                uint2 t = tt[sym];
+                uint32_t bo = (t.x + state) >> 16;
+                f = (state & ((1u << bo) - 1u)) | (bo << 16);
+                state = tab[(int32_t)(state >> bo) + (int32_t)t.y];
+            }
+            fld[r * 32 + ((((kcol >> 2) ^ (r & 7)) << 2) | (kcol & 3))] = f;
+        }
+        __syncwarp();
+        // pass 2: lane L serialises round L (32 consecutive fields of the stream)
+        BitRow br;
+        br.init(myrow, lane == 0 ? cw : 0u, lane == 0 ? cb : 0u);
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            uint4 x = *reinterpret_cast<const uint4 *>(fld + lane * 32 + ((q ^ (lane & 7)) << 2));
+            br.put(x.x & 0xffff, x.x >> 16);
+            br.put(x.y & 0xffff, x.y >> 16);
+            br.put(x.z & 0xffff, x.z >> 16);
+            br.put(x.w & 0xffff, x.w >> 16);
+        }
+        uint32_t tot = br.finish();
+        __syncwarp();
+        wdone += warp_place(myrow, tot, pay + wdone, cap_words - wdone, lane, cw, cb, overflow);
+        __syncwarp();
+    }
+    // final states N-1 .. 0 (fse.rs:248-250, order lib.rs:178-179), then the marker bit (lib.rs:141,181)
+    {
+        uint32_t st = __shfl_sync(FULL, state, (N - 1 - lane) & 31);
+        BitRow br;
+        br.init(myrow, lane == 0 ? cw : 0u, lane == 0 ? cb : 0u);
+        if (act) br.put(st & ((1u << log2) - 1u), log2);
+        if ((uint32_t)lane == N - 1) br.put(1, 1);
+        uint32_t tot = br.finish();
+        __syncwarp();
+        wdone += warp_place(myrow, tot, pay + wdone, cap_words - wdone, lane, cw, cb, overflow);
+        __syncwarp();
+    }
+    if (cb) {
+        if (wdone < cap_words) { if (lane == 0) pay[wdone] = cw; }
+        else overflow = true;
+    }
+    bits_out = wdone * 32 + cb;
+}
+
+__global__ void __launch_bounds__(512) k_encode_blocks(EncArgs a)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    const EncLayout lay = enc_layout(a.tlmax);
+    uint8_t *my = smem_raw + (size_t)warp * lay.total;
+    uint16_t *tab = reinterpret_cast<uint16_t *>(my + lay.tab);
+    uint2 *tt = reinterpret_cast<uint2 *>(my + lay.tt);
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(my + lay.work);
+    int32_t *norm = reinterpret_cast<int32_t *>(my + lay.work + 1024);
+    uint32_t *cum = reinterpret_cast<uint32_t *>(my + lay.work + 2048);
+    uint8_t *spread = my + lay.work + 3072;
+    uint32_t *fld = reinterpret_cast<uint32_t *>(my + lay.work);
+    uint32_t *rows = reinterpret_cast<uint32_t *>(my + lay.rows);
+    const uint32_t N = a.n_states;
+
+    uint32_t glog2 = 0;
+    if (a.global_mode) {  // the shared table is loaded once per warp
+        glog2 = a.g.log2;
+        for (uint32_t i = lane; i < (1u << glog2); i += 32) tab[i] = a.g.enc_table[i];
+        for (uint32_t i = lane; i < 256; i += 32) tt[i] = a.g.enc_tt[i];
+        __syncwarp();
+    }
+
+    for (uint32_t b = blockIdx.x * wpc + warp; b < a.nblocks; b += gridDim.x * wpc) {
+        const size_t off = (size_t)b * a.block_size;
+        const uint32_t bn = (uint32_t)min((size_t)a.block_size, a.n - off);
+        const uint8_t *bsrc = a.src + off;
+        uint8_t *bs = a.scratch + (size_t)b * a.stride;
+        uint32_t *hdr_words = reinterpret_cast<uint32_t *>(bs);
+        uint32_t *pay = reinterpret_cast<uint32_t *>(bs + HDR_RESERVE);
+        uint32_t log2 = glog2, hbytes = 0;
+        int st = ST_OK;
+
+        if (!a.global_mode) {
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 8; k++) cnt[k * 32 + lane] = a.counts[(size_t)b * 256 + k * 32 + lane];
+            __syncwarp();
+            uint32_t table_len;
+            int rc = warp_normalize(cnt, (uint64_t)bn, a.req_log2, norm, lane, log2, table_len);
+            if (rc < 0) {
+                // blocks the reference panics on: stored with an escape byte (include/fse_b200.h)
+                if (table_len <= 1) {            // all bytes zero: histogram.rs:98
+                    if (lane == 0) { bs[0] = 0x0E; bs[1] = 0x00; a.hlen[b] = 2; a.plen[b] = 0; a.status[b] = 2; }
+                } else if (bn <= 4) {            // histogram.rs:271
+                    if (lane == 0) {
+                        bs[0] = 0x0F;
+                        for (uint32_t i = 0; i < bn; i++) bs[1 + i] = bsrc[i];
+                        a.hlen[b] = 1 + bn; a.plen[b] = 0; a.status[b] = 1;
+                    }
+                } else if (lane == 0) { a.hlen[b] = 0; a.plen[b] = 0; a.status[b] = rc; }
+                continue;
+            }
+            if (bn < N) {                        // fewer symbols than states: lib.rs:121,154,156
+                if ((uint32_t)lane < bn) bs[1 + lane] = bsrc[lane];
+                if (lane == 0) { bs[0] = 0x0F; a.hlen[b] = 1 + bn; a.plen[b] = 0; a.status[b] = 1; }
+                continue;
+            }
+            if (log2 > a.tlmax) {
+                if (lane == 0) { a.hlen[b] = 0; a.plen[b] = 0; a.status[b] = ST_UNSUPPORTED; }
+                continue;
+            }
+            uint32_t hbits = warp_ncount_write(norm, log2, table_len, rows, hdr_words, lane);
+            hbytes = (hbits + 7) >> 3;
+            warp_spread(norm, log2, table_len, spread, cum, tab, lane);
+            warp_build_encode(norm, log2, table_len, spread, cum, tab, tt, lane);
+        } else if (bn < N) {                     // global mode: a short tail is stored raw, no escape
+            if ((uint32_t)lane < bn) bs[lane] = bsrc[lane];
+            if (lane == 0) { a.hlen[b] = bn; a.plen[b] = 0; a.status[b] = 1; }
+            continue;
+        }
+        uint32_t pbits;
+        bool ovf;
+        encode_payload_warp(bsrc, bn, N, log2, tab, tt, fld, rows, pay, a.pay_cap_words, lane, pbits, ovf);
+        if (ovf) st = ST_CAPACITY;
+        if (lane == 0) {
+            a.hlen[b] = ovf ? 0 : hbytes;
+            a.plen[b] = ovf ? 0 : (pbits + 7) >> 3;
+            a.status[b] = st;
+        }
+    }
+}
+
+// exclusive scan of block sizes -> uint64 offsets[nblocks+1]; single CTA of 1024 threads
+__global__ void __launch_bounds__(1024) k_scan_sizes(const uint32_t *__restrict__ hlen, const uint32_t *__restrict__ plen,
+                                                      uint32_t nblocks, unsigned long long *offsets)
+{
+    __shared__ unsigned long long wsum[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t per = (nblocks + 1023) / 1024;
+    const uint32_t b0 = tid * per, b1 = min(nblocks, b0 + per);
+    unsigned long long s = 0;
+    for (uint32_t b = b0; b < b1; b++) s += (unsigned long long)hlen[b] + plen[b];
+    unsigned long long incl = warp_incl_add(s, lane);
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long w = wsum[lane];
+        unsigned long long wi = warp_incl_add(w, lane);
+        wsum[lane] = wi - w;
+    }
+    __syncthreads();
+    unsigned long long run = wsum[warp] + incl - s;
+    for (uint32_t b = b0; b < b1; b++) { offsets[b] = run; run += (unsigned long long)hlen[b] + plen[b]; }
+    if (nblocks == 0 ? tid == 0 : (b0 < b1 && b1 == nblocks)) offsets[nblocks] = run;
+}
+
+// byte copy with 4-byte aligned destination stores and funnel-shifted source words
+__device__ __forceinline__ void block_copy_bytes(uint8_t *dst, const uint8_t *src /*4-aligned*/, uint32_t len, int tid, int nthr)
+{
+    uint32_t head = (uint32_t)((4 - ((uintptr_t)dst & 3)) & 3);
+    if (head > len) head = len;
+    if (tid < (int)head) dst[tid] = src[tid];
+    uint32_t nwords = (len - head) >> 2;
+    const uint32_t *sw = reinterpret_cast<const uint32_t *>(src);  // word k of dst body = src bytes head+4k..
+    uint32_t *dw = reinterpret_cast<uint32_t *>(dst + head);
+    uint32_t sh = head * 8;
+    for (uint32_t k = tid; k < nwords; k += nthr) {
+        uint32_t w0 = sw[k], w1 = sh ? sw[k + 1] : 0u;
+        dw[k] = __funnelshift_r(w0, w1, sh);
+    }
+    uint32_t t0 = head + (nwords << 2);
+    if (t0 + tid < len) dst[t0 + tid] = src[t0 + tid];
+}
+
+// K6: gather header || payload of every block to its scanned offset
+__global__ void __launch_bounds__(256) k_gather(const uint8_t *__restrict__ scratch, size_t stride,
+                                                 const uint32_t *__restrict__ hlen, const uint32_t *__restrict__ plen,
+                                                 const unsigned long long *__restrict__ offsets, uint32_t nblocks,
+                                                 uint8_t *__restrict__ dst)
+{
+    for (uint32_t b = blockIdx.x; b < nblocks; b += gridDim.x) {
+        const uint8_t *bs = scratch + (size_t)b * stride;
+        uint8_t *d = dst + offsets[b];
+        uint32_t h = hlen[b], p = plen[b];
+        block_copy_bytes(d, bs, h, threadIdx.x, blockDim.x);
+        block_copy_bytes(d + h, bs + HDR_RESERVE, p, threadIdx.x, blockDim.x);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K5: per block  header parse -> decode table -> stack-order N-state decode, length driven.
+// ------------------------------------------------------------------------------------------
+struct DecArgs {
+    const uint8_t *comp;
+    size_t comp_bytes;
+    const unsigned long long *offsets;
+    uint32_t nblocks, block_size;
+    size_t n;
+    uint32_t n_states, tlmax;
+    uint8_t *dst;
+    int32_t *status;
+    GlobalTable g;
+    int global_mode;
+    // exhaust mode (the reference's own termination rule, src/lib.rs:198,228: decode until the bit
+    // stack cannot supply num_bits): block b may produce up to block_size bytes, out_len[b] = produced
+    int exhaust;
+    uint32_t *out_len;
+};
+
+// value of stream bits [bitpos, bitpos+nb) of the bytes at `base` (nb <= 16); never loads a word
+// that starts at or after wend
+__device__ __forceinline__ uint32_t read_bits(const uint8_t *base, uint32_t bitpos, uint32_t nb, const uint32_t *wend)
+{
+    uintptr_t a = (uintptr_t)(base + (bitpos >> 3));
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+    uint32_t sh = (uint32_t)((a & 3) << 3) + (bitpos & 7);
+    uint32_t w0 = __ldg(w);
+    uint32_t w1 = (w + 1 < wend) ? __ldg(w + 1) : 0u;
+    return __funnelshift_r(w0, w1, sh) & ((1u << nb) - 1u);
+}
+
+__global__ void __launch_bounds__(512) k_decode_blocks(DecArgs a)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    const DecLayout lay = dec_layout(a.tlmax);
+    uint8_t *my = smem_raw + (size_t)warp * lay.total;
+    uint32_t *tab = reinterpret_cast<uint32_t *>(my + lay.tab);
+    int32_t *norm = reinterpret_cast<int32_t *>(my + lay.norm);
+    uint32_t *ctr = reinterpret_cast<uint32_t *>(my + lay.ctr);
+    uint8_t *spread = my + lay.spread;
+    const uint32_t N = a.n_states;
+    const uint32_t *wend = reinterpret_cast<const uint32_t *>(((uintptr_t)(a.comp + a.comp_bytes) + 3) & ~(uintptr_t)3);
+
+    uint32_t glog2 = 0;
+    if (a.global_mode) {
+        glog2 = a.g.log2;
+        for (uint32_t i = lane; i < (1u << glog2); i += 32) tab[i] = a.g.dec_table[i];
+        __syncwarp();
+    }
+
+    for (uint32_t b = blockIdx.x * wpc + warp; b < a.nblocks; b += gridDim.x * wpc) {
+        const size_t off = (size_t)b * a.block_size;
+        const uint32_t bn = (uint32_t)min((size_t)a.block_size, a.n - off);
+        uint8_t *out = a.dst + off;
+        const unsigned long long o0 = a.offsets[b], o1 = a.offsets[b + 1];
+        int st = ST_OK;
+        if (o1 < o0 || o1 > a.comp_bytes || o1 - o0 > 0xffffffffull) {
+            if (lane == 0) a.status[b] = ST_LENGTH;
+            continue;
+        }
+        const uint8_t *cs = a.comp + o0;
+        const uint32_t clen = (uint32_t)(o1 - o0);
+        uint32_t log2 = glog2, consumed = 0;
+        __syncwarp();
+        if (!a.global_mode) {
+            if (clen == 0) { if (lane == 0) a.status[b] = ST_PANIC; continue; }   // stream_reader.rs:17
+            uint32_t first = cs[0];
+            if (a.exhaust && (first & 0x0f) > 10) {   // TableLogTooLarge -> None, histogram.rs:439-441, lib.rs:191,219
+                if (lane == 0) { a.status[b] = ST_TABLE_LOG; a.out_len[b] = 0; }
+                continue;
+            }
+            if ((first & 0x0f) == 0x0f) {        // raw escape
+                if (clen != 1 + bn) { if (lane == 0) a.status[b] = ST_LENGTH; continue; }
+                for (uint32_t i = lane; i < bn; i += 32) out[i] = cs[1 + i];
+                if (lane == 0) a.status[b] = 1;
+                continue;
+            }
+            if ((first & 0x0f) == 0x0e) {        // run escape
+                if (clen != 2) { if (lane == 0) a.status[b] = ST_LENGTH; continue; }
+                uint8_t v = cs[1];
+                for (uint32_t i = lane; i < bn; i += 32) out[i] = v;
+                if (lane == 0) a.status[b] = 2;
+                continue;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) norm[k * 32 + lane] = 0;
+            __syncwarp();
+            uint32_t table_len = 0;
+            int rc = 0;
+            if (lane == 0) rc = ncount_read_serial(cs, clen, norm, log2, table_len, consumed);
+            rc = __shfl_sync(FULL, rc, 0);
+            log2 = __shfl_sync(FULL, log2, 0);
+            table_len = __shfl_sync(FULL, table_len, 0);
+            consumed = __shfl_sync(FULL, consumed, 0);
+            __syncwarp();
+            if (rc < 0) { if (lane == 0) a.status[b] = rc; continue; }
+            if (log2 > a.tlmax) { if (lane == 0) a.status[b] = ST_UNSUPPORTED; continue; }
+            warp_spread(norm, log2, table_len, spread, ctr, reinterpret_cast<uint16_t *>(tab), lane);
+            warp_build_decode(norm, log2, table_len, spread, ctr, tab, lane);
+        } else if (bn < N) {
+            if (clen != bn) { if (lane == 0) a.status[b] = ST_LENGTH; continue; }
+            if ((uint32_t)lane < bn) out[lane] = cs[lane];
+            if (lane == 0) a.status[b] = 1;
+            continue;
+        }
+        if (bn < N) { if (lane == 0) a.status[b] = ST_LENGTH; continue; }
+        // BitStackReader::new, stack_reader.rs:17-92: the highest set bit of the last byte is the marker
+        const uint8_t *pay = cs + consumed;
+        const uint32_t plen = clen - consumed;
+        if (plen == 0 || pay[plen - 1] == 0) { if (lane == 0) a.status[b] = ST_NO_MARKER; continue; }
+        uint32_t cur = (plen - 1) * 8 + ilog2u(pay[plen - 1]);
+        if (cur < N * log2) { if (lane == 0) a.status[b] = ST_LENGTH; continue; }   // lib.rs:197,224-225
+        const bool act = (uint32_t)lane < N;
+        // Decoder::new, fse.rs:349-352: state 0 is read first (it was written last)
+        uint32_t state = act ? read_bits(pay, cur - (lane + 1) * log2, log2, wend) : 0u;
+        cur -= N * log2;
+        const uint32_t body = bn - N;   // exhaust mode: bn == capacity
+        bool bad = false;
+        uint32_t stop_i = body, stop_lane = body & (N - 1);
+        for (uint32_t i0 = 0;; i0 += N) {
+            if (i0 >= body) {
+                if (a.exhaust) bad = true;                 // ran past the capacity (quirk Q1)
+                break;
+            }
+            uint32_t i = i0 + lane;
+            bool on = act && i < body;
+            uint32_t e = tab[state];                       // fse.rs:363-373
+            uint32_t nb = on ? (e >> 24) : 0u;
+            uint32_t incl = warp_incl_add(nb, lane);
+            uint32_t tot = __shfl_sync(FULL, incl, 31);
+            if (tot > cur) {                               // the stack cannot supply this round
+                if (!a.exhaust) { bad = true; break; }
+                // reference rule: the first decoder that gets None stops the loop (lib.rs:198,228-241)
+                uint32_t okm = __ballot_sync(FULL, on && incl <= cur);
+                uint32_t s = __popc(okm);                  // lanes [0, s) still decode
+                if (on && (uint32_t)lane < s) {
+                    uint32_t bits = read_bits(pay, cur - incl, nb, wend);
+                    out[i] = (uint8_t)(e >> 16);
+                    state = (e & 0xffffu) + bits;
+                }
+                uint32_t used = s ? __shfl_sync(FULL, incl, (s - 1) & 31) : 0u;
+                cur -= used;
+                if (i0 + s >= body) bad = true;            // would not fit the capacity
+                stop_i = i0 + s;
+                stop_lane = s & (N - 1);
+                break;
+            }
+            if (on) {
+                uint32_t bits = read_bits(pay, cur - incl, nb, wend);
+                out[i] = (uint8_t)(e >> 16);
+                state = (e & 0xffffu) + bits;
+            }
+            cur -= tot;
+        }
+        if (!bad && act) {                                 // Decoder::finish, fse.rs:383-385 (order lib.rs:236-243)
+            uint32_t i = stop_i + ((lane - stop_lane) & (N - 1));
+            out[i] = (uint8_t)(tab[state] >> 16);
+        }
+        if (a.exhaust) {
+            if (lane == 0) { a.out_len[b] = bad ? 0 : stop_i + N; a.status[b] = bad ? ST_CAPACITY : ST_OK; }
+            continue;
+        }
+        if (bad || cur != 0) st = ST_LENGTH;
+        if (lane == 0) a.status[b] = st;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Stage kernels (one warp per table) behind the stage entry points of the C ABI
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) k_normalize(const unsigned long long *__restrict__ counts64, uint32_t ntables,
+                                                   uint32_t req_log2, int32_t *norm_out, uint32_t *log2_out,
+                                                   uint32_t *table_len_out, int32_t *status)
+{
+    __shared__ int32_t norm[256];
+    const int lane = threadIdx.x;
+    for (uint32_t t = blockIdx.x; t < ntables; t += gridDim.x) {
+        const unsigned long long *c = counts64 + (size_t)t * 256;
+        unsigned long long s = 0;
+        for (int k = 0; k < 8; k++) s += c[lane * 8 + k];
+#pragma unroll
+        for (int d = 16; d; d >>= 1) s += __shfl_xor_sync(FULL, s, d);
+        uint32_t log2 = 0, table_len = 0;
+        __syncwarp();
+        int rc = warp_normalize(c, (uint64_t)s, req_log2, norm, lane, log2, table_len);
+        for (int k = 0; k < 8; k++) norm_out[(size_t)t * 256 + lane * 8 + k] = rc < 0 ? 0 : norm[lane * 8 + k];
+        if (lane == 0) { log2_out[t] = log2; table_len_out[t] = table_len; status[t] = rc; }
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(32) k_ncount_write(const int32_t *__restrict__ norm_in, const uint32_t *__restrict__ log2,
+                                                      const uint32_t *__restrict__ table_len, uint32_t ntables,
+                                                      uint8_t *out, size_t stride, uint32_t *bytes, uint32_t *bits)
+{
+    __shared__ int32_t norm[256];
+    __shared__ uint32_t rows[ROWS_WORDS];
+    __shared__ __align__(16) uint32_t hdr[HDR_RESERVE / 4];
+    const int lane = threadIdx.x;
+    for (uint32_t t = blockIdx.x; t < ntables; t += gridDim.x) {
+        for (int k = 0; k < 8; k++) norm[k * 32 + lane] = norm_in[(size_t)t * 256 + k * 32 + lane];
+        __syncwarp();
+        uint32_t hb = warp_ncount_write(norm, log2[t], table_len[t], rows, hdr, lane);
+        uint32_t nbytes = (hb + 7) >> 3;
+        __syncwarp();
+        const uint8_t *h8 = reinterpret_cast<const uint8_t *>(hdr);
+        for (uint32_t i = lane; i < nbytes && i < stride; i += 32) out[(size_t)t * stride + i] = h8[i];
+        if (lane == 0) { bytes[t] = nbytes; bits[t] = hb; }
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(32) k_ncount_read(const uint8_t *__restrict__ in, size_t stride, const uint32_t *__restrict__ len,
+                                                     uint32_t ntables, int32_t *norm_out, uint32_t *log2_out,
+                                                     uint32_t *table_len_out, uint32_t *consumed_out, int32_t *status)
+{
+    __shared__ int32_t norm[256];
+    const int lane = threadIdx.x;
+    for (uint32_t t = blockIdx.x; t < ntables; t += gridDim.x) {
+        for (int k = 0; k < 8; k++) norm[k * 32 + lane] = 0;
+        __syncwarp();
+        uint32_t log2 = 0, table_len = 0, consumed = 0;
+        int rc = 0;
+        if (lane == 0) rc = ncount_read_serial(in + (size_t)t * stride, len[t], norm, log2, table_len, consumed);
+        __syncwarp();
+        for (int k = 0; k < 8; k++) norm_out[(size_t)t * 256 + k * 32 + lane] = norm[k * 32 + lane];
+        if (lane == 0) { log2_out[t] = log2; table_len_out[t] = table_len; consumed_out[t] = consumed; status[t] = rc; }
+        __syncwarp();
+    }
+}
+
+// dynamic smem: norm i32[256] | cum u32[256] | spread u8[size] | table (u16 or u32)[size] | tt uint2[256]
+__global__ void __launch_bounds__(32) k_build_tables(const int32_t *__restrict__ norm_in, const uint32_t *__restrict__ log2_in,
+                                                      const uint32_t *__restrict__ table_len_in, uint32_t ntables,
+                                                      uint32_t max_log2, int decode, uint16_t *enc_table, uint2 *enc_tt,
+                                                      uint8_t *symbols, uint32_t *dec_table, int32_t *status)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const uint32_t msize = 1u << max_log2;
+    int32_t *norm = reinterpret_cast<int32_t *>(smem_raw);
+    uint32_t *cum = reinterpret_cast<uint32_t *>(smem_raw + 1024);
+    uint2 *tt = reinterpret_cast<uint2 *>(smem_raw + 2048);
+    uint32_t *table32 = reinterpret_cast<uint32_t *>(smem_raw + 4096);
+    uint16_t *table16 = reinterpret_cast<uint16_t *>(smem_raw + 4096);
+    uint8_t *spread = smem_raw + 4096 + (size_t)msize * 4;
+    const int lane = threadIdx.x;
+    for (uint32_t t = blockIdx.x; t < ntables; t += gridDim.x) {
+        const uint32_t log2 = log2_in[t], table_len = table_len_in[t];
+        if (log2 < TL_MIN || log2 > max_log2 || table_len == 0 || table_len > 256) {
+            if (lane == 0) status[t] = log2 > max_log2 ? ST_UNSUPPORTED : ST_PANIC;
+            continue;
+        }
+        const uint32_t size = 1u << log2;
+        for (int k = 0; k < 8; k++) norm[k * 32 + lane] = norm_in[(size_t)t * 256 + k * 32 + lane];
+        __syncwarp();
+        warp_spread(norm, log2, table_len, spread, cum, table16, lane);
+        if (!decode) {
+            warp_build_encode(norm, log2, table_len, spread, cum, table16, tt, lane);
+            for (uint32_t i = lane; i < size; i += 32) enc_table[(size_t)t * msize + i] = table16[i];
+            for (uint32_t i = lane; i < 256; i += 32) enc_tt[(size_t)t * 256 + i] = tt[i];
+            if (symbols) for (uint32_t i = lane; i < size; i += 32) symbols[(size_t)t * msize + i] = spread[i];
+        } else {
+            warp_build_decode(norm, log2, table_len, spread, cum, table32, lane);
+            for (uint32_t i = lane; i < size; i += 32) dec_table[(size_t)t * msize + i] = table32[i];
+        }
+        if (lane == 0) status[t] = 0;
+        __syncwarp();
+    }
+}
+
+// widen uint32 counts to uint64 (stage API / global table plumbing)
+__global__ void k_widen_counts(const uint32_t *__restrict__ in, unsigned long long *out, size_t count)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) out[i] = in[i];
+}
+
+// synthetic generators of SURVEY.md 8(d): byte i = LUT[r16(seed, i) & (lut_len-1)]
+__global__ void k_generate(const uint8_t *__restrict__ lut, uint32_t lut_mask, uint64_t seed, uint64_t first_index,
+                           uint8_t *__restrict__ dst, size_t n)
+{
+    // one thread per group of four bytes that share one splitmix64 draw
+    size_t q0 = first_index >> 2;
+    size_t nq = ((first_index + n + 3) >> 2) - q0;
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (size_t)gridDim.x * blockDim.x) {
+        uint64_t z = splitmix64(seed + q0 + q);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            uint64_t i = ((q0 + q) << 2) + k;
+            if (i >= first_index && i < first_index + n)
+                dst[i - first_index] = lut[(uint32_t)((z >> (16 * k)) & 0xFFFF) & lut_mask];
+        }
+    }
+}
+
+}  // namespace fsed

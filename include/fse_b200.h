@@ -1,0 +1,223 @@
+/*
+ * fse_b200.h -- C ABI of libfse_b200.so: a B200 (sm_100a) implementation of the FSE / tANS hot
+ * path of the Rust crate Cognoscan/entropy_coders.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++ or torch types.  Every entry
+ * point names the reference interface it replaces (paths relative to the crate root).  The Rust
+ * side binds these with `extern "C"` (see INTEGRATION.md and rust/); in this repository the same
+ * symbols are bound from Python with ctypes (entropy_coders_b200/_capi.py).
+ *
+ * The library has no CPU fallback: every call needs a CUDA device and fails with
+ * FSE_B200_ERR_CUDA otherwise.
+ *
+ * Conventions
+ *  - "d_" pointers are device pointers on the context's device, "h_" pointers are host pointers.
+ *  - All functions return FSE_B200_OK (0) or a negative fse_b200_status.  Nothing throws or aborts.
+ *  - Entry points are synchronous (they return after the context's stream has drained) unless
+ *    the name ends in _async.
+ *  - A context is single-owner: one host thread at a time.  Distinct contexts are independent.
+ *
+ * Block streams
+ *  The reference codes ONE slice into ONE stream (src/lib.rs:112-183).  This library cuts the
+ *  input into independent blocks of `block_size` bytes (last block may be shorter); block b's bytes
+ *  are exactly what the reference emits when handed that block as `src`:
+ *      [ NCount header (src/histogram.rs:376-431) ][ payload (src/lib.rs:118-142 / :151-182) ]
+ *  with `n_states` interleaved encoder states (1 = fse_compress, 2 = fse_compress2; wider N is the
+ *  same composition of fse::Encoder the crate documents at src/fse.rs:16-17: state j owns the
+ *  symbols whose index is j modulo N, symbols are consumed in decreasing index order, final states
+ *  are written N-1..0, then the marker bit).  The compressed blocks are concatenated densely;
+ *  offsets[b]..offsets[b+1] delimit block b.
+ *  Blocks on which the reference panics (all bytes zero: src/histogram.rs:98; fewer symbols than
+ *  states or <= 4 bytes with automatic table_log: src/lib.rs:121,154, src/histogram.rs:271) are
+ *  stored with an escape byte that no valid header can start with (low nibble > 10 means
+ *  table_log > 15, rejected at src/histogram.rs:439-441):  0x0F = raw bytes follow,
+ *  0x0E = one byte follows, repeated.  status[b] reports 1 / 2 for those.
+ */
+#ifndef FSE_B200_H
+#define FSE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FSE_B200_TABLE_LOG_MIN 5      /* src/lib.rs:9  */
+#define FSE_B200_TABLE_LOG_MAX 15     /* src/lib.rs:10 */
+#define FSE_B200_TABLE_LOG_DEFAULT 11 /* src/lib.rs:12 */
+
+typedef enum {
+    FSE_B200_OK = 0,
+    FSE_B200_ERR_ARG = -1,          /* bad argument (null pointer, block_size 0, n_states not supported ...) */
+    FSE_B200_ERR_CAPACITY = -2,     /* caller buffer too small */
+    FSE_B200_ERR_TABLE_LOG = -3,    /* HistError::TableLogTooLarge  src/histogram.rs:439-441 */
+    FSE_B200_ERR_TOO_MANY = -4,     /* HistError::TooManySymbols    src/histogram.rs:498-500 */
+    FSE_B200_ERR_IO = -5,           /* HistError::Io (header ran out of bits) src/bitstream/stream_reader.rs:70-72 */
+    FSE_B200_ERR_NO_MARKER = -6,    /* BitStackReader::new -> None  src/bitstream/stack_reader.rs:18-20,77-83 */
+    FSE_B200_ERR_LENGTH = -7,       /* payload bits do not match the block length / fewer than N*table_log bits (src/lib.rs:197,224) */
+    FSE_B200_ERR_PANIC = -8,        /* the reference would panic on this input (e.g. src/histogram.rs:248,420) */
+    FSE_B200_ERR_UNSUPPORTED = -9,  /* table_log above the limit this launch was sized for */
+    FSE_B200_ERR_CUDA = -10,        /* CUDA runtime error; see fse_b200_last_error() */
+    FSE_B200_ERR_BLOCK = -11        /* at least one block failed; inspect status[] */
+} fse_b200_status;
+
+/* per-block status values >= 0 */
+#define FSE_B200_BLOCK_FSE 0
+#define FSE_B200_BLOCK_RAW 1
+#define FSE_B200_BLOCK_RLE 2
+
+#define FSE_B200_TABLE_PER_BLOCK 0
+#define FSE_B200_TABLE_GLOBAL 1
+
+typedef struct {
+    uint32_t block_size;  /* bytes per block (> 0) */
+    uint32_t table_log;   /* 0 = Histogram::optimal_log2 per table (src/histogram.rs:264-277); else the
+                             value handed to Histogram::normalize (src/histogram.rs:95), 5..15 */
+    uint32_t n_states;    /* interleaved states per block: 1, 2, 4, 8, 16 or 32 */
+    uint32_t table_mode;  /* FSE_B200_TABLE_PER_BLOCK or FSE_B200_TABLE_GLOBAL */
+} fse_b200_params;
+
+/* src/fse.rs:80-84 SymbolTransform */
+typedef struct { uint32_t bits; int32_t find_state; } fse_b200_symbol_transform;
+/* src/fse.rs:260-265 DecodeTransform */
+typedef struct { uint16_t new_state; uint8_t symbol; uint8_t num_bits; } fse_b200_decode_transform;
+
+typedef struct fse_b200_ctx fse_b200_ctx;
+
+/* ---- context ------------------------------------------------------------------------------- */
+/* stream: a cudaStream_t (or NULL for a context-owned stream).  The context owns device
+ * workspaces that grow on demand and are reused across calls (the analogue of
+ * EncodeTable::update / DecodeTable::update reusing their Vecs, src/fse.rs:101,280). */
+int fse_b200_create(int device, void *stream, fse_b200_ctx **out);
+void fse_b200_destroy(fse_b200_ctx *ctx);
+const char *fse_b200_last_error(const fse_b200_ctx *ctx);
+const char *fse_b200_version(void);
+/* number of kernels launched by this context so far (bench.py's gpu_launches) */
+uint64_t fse_b200_launch_count(const fse_b200_ctx *ctx);
+int fse_b200_sync(fse_b200_ctx *ctx);
+
+/* Per-kernel device timing of the fused pipelines (CUDA events on the context's stream around each
+ * launch).  set_timing(1) starts a fresh measurement; get_timing synchronises and returns the summed
+ * milliseconds and launch counts per kernel, indexed by the FSE_B200_K_* constants. */
+#define FSE_B200_K_HIST 0     /* k_hist_blocks   */
+#define FSE_B200_K_ENCODE 1   /* k_encode_blocks */
+#define FSE_B200_K_SCAN 2     /* k_scan_sizes    */
+#define FSE_B200_K_GATHER 3   /* k_gather        */
+#define FSE_B200_K_DECODE 4   /* k_decode_blocks */
+#define FSE_B200_NUM_KERNELS 5
+int fse_b200_set_timing(fse_b200_ctx *ctx, int enable);
+int fse_b200_get_timing(fse_b200_ctx *ctx, double *ms_total, uint64_t *count);
+
+/* ---- sizing -------------------------------------------------------------------------------- */
+/* EncodeTable::compress_bound, src/fse.rs:191-193 */
+size_t fse_b200_compress_bound(size_t size);
+/* worst-case bytes of the dense output of fse_b200_compress_blocks for n input bytes */
+size_t fse_b200_compress_blocks_bound(size_t n, const fse_b200_params *p);
+size_t fse_b200_num_blocks(size_t n, uint32_t block_size);
+
+/* ---- stage entry points (device pointers) --------------------------------------------------- */
+/* Histogram::new per block, src/histogram.rs:18-66.
+ * d_counts: uint32[nblocks*256]; d_table_len: uint32[nblocks] (highest present symbol + 1, :52-59). */
+int fse_b200_histogram_blocks(fse_b200_ctx *ctx, const uint8_t *d_src, size_t n, uint32_t block_size,
+                              uint32_t *d_counts, uint32_t *d_table_len);
+/* Whole-buffer histogram accumulated in 64 bit (the multi-GPU global table sums these with an
+ * all-reduce).  d_counts64: uint64[256], overwritten. */
+int fse_b200_histogram_global(fse_b200_ctx *ctx, const uint8_t *d_src, size_t n, uint64_t *d_counts64);
+
+/* Histogram::optimal_log2 + Histogram::normalize (+ normalize_slow), src/histogram.rs:95-277, for
+ * `ntables` histograms.  d_counts64: uint64[ntables*256].  table_log 0 = optimal_log2.
+ * Outputs: d_norm int32[ntables*256]; d_log2 uint32[ntables] (effective, may be raised: :96-98);
+ * d_table_len uint32[ntables]; d_status int32[ntables] (0, 1 = normalize_slow taken, <0 error). */
+int fse_b200_normalize(fse_b200_ctx *ctx, const uint64_t *d_counts64, size_t ntables, uint32_t table_log,
+                       int32_t *d_norm, uint32_t *d_log2, uint32_t *d_table_len, int32_t *d_status);
+
+/* NormHistogram::write, src/histogram.rs:376-431.  d_out: ntables rows of `stride` bytes;
+ * d_bytes / d_bits: uint32[ntables] (bytes appended / header bits, the latter is write()'s return). */
+int fse_b200_ncount_write(fse_b200_ctx *ctx, const int32_t *d_norm, const uint32_t *d_log2,
+                          const uint32_t *d_table_len, size_t ntables,
+                          uint8_t *d_out, size_t stride, uint32_t *d_bytes, uint32_t *d_bits);
+/* NormHistogram::read, src/histogram.rs:436-505.  d_in rows of `stride` bytes with d_len[t] valid.
+ * d_consumed: byte offset of the remainder (finish_byte, src/bitstream/stream_reader.rs:132-135). */
+int fse_b200_ncount_read(fse_b200_ctx *ctx, const uint8_t *d_in, size_t stride, const uint32_t *d_len,
+                         size_t ntables, int32_t *d_norm, uint32_t *d_log2, uint32_t *d_table_len,
+                         uint32_t *d_consumed, int32_t *d_status);
+
+/* EncodeTable::new / update, src/fse.rs:88-189.  max_table_log sizes the rows: row t of
+ * d_table has 1<<max_table_log uint16 entries (first 1<<log2[t] valid); d_symbol_tt: [ntables*256];
+ * d_symbols (the spread, src/fse.rs:139-151): uint8 rows of 1<<max_table_log, may be NULL. */
+int fse_b200_build_encode_tables(fse_b200_ctx *ctx, const int32_t *d_norm, const uint32_t *d_log2,
+                                 const uint32_t *d_table_len, size_t ntables, uint32_t max_table_log,
+                                 uint16_t *d_table, fse_b200_symbol_transform *d_symbol_tt,
+                                 uint8_t *d_symbols, int32_t *d_status);
+/* DecodeTable::new / update, src/fse.rs:269-338. */
+int fse_b200_build_decode_tables(fse_b200_ctx *ctx, const int32_t *d_norm, const uint32_t *d_log2,
+                                 const uint32_t *d_table_len, size_t ntables, uint32_t max_table_log,
+                                 fse_b200_decode_transform *d_table, int32_t *d_status);
+
+/* ---- fused pipelines (device pointers) ------------------------------------------------------ */
+/* fse_compress / fse_compress2 per block, src/lib.rs:112-183 (histogram + normalise + header +
+ * encode table + encode), then an exclusive scan of the block sizes and a gather into d_dst.
+ *   d_dst      : dense output, capacity dst_cap >= fse_b200_compress_blocks_bound(n, p)
+ *   d_offsets  : uint64[nblocks+1] byte offsets into d_dst
+ *   d_status   : int32[nblocks]
+ *   h_total    : host, total compressed bytes (= offsets[nblocks])
+ * In FSE_B200_TABLE_GLOBAL mode the blocks share the table installed with
+ * fse_b200_set_global_table and carry no header (the header-less variant the crate tests at
+ * src/fse.rs:394-421). */
+int fse_b200_compress_blocks(fse_b200_ctx *ctx, const uint8_t *d_src, size_t n, const fse_b200_params *p,
+                             uint8_t *d_dst, size_t dst_cap, uint64_t *d_offsets, int32_t *d_status,
+                             uint64_t *h_total);
+int fse_b200_compress_blocks_async(fse_b200_ctx *ctx, const uint8_t *d_src, size_t n, const fse_b200_params *p,
+                                   uint8_t *d_dst, size_t dst_cap, uint64_t *d_offsets, int32_t *d_status);
+
+/* fse_decompress / fse_decompress2 per block, src/lib.rs:187-248 (header parse + decode table +
+ * decode), length driven: block b yields exactly min(block_size, n - b*block_size) bytes and must
+ * consume its payload exactly (the reference stops on bit exhaustion and over-produces when the
+ * final states need 0 bits -- SURVEY.md Q1). */
+int fse_b200_decompress_blocks(fse_b200_ctx *ctx, const uint8_t *d_comp, size_t comp_bytes,
+                               const uint64_t *d_offsets, size_t nblocks, const fse_b200_params *p,
+                               uint8_t *d_dst, size_t n, int32_t *d_status);
+int fse_b200_decompress_blocks_async(fse_b200_ctx *ctx, const uint8_t *d_comp, size_t comp_bytes,
+                                     const uint64_t *d_offsets, size_t nblocks, const fse_b200_params *p,
+                                     uint8_t *d_dst, size_t n, int32_t *d_status);
+
+/* The reference's own termination rule (src/lib.rs:198, :228-241): no length is stored, decoding
+ * stops when the bit stack cannot supply num_bits.  Block b may produce up to p->block_size bytes
+ * into d_dst + b*block_size; d_out_len[b] receives the count.  A stream that would run past the
+ * capacity (the reference never terminates on it) gets FSE_B200_ERR_CAPACITY.
+ * p->table_log is the largest table_log accepted (0 = 11). */
+int fse_b200_decompress_exhaust(fse_b200_ctx *ctx, const uint8_t *d_comp, size_t comp_bytes,
+                                const uint64_t *d_offsets, size_t nblocks, const fse_b200_params *p,
+                                uint8_t *d_dst, uint32_t *d_out_len, int32_t *d_status);
+
+/* Global-table mode: normalise d_counts64 (uint64[256], e.g. the all-reduced sum of
+ * fse_b200_histogram_global over all ranks) with `table_log` and keep the encode and decode tables
+ * in the context.  h_header receives the NCount header (stored once for the whole job);
+ * *h_header_bytes in: capacity, out: bytes. */
+int fse_b200_set_global_table(fse_b200_ctx *ctx, const uint64_t *d_counts64, uint32_t table_log,
+                              uint8_t *h_header, size_t *h_header_bytes, uint32_t *h_log2);
+/* Same, from a stored header (decode side). */
+int fse_b200_set_global_table_from_header(fse_b200_ctx *ctx, const uint8_t *h_header, size_t header_bytes,
+                                          uint32_t *h_log2);
+
+/* ---- host-buffer conveniences (what a crate user calls; copies are part of the call) --------- */
+/* src/lib.rs:112 / :146 over blocks: h_src -> h_dst.  h_offsets uint64[nblocks+1], h_status int32[nblocks]
+ * (either may be NULL).  *h_total out. */
+int fse_b200_compress_host(fse_b200_ctx *ctx, const uint8_t *h_src, size_t n, const fse_b200_params *p,
+                           uint8_t *h_dst, size_t dst_cap, uint64_t *h_offsets, int32_t *h_status,
+                           uint64_t *h_total);
+/* src/lib.rs:187 / :215 over blocks. */
+int fse_b200_decompress_host(fse_b200_ctx *ctx, const uint8_t *h_comp, size_t comp_bytes,
+                             const uint64_t *h_offsets, size_t nblocks, const fse_b200_params *p,
+                             uint8_t *h_dst, size_t n, int32_t *h_status);
+
+/* Synthetic byte streams of SURVEY.md section 8(d), generated on the device (bench input).
+ * kind: 0 geometric(0.2) (the crate's gen_sequence, src/lib.rs:255-278), 1 text-like, 2 few-symbol,
+ * 3 uniform.  Byte i depends only on (seed, first_index + i). */
+int fse_b200_generate(fse_b200_ctx *ctx, int kind, uint64_t seed, uint64_t first_index, uint8_t *d_dst, size_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FSE_B200_H */
