@@ -33,6 +33,7 @@ struct DecLayout {
     uint32_t norm;   // int32[256]
     uint32_t ctr;    // uint32[256]       cum (unused output of warp_spread) then symbol_next
     uint32_t spread; // uint8[size]
+    uint32_t ring;   // uint32[256]       payload staging ring
     uint32_t total;
 };
 __host__ __device__ inline DecLayout dec_layout(uint32_t tlmax)
@@ -43,7 +44,8 @@ __host__ __device__ inline DecLayout dec_layout(uint32_t tlmax)
     l.norm = size * 4;
     l.ctr = l.norm + 1024;
     l.spread = l.ctr + 1024;
-    l.total = (l.spread + size + 15u) & ~15u;
+    l.ring = (l.spread + size + 15u) & ~15u;
+    l.total = l.ring + 1024;
     return l;
 }
 
@@ -183,7 +185,6 @@ __device__ void encode_payload_warp(const uint8_t *__restrict__ bsrc, uint32_t b
     const bool act = (uint32_t)lane < N;
     const uint32_t c = (bn - 1) & (N - 1);
     const uint32_t kcol = act ? ((c - (uint32_t)lane) & (N - 1)) : (uint32_t)lane;  // stream position in a round
-    // swizzled field address: row r, 16-byte chunk (kcol>>2) ^ (r&7)
     uint32_t state = 0;
     int32_t i0 = (int32_t)bn - 1 - (int32_t)kcol;  // my highest symbol (costs no bits, lib.rs:123,155-165)
     if (act) state = enc_first(tab, tt, __ldg(bsrc + i0));
@@ -191,21 +192,38 @@ __device__ void encode_payload_warp(const uint8_t *__restrict__ bsrc, uint32_t b
     const uint32_t G = (bn - N + N - 1) / N;  // rounds of N transitions
     uint32_t cw = 0, cb = 0, wdone = 0;
     uint32_t *myrow = rows + lane * ROW_STRIDE;
+    uint32_t *obuf = fld;                      // fld is dead between pass 2 and the next pass 1
     overflow = false;
+
+    // my 32 symbols of a chunk, fetched one chunk ahead so that DRAM latency hides behind pass 2
+    uint32_t sy[32];
+    const uint32_t NOSYM = 0x100;
+#pragma unroll
+    for (int r = 0; r < 32; r++) {
+        int32_t ii = i0 - (int32_t)(r * N);
+        sy[r] = (act && ii >= 0) ? (uint32_t)__ldg(bsrc + ii) : NOSYM;
+    }
     for (uint32_t g0 = 0; g0 < G; g0 += 32) {
-        // pass 1: 32 rounds of the state transform (fse.rs:227-239); fields go to fld in stream order
-#pragma unroll 8
+        // pass 1: 32 rounds of the state transform (fse.rs:227-239); fields go to fld in stream order,
+        // row r, 16-byte chunk (kcol>>2) ^ (r&7) (conflict free for the writer and for pass 2's reader)
+#pragma unroll
         for (int r = 0; r < 32; r++) {
-            int32_t ii = i0 - (int32_t)((g0 + r) * N);
             uint32_t f = 0;
-            if (act && ii >= 0) {
-                uint32_t sym = __ldg(bsrc + ii);
-                uint2 t = tt[sym];
+            if (sy[r] != NOSYM) {
+                uint2 t = tt[sy[r]];
                 uint32_t bo = (t.x + state) >> 16;
                 f = (state & ((1u << bo) - 1u)) | (bo << 16);
                 state = tab[(int32_t)(state >> bo) + (int32_t)t.y];
             }
             fld[r * 32 + ((((kcol >> 2) ^ (r & 7)) << 2) | (kcol & 3))] = f;
+        }
+        {   // prefetch the next chunk's symbols
+            int32_t base = i0 - (int32_t)((g0 + 32) * N);
+#pragma unroll
+            for (int r = 0; r < 32; r++) {
+                int32_t ii = base - (int32_t)(r * N);
+                sy[r] = (act && ii >= 0) ? (uint32_t)__ldg(bsrc + ii) : NOSYM;
+            }
         }
         __syncwarp();
         // pass 2: lane L serialises round L (32 consecutive fields of the stream)
@@ -221,7 +239,12 @@ __device__ void encode_payload_warp(const uint8_t *__restrict__ bsrc, uint32_t b
         }
         uint32_t tot = br.finish();
         __syncwarp();
-        wdone += warp_place(myrow, tot, pay + wdone, cap_words - wdone, lane, cw, cb, overflow);
+        // concatenate into obuf, then stream the full words out as whole 128-byte lines
+        uint32_t nw = warp_place(myrow, tot, obuf, 1024, lane, cw, cb, overflow);
+        __syncwarp();
+        if (wdone + nw > cap_words) { overflow = true; nw = 0; }
+        for (uint32_t j = lane; j < nw; j += 32) pay[wdone + j] = obuf[j];
+        wdone += nw;
         __syncwarp();
     }
     // final states N-1 .. 0 (fse.rs:248-250, order lib.rs:178-179), then the marker bit (lib.rs:141,181)
@@ -233,7 +256,7 @@ __device__ void encode_payload_warp(const uint8_t *__restrict__ bsrc, uint32_t b
         if ((uint32_t)lane == N - 1) br.put(1, 1);
         uint32_t tot = br.finish();
         __syncwarp();
-        wdone += warp_place(myrow, tot, pay + wdone, cap_words - wdone, lane, cw, cb, overflow);
+        wdone += warp_place(myrow, tot, pay + wdone, cap_words > wdone ? cap_words - wdone : 0, lane, cw, cb, overflow);
         __syncwarp();
     }
     if (cb) {
@@ -426,6 +449,7 @@ __global__ void __launch_bounds__(512) k_decode_blocks(DecArgs a)
     int32_t *norm = reinterpret_cast<int32_t *>(my + lay.norm);
     uint32_t *ctr = reinterpret_cast<uint32_t *>(my + lay.ctr);
     uint8_t *spread = my + lay.spread;
+    uint32_t *ring = reinterpret_cast<uint32_t *>(my + lay.ring);
     const uint32_t N = a.n_states;
     const uint32_t *wend = reinterpret_cast<const uint32_t *>(((uintptr_t)(a.comp + a.comp_bytes) + 3) & ~(uintptr_t)3);
 
@@ -496,11 +520,33 @@ __global__ void __launch_bounds__(512) k_decode_blocks(DecArgs a)
         const uint8_t *pay = cs + consumed;
         const uint32_t plen = clen - consumed;
         if (plen == 0 || pay[plen - 1] == 0) { if (lane == 0) a.status[b] = ST_NO_MARKER; continue; }
-        uint32_t cur = (plen - 1) * 8 + ilog2u(pay[plen - 1]);
-        if (cur < N * log2) { if (lane == 0) a.status[b] = ST_LENGTH; continue; }   // lib.rs:197,224-225
+        // The payload is staged through a 256-word ring in shared memory, refilled 128 words at a time
+        // from registers that were loaded one refill earlier (DRAM latency never sits in the state chain).
+        // Bit positions below are relative to `origin`, the 4-byte aligned word holding the first byte.
+        const uint32_t bias = (uint32_t)((uintptr_t)pay & 3);
+        const uint32_t *origin = reinterpret_cast<const uint32_t *>(pay - bias);
+        uint32_t cur = (plen - 1) * 8 + ilog2u(pay[plen - 1]) + 8 * bias;   // marker position
+        const uint32_t floor_bits = 8 * bias;                                 // stream bit 0
+        if (cur - floor_bits < N * log2) { if (lane == 0) a.status[b] = ST_LENGTH; continue; }   // lib.rs:197,224-225
+        const uint32_t topq = cur >> 5;
+        uint32_t lowq = (topq & ~127u) >= 128 ? (topq & ~127u) - 128 : 0;
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            uint32_t w = lowq + lane + 32 * k;
+            if (w <= topq) ring[w & 255] = __ldg(origin + w);
+        }
+        uint32_t pre[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) pre[k] = (lowq >= 128) ? __ldg(origin + lowq - 128 + lane + 32 * k) : 0u;
+        __syncwarp();
+        auto ring_bits = [&](uint32_t q, uint32_t nb) -> uint32_t {
+            uint32_t w = q >> 5;
+            return __funnelshift_r(ring[w & 255], ring[(w + 1) & 255], q & 31) & ((1u << nb) - 1u);
+        };
         const bool act = (uint32_t)lane < N;
         // Decoder::new, fse.rs:349-352: state 0 is read first (it was written last)
-        uint32_t state = act ? read_bits(pay, cur - (lane + 1) * log2, log2, wend) : 0u;
+        uint32_t state = act ? ring_bits(cur - (lane + 1) * log2, log2) : 0u;
         cur -= N * log2;
         const uint32_t body = bn - N;   // exhaust mode: bn == capacity
         bool bad = false;
@@ -510,19 +556,28 @@ __global__ void __launch_bounds__(512) k_decode_blocks(DecArgs a)
                 if (a.exhaust) bad = true;                 // ran past the capacity (quirk Q1)
                 break;
             }
+            if ((cur >> 5) < lowq + 17 && lowq) {          // a round takes at most 15 words: refill the ring
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < 4; k++) ring[(lowq - 128 + lane + 32 * k) & 255] = pre[k];
+                lowq -= 128;
+#pragma unroll
+                for (int k = 0; k < 4; k++) pre[k] = (lowq >= 128) ? __ldg(origin + lowq - 128 + lane + 32 * k) : 0u;
+                __syncwarp();
+            }
             uint32_t i = i0 + lane;
             bool on = act && i < body;
             uint32_t e = tab[state];                       // fse.rs:363-373
             uint32_t nb = on ? (e >> 24) : 0u;
             uint32_t incl = warp_incl_add(nb, lane);
             uint32_t tot = __shfl_sync(FULL, incl, 31);
-            if (tot > cur) {                               // the stack cannot supply this round
+            if (tot > cur - floor_bits) {                  // the stack cannot supply this round
                 if (!a.exhaust) { bad = true; break; }
                 // reference rule: the first decoder that gets None stops the loop (lib.rs:198,228-241)
-                uint32_t okm = __ballot_sync(FULL, on && incl <= cur);
+                uint32_t okm = __ballot_sync(FULL, on && incl <= cur - floor_bits);
                 uint32_t s = __popc(okm);                  // lanes [0, s) still decode
                 if (on && (uint32_t)lane < s) {
-                    uint32_t bits = read_bits(pay, cur - incl, nb, wend);
+                    uint32_t bits = ring_bits(cur - incl, nb);
                     out[i] = (uint8_t)(e >> 16);
                     state = (e & 0xffffu) + bits;
                 }
@@ -534,12 +589,13 @@ __global__ void __launch_bounds__(512) k_decode_blocks(DecArgs a)
                 break;
             }
             if (on) {
-                uint32_t bits = read_bits(pay, cur - incl, nb, wend);
+                uint32_t bits = ring_bits(cur - incl, nb);
                 out[i] = (uint8_t)(e >> 16);
                 state = (e & 0xffffu) + bits;
             }
             cur -= tot;
         }
+        cur -= floor_bits;
         if (!bad && act) {                                 // Decoder::finish, fse.rs:383-385 (order lib.rs:236-243)
             uint32_t i = stop_i + ((lane - stop_lane) & (N - 1));
             out[i] = (uint8_t)(tab[state] >> 16);
