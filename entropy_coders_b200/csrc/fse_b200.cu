@@ -1,7 +1,7 @@
 // fse_b200.cu -- C ABI of libfse_b200.so (see include/fse_b200.h).  Host orchestration only;
 // all arithmetic runs in the kernels of fse_kernels.cuh.  There is no CPU fallback.
 #include "../../include/fse_b200.h"
-#include "fse_kernels.cuh"
+#include "fse_kernels64.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -125,7 +125,8 @@ int check_params(fse_b200_ctx *ctx, const fse_b200_params *p)
 {
     if (!ctx || !p) return FSE_B200_ERR_ARG;
     if (p->block_size == 0 || p->block_size > (1u << 30)) return fail(ctx, FSE_B200_ERR_ARG, "block_size must be in 1..2^30");
-    if (!pow2(p->n_states) || p->n_states > 32) return fail(ctx, FSE_B200_ERR_ARG, "n_states must be 1, 2, 4, 8, 16 or 32");
+    if (!pow2(p->n_states) || p->n_states > 64) return fail(ctx, FSE_B200_ERR_ARG, "n_states must be 1, 2, 4, 8, 16, 32 or 64");
+    if (p->n_states == 64 && p->table_log > 13) return fail(ctx, FSE_B200_ERR_UNSUPPORTED, "n_states 64 needs table_log <= 13");
     if (p->table_log != 0 && (p->table_log < 5 || p->table_log > 15)) return fail(ctx, FSE_B200_ERR_ARG, "table_log must be 0 or 5..15");
     if (p->table_mode > 1) return fail(ctx, FSE_B200_ERR_ARG, "table_mode");
     return 0;
@@ -186,6 +187,8 @@ int fse_b200_create(int device, void *stream, fse_b200_ctx **out)
     cudaFuncSetAttribute(k_hist_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, HIST_SMEM);
     cudaFuncSetAttribute(k_encode_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
     cudaFuncSetAttribute(k_decode_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
+    cudaFuncSetAttribute(k_encode64_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
+    cudaFuncSetAttribute(k_decode64_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
     cudaFuncSetAttribute(k_build_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { fse_b200_destroy(ctx); return FSE_B200_ERR_CUDA; }
@@ -502,13 +505,16 @@ int fse_b200_compress_blocks_async(fse_b200_ctx *ctx, const uint8_t *d_src, size
     a.global_mode = global ? 1 : 0;
     a.g.log2 = ctx->g_log2; a.g.table_len = ctx->g_table_len;
     a.g.enc_table = ctx->g_enc_table.as<uint16_t>(); a.g.enc_tt = ctx->g_enc_tt.as<uint2>(); a.g.dec_table = ctx->g_dec_table.as<uint32_t>();
-    const EncLayout lay = enc_layout(tlmax);
-    int wpc = pick_warps(nb, ctx->num_sms, lay.total, ctx->smem_optin, 16);
+    const bool wide = p->n_states == 64;
+    if (wide && tlmax > 13) return fail(ctx, FSE_B200_ERR_UNSUPPORTED, "n_states 64 needs table_log <= 13");
+    const size_t per_warp = wide ? enc64_layout(tlmax).total : enc_layout(tlmax).total;
+    int wpc = pick_warps(nb, ctx->num_sms, per_warp, ctx->smem_optin, 16);
     if (wpc < 1) return fail(ctx, FSE_B200_ERR_UNSUPPORTED, "table_log too large for shared memory");
     int grid = (int)std::min<size_t>((nb + wpc - 1) / wpc, (size_t)ctx->num_sms);
     {
         Timed t(ctx, FSE_B200_K_ENCODE);
-        k_encode_blocks<<<grid, wpc * 32, (size_t)wpc * lay.total, ctx->stream>>>(a);
+        if (wide) k_encode64_blocks<<<grid, wpc * 32, (size_t)wpc * per_warp, ctx->stream>>>(a);
+        else k_encode_blocks<<<grid, wpc * 32, (size_t)wpc * per_warp, ctx->stream>>>(a);
     }
     {
         Timed t(ctx, FSE_B200_K_SCAN);
@@ -560,9 +566,11 @@ int fse_b200_decompress_blocks_async(fse_b200_ctx *ctx, const uint8_t *d_comp, s
     int wpc = pick_warps(nblocks, ctx->num_sms, lay.total, ctx->smem_optin, 16);
     if (wpc < 1) return fail(ctx, FSE_B200_ERR_UNSUPPORTED, "table_log too large for shared memory");
     int grid = (int)std::min<size_t>((nblocks + wpc - 1) / wpc, (size_t)ctx->num_sms);
+    if (p->n_states == 64 && tlmax > 13) return fail(ctx, FSE_B200_ERR_UNSUPPORTED, "n_states 64 needs table_log <= 13");
     {
         Timed t(ctx, FSE_B200_K_DECODE);
-        k_decode_blocks<<<grid, wpc * 32, (size_t)wpc * lay.total, ctx->stream>>>(a);
+        if (p->n_states == 64) k_decode64_blocks<<<grid, wpc * 32, (size_t)wpc * lay.total, ctx->stream>>>(a);
+        else k_decode_blocks<<<grid, wpc * 32, (size_t)wpc * lay.total, ctx->stream>>>(a);
     }
     CK(cudaGetLastError());
     return FSE_B200_OK;
@@ -584,6 +592,7 @@ int fse_b200_decompress_exhaust(fse_b200_ctx *ctx, const uint8_t *d_comp, size_t
     if (rc) return rc;
     if (!d_comp || !d_offsets || !d_dst || !d_out_len || !d_status) return fail(ctx, FSE_B200_ERR_ARG, "decompress_exhaust: null pointer");
     if (p->table_mode != FSE_B200_TABLE_PER_BLOCK) return fail(ctx, FSE_B200_ERR_ARG, "decompress_exhaust: per-block tables only");
+    if (p->n_states > 32) return fail(ctx, FSE_B200_ERR_ARG, "decompress_exhaust: n_states <= 32");
     if (nblocks > 0x7fffffffull) return fail(ctx, FSE_B200_ERR_ARG, "too many blocks");
     CK(cudaSetDevice(ctx->device));
     if (nblocks == 0) return FSE_B200_OK;

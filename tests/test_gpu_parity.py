@@ -205,7 +205,7 @@ def test_kat_bytes(ctx, k):
     from test_oracle import kat_src
     src = np.frombuffer(kat_src(k), np.uint8)
     for ns, p in k["payload"].items():
-        if int(ns) not in (1, 2, 4, 32):
+        if int(ns) not in (1, 2, 4, 32, 64):
             continue
         blocks, st, _ = gpu_blocks(ctx, src, len(src), k["table_log_req"], int(ns))
         assert st[0] == 0
@@ -213,10 +213,10 @@ def test_kat_bytes(ctx, k):
 
 
 @pytest.mark.parametrize("kind", ["geo", "text", "few", "uniform"])
-@pytest.mark.parametrize("n_states", [1, 2, 4, 32])
+@pytest.mark.parametrize("n_states", [1, 2, 4, 32, 64])
 def test_compress_blocks_bit_exact(ctx, kind, n_states):
     """every block's bytes equal the oracle's fse_compress(N)(block); decode round-trips"""
-    block_size = 65536 if n_states == 32 else 8192
+    block_size = 65536 if n_states >= 32 else 8192
     n = 9 * block_size + 4321
     src = O.generate(kind, 0xC0FFEE00 + n_states, n)
     blocks, st, (d, off, total) = gpu_blocks(ctx, src, block_size, 0, n_states)
@@ -230,36 +230,53 @@ def test_compress_blocks_bit_exact(ctx, kind, n_states):
     assert np.array_equal(out.cpu().numpy(), src)
 
 
-@pytest.mark.parametrize("table_log", [9, 11, 12])
+@pytest.mark.parametrize("n_states", [32, 64])
+@pytest.mark.parametrize("table_log", [9, 11, 12, 13])
 @pytest.mark.parametrize("kind", ["few", "uniform", "text"])
-def test_table_log_sweep(ctx, kind, table_log):
+def test_table_log_sweep(ctx, kind, table_log, n_states):
     """BASELINE config 3: explicit table_log 9/11/12 (Histogram::normalize(tl), histogram.rs:95)"""
     block_size, n = 65536, 6 * 65536
     src = O.generate(kind, 0xC0FFEE03, n)
-    blocks, st, (d, off, total) = gpu_blocks(ctx, src, block_size, table_log, 32)
-    exp = oracle_blocks(src, block_size, table_log, 32)
+    blocks, st, (d, off, total) = gpu_blocks(ctx, src, block_size, table_log, n_states)
+    exp = oracle_blocks(src, block_size, table_log, n_states)
     for b, (g, e) in enumerate(zip(blocks, exp)):
         assert st[b] == 0 and g == e, "block %d differs" % b
-    out, dst_ = ctx.decompress_blocks(d, total, dev(ctx, off), n, block_size, table_log, 32)
+    out, dst_ = ctx.decompress_blocks(d, total, dev(ctx, off), n, block_size, table_log, n_states)
     assert not dst_.cpu().numpy().any() and np.array_equal(out.cpu().numpy(), src)
 
 
-def test_block_128k(ctx):
+@pytest.mark.parametrize("n_states", [32, 64])
+def test_block_128k(ctx, n_states):
     """BASELINE config 4 block size"""
     n = 5 * 131072 + 99
     src = O.generate("geo", 0xC0FFEE04, n)
-    blocks, st, (d, off, total) = gpu_blocks(ctx, src, 131072, 0, 32)
-    exp = oracle_blocks(src, 131072, 0, 32)
+    blocks, st, (d, off, total) = gpu_blocks(ctx, src, 131072, 0, n_states)
+    exp = oracle_blocks(src, 131072, 0, n_states)
     for b, (g, e) in enumerate(zip(blocks, exp)):
         assert st[b] == 0 and g == e
-    out, _ = ctx.decompress_blocks(d, total, dev(ctx, off), n, 131072, 0, 32)
+    out, _ = ctx.decompress_blocks(d, total, dev(ctx, off), n, 131072, 0, n_states)
     assert np.array_equal(out.cpu().numpy(), src)
 
 
-@pytest.mark.parametrize("n_states", [1, 2, 32])
+def test_unaligned_source_and_destination_64(ctx):
+    """the 64-state path uses 16-bit loads/stores when it can: odd base addresses take the byte path"""
+    src = O.generate("text", 21, 3 * 8192 + 1)
+    dsrc = dev(ctx, src)[1:]
+    d, off, st, total = ctx.compress_blocks(dsrc, 8191, 0, 64)
+    offh = off.cpu().numpy()
+    buf = d[:total].cpu().numpy().tobytes()
+    exp = oracle_blocks(src[1:], 8191, 0, 64)
+    assert exp[-1] is None                                  # 3-byte tail: raw escape
+    assert [buf[offh[i]:offh[i + 1]] for i in range(len(exp) - 1)] == exp[:-1]
+    out, st2 = ctx.decompress_blocks(d, total, off, src.size - 1, 8191, 0, 64)
+    assert not st2.cpu().numpy().any() and np.array_equal(out.cpu().numpy(), src[1:])
+
+
+@pytest.mark.parametrize("n_states", [1, 2, 32, 64])
 def test_ragged_lengths(ctx, n_states):
-    """every residue of the block length modulo N, lengths around multiples of the chunk (1024 symbols)"""
-    lens = list(range(max(n_states, 5), max(n_states, 5) + 70)) + [1023, 1024, 1025, 1056, 1057, 2047, 2048, 2049, 4099]
+    """every residue of the block length modulo N, lengths around multiples of the chunk (1024 / 2048 symbols)"""
+    lens = list(range(max(n_states, 5), max(n_states, 5) + 70)) + [1023, 1024, 1025, 1056, 1057, 2047, 2048, 2049, 2111, 2112,
+                                                                     2113, 4095, 4096, 4097, 4099, 4160, 4161, 6207, 6209]
     for ln in lens:
         src = O.generate("text", 1000 + ln, ln)
         blocks, st, (d, off, total) = gpu_blocks(ctx, src, ln, 0, n_states)
