@@ -1,7 +1,7 @@
 // fse_b200.cu -- C ABI of libfse_b200.so (see include/fse_b200.h).  Host orchestration only;
 // all arithmetic runs in the kernels of fse_kernels.cuh.  There is no CPU fallback.
 #include "../../include/fse_b200.h"
-#include "fse_kernels64.cuh"
+#include "fse_decode64c.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -52,6 +52,7 @@ struct fse_b200_ctx {
     bool own_stream = false;
     int num_sms = 148;
     size_t smem_optin = 0;
+    size_t smem_per_sm = 0;
     uint64_t launches = 0;
     std::string err;
     // workspaces
@@ -179,6 +180,7 @@ int fse_b200_create(int device, void *stream, fse_b200_ctx **out)
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return FSE_B200_ERR_CUDA; }
     ctx->num_sms = prop.multiProcessorCount;
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    ctx->smem_per_sm = prop.sharedMemPerMultiprocessor;
     if (stream) ctx->stream = (cudaStream_t)stream;
     else {
         if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return FSE_B200_ERR_CUDA; }
@@ -189,6 +191,7 @@ int fse_b200_create(int device, void *stream, fse_b200_ctx **out)
     cudaFuncSetAttribute(k_decode_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
     cudaFuncSetAttribute(k_encode64_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
     cudaFuncSetAttribute(k_decode64_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
+    cudaFuncSetAttribute(k_decode64c_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
     cudaFuncSetAttribute(k_build_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { fse_b200_destroy(ctx); return FSE_B200_ERR_CUDA; }
@@ -562,12 +565,21 @@ int fse_b200_decompress_blocks_async(fse_b200_ctx *ctx, const uint8_t *d_comp, s
     a.exhaust = 0; a.out_len = nullptr;
     a.g.log2 = ctx->g_log2; a.g.table_len = ctx->g_table_len;
     a.g.enc_table = ctx->g_enc_table.as<uint16_t>(); a.g.enc_tt = ctx->g_enc_tt.as<uint2>(); a.g.dec_table = ctx->g_dec_table.as<uint32_t>();
-    const DecLayout lay = dec_layout(tlmax);
-    int wpc = pick_warps(nblocks, ctx->num_sms, lay.total, ctx->smem_optin, 16);
-    if (wpc < 1) return fail(ctx, FSE_B200_ERR_UNSUPPORTED, "table_log too large for shared memory");
-    int grid = (int)std::min<size_t>((nblocks + wpc - 1) / wpc, (size_t)ctx->num_sms);
     if (p->n_states == 64 && tlmax > 13) return fail(ctx, FSE_B200_ERR_UNSUPPORTED, "n_states 64 needs table_log <= 13");
-    {
+    if (p->n_states == 64 && tlmax <= 12) {
+        // compact layout: two CTAs per SM, each with half of the SM's shared memory
+        const Dec64cLayout lay = dec64c_layout(tlmax);
+        const size_t half = (ctx->smem_per_sm - 2048) / 2 - 1024;   // 1 KiB per CTA is reserved by the runtime
+        int wpc = pick_warps(nblocks, ctx->num_sms * 2, lay.total, std::min(half, ctx->smem_optin), 16);
+        if (wpc < 1) return fail(ctx, FSE_B200_ERR_UNSUPPORTED, "table_log too large for shared memory");
+        int grid = (int)std::min<size_t>((nblocks + wpc - 1) / wpc, (size_t)ctx->num_sms * 2);
+        Timed t(ctx, FSE_B200_K_DECODE);
+        k_decode64c_blocks<<<grid, wpc * 32, (size_t)wpc * lay.total, ctx->stream>>>(a);
+    } else {
+        const DecLayout lay = dec_layout(tlmax);
+        int wpc = pick_warps(nblocks, ctx->num_sms, lay.total, ctx->smem_optin, 16);
+        if (wpc < 1) return fail(ctx, FSE_B200_ERR_UNSUPPORTED, "table_log too large for shared memory");
+        int grid = (int)std::min<size_t>((nblocks + wpc - 1) / wpc, (size_t)ctx->num_sms);
         Timed t(ctx, FSE_B200_K_DECODE);
         if (p->n_states == 64) k_decode64_blocks<<<grid, wpc * 32, (size_t)wpc * lay.total, ctx->stream>>>(a);
         else k_decode_blocks<<<grid, wpc * 32, (size_t)wpc * lay.total, ctx->stream>>>(a);

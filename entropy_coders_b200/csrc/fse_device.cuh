@@ -35,6 +35,16 @@ __device__ __forceinline__ T warp_incl_add(T v, int lane)
     return v;
 }
 
+// Inclusive prefix sum of a value < 32 per lane from five ballots: five independent VOTE + POPC
+// pairs instead of a chain of five dependent shuffles (the scan sits on the decoder's critical path).
+__device__ __forceinline__ uint32_t warp_incl_add5(uint32_t v, int lane)
+{
+    const uint32_t le = 0xffffffffu >> (31 - lane);
+    uint32_t b0 = __ballot_sync(FULL, v & 1u), b1 = __ballot_sync(FULL, v & 2u), b2 = __ballot_sync(FULL, v & 4u);
+    uint32_t b3 = __ballot_sync(FULL, v & 8u), b4 = __ballot_sync(FULL, v & 16u);
+    return __popc(b0 & le) + 2u * __popc(b1 & le) + 4u * __popc(b2 & le) + 8u * __popc(b3 & le) + 16u * __popc(b4 & le);
+}
+
 __device__ __forceinline__ int warp_incl_max(int v, int lane)
 {
 #pragma unroll

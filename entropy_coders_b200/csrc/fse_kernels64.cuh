@@ -399,10 +399,10 @@ __global__ void __launch_bounds__(512) k_decode64_blocks(DecArgs a)
             uint32_t e0 = tab[st0], e1 = tab[st1];          // fse.rs:363-373, two independent chains
             uint32_t nb0 = e0 >> 24, nb1 = e1 >> 24;
             uint32_t nbs = nb0 + nb1;
-            uint32_t incl = warp_incl_add(nbs, lane);
-            uint32_t tot = __shfl_sync(FULL, incl, 31);
-            if (tot > cur - floor_bits) { bad = true; break; }
+            uint32_t incl = warp_incl_add5(nbs, lane);      // nbs <= 26
             uint32_t w = ring_bits(cur - incl, nbs);        // state 2l's bits are the upper part
+            uint32_t tot = __shfl_sync(FULL, incl, 31);     // off the critical path: a bad stream only reads stale ring words
+            if (tot > cur - floor_bits) { bad = true; break; }
             st0 = (e0 & 0xffffu) + (w >> nb1);
             st1 = (e1 & 0xffffu) + (w & ((1u << nb1) - 1u));
             uint32_t sy = ((e0 >> 16) & 0xffu) | ((e1 >> 8) & 0xff00u);

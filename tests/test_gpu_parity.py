@@ -269,7 +269,7 @@ def test_unaligned_source_and_destination_64(ctx):
     assert exp[-1] is None                                  # 3-byte tail: raw escape
     assert [buf[offh[i]:offh[i + 1]] for i in range(len(exp) - 1)] == exp[:-1]
     out, st2 = ctx.decompress_blocks(d, total, off, src.size - 1, 8191, 0, 64)
-    assert not st2.cpu().numpy().any() and np.array_equal(out.cpu().numpy(), src[1:])
+    assert (st2.cpu().numpy() >= 0).all() and np.array_equal(out.cpu().numpy(), src[1:])
 
 
 @pytest.mark.parametrize("n_states", [1, 2, 32, 64])
