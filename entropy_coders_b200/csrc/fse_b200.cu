@@ -2,6 +2,7 @@
 // all arithmetic runs in the kernels of fse_kernels.cuh.  There is no CPU fallback.
 #include "../../include/fse_b200.h"
 #include "fse_decode64c.cuh"
+#include "fse_hist16.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -160,6 +161,20 @@ int pick_warps(size_t nblocks, int num_sms, size_t per_warp_smem, size_t smem_li
     return best;
 }
 
+// Histogram::new per block: 16-bit lane-private columns (one warp per block) up to 1 MiB blocks,
+// 32-bit columns (one CTA per block) beyond
+void launch_hist(fse_b200_ctx *ctx, const uint8_t *d_src, size_t n, uint32_t block_size, size_t nb, uint32_t *d_counts,
+                 uint32_t *d_table_len)
+{
+    if (block_size <= HIST16_MAX_BLOCK) {
+        int grid = (int)std::min<size_t>((nb + HIST16_WARPS - 1) / HIST16_WARPS, (size_t)ctx->num_sms);
+        k_hist_blocks16<<<grid, HIST16_WARPS * 32, HIST16_SMEM, ctx->stream>>>(d_src, n, block_size, (uint32_t)nb, d_counts, d_table_len);
+    } else {
+        int grid = (int)std::min<size_t>(nb, (size_t)ctx->num_sms * 3);
+        k_hist_blocks<<<grid, HIST_WARPS * 32, HIST_SMEM, ctx->stream>>>(d_src, n, block_size, (uint32_t)nb, d_counts, d_table_len);
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -187,6 +202,7 @@ int fse_b200_create(int device, void *stream, fse_b200_ctx **out)
         ctx->own_stream = true;
     }
     cudaFuncSetAttribute(k_hist_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, HIST_SMEM);
+    cudaFuncSetAttribute(k_hist_blocks16, cudaFuncAttributeMaxDynamicSharedMemorySize, HIST16_SMEM);
     cudaFuncSetAttribute(k_encode_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
     cudaFuncSetAttribute(k_decode_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
     cudaFuncSetAttribute(k_encode64_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
@@ -271,8 +287,7 @@ int fse_b200_histogram_blocks(fse_b200_ctx *ctx, const uint8_t *d_src, size_t n,
     size_t nb = fse_b200_num_blocks(n, block_size);
     if (nb == 0) return FSE_B200_OK;
     if (nb > 0xffffffffull) return fail(ctx, FSE_B200_ERR_ARG, "too many blocks");
-    int grid = (int)std::min<size_t>(nb, (size_t)ctx->num_sms * 3);
-    k_hist_blocks<<<grid, HIST_WARPS * 32, HIST_SMEM, ctx->stream>>>(d_src, n, block_size, (uint32_t)nb, d_counts, d_table_len);
+    launch_hist(ctx, d_src, n, block_size, nb, d_counts, d_table_len);
     ctx->launches++;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(ctx->stream));
@@ -287,8 +302,7 @@ static int hist_global_async(fse_b200_ctx *ctx, const uint8_t *d_src, size_t n, 
     CK(cudaMemsetAsync(d_counts64, 0, 256 * sizeof(uint64_t), ctx->stream));
     if (nb == 0) return FSE_B200_OK;
     CK(ctx->counts.reserve(nb * 256 * sizeof(uint32_t)));
-    int grid = (int)std::min<size_t>(nb, (size_t)ctx->num_sms * 3);
-    k_hist_blocks<<<grid, HIST_WARPS * 32, HIST_SMEM, ctx->stream>>>(d_src, n, piece, (uint32_t)nb, ctx->counts.as<uint32_t>(), nullptr);
+    launch_hist(ctx, d_src, n, piece, nb, ctx->counts.as<uint32_t>(), nullptr);
     ctx->launches++;
     k_hist_reduce<<<(int)std::min<size_t>(nb, 64), 256, 0, ctx->stream>>>(ctx->counts.as<uint32_t>(), (uint32_t)nb,
                                                                           reinterpret_cast<unsigned long long *>(d_counts64));
@@ -493,10 +507,8 @@ int fse_b200_compress_blocks_async(fse_b200_ctx *ctx, const uint8_t *d_src, size
     CK(ctx->scratch.reserve(nb * stride));
     if (!global) {
         CK(ctx->counts.reserve(nb * 256 * sizeof(uint32_t)));
-        int grid = (int)std::min<size_t>(nb, (size_t)ctx->num_sms * 3);
         Timed t(ctx, FSE_B200_K_HIST);
-        k_hist_blocks<<<grid, HIST_WARPS * 32, HIST_SMEM, ctx->stream>>>(d_src, n, p->block_size, (uint32_t)nb,
-                                                                       ctx->counts.as<uint32_t>(), nullptr);
+        launch_hist(ctx, d_src, n, p->block_size, nb, ctx->counts.as<uint32_t>(), nullptr);
     }
     EncArgs a;
     a.src = d_src; a.n = n; a.block_size = p->block_size; a.nblocks = (uint32_t)nb;

@@ -29,6 +29,29 @@ __host__ __device__ inline Dec64cLayout dec64c_layout(uint32_t tlmax)
     return l;
 }
 
+// Inclusive warp prefix sum with the classic predicated add: shfl.up returns "source lane valid" as a
+// predicate, so each step is SHFL + @p IADD (no select, nothing on the ALU pipe).
+__device__ __forceinline__ uint32_t warp_incl_add_pred(uint32_t v)
+{
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+        asm volatile("{ .reg .u32 t; .reg .pred p; shfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff; @p add.u32 %0, %0, t; }"
+                     : "+r"(v) : "r"(d));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32_4(uint32_t saddr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+
 // DecodeTable::update, fse.rs:328-337, compact form
 __device__ __forceinline__ void warp_build_decode16(const int32_t *norm, uint32_t log2, uint32_t table_len,
                                                     const uint8_t *spread, uint32_t *ctr, uint16_t *table, int lane)
@@ -146,15 +169,20 @@ __global__ void __launch_bounds__(512, 2) k_decode64c_blocks(DecArgs a)
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             uint32_t w = lowq + lane + 32 * k;
-            if (w <= topq) ring[w & 255] = __ldg(origin + w);
+            if (w <= topq) {
+                uint32_t x = __ldg(origin + w);
+                ring[w & 255] = x;
+                if ((w & 255) == 0) ring[256] = x;          // mirror: ring[256] == ring[0]
+            }
         }
         uint32_t pre[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) pre[k] = (lowq >= 128) ? __ldg(origin + lowq - 128 + lane + 32 * k) : 0u;
         __syncwarp();
+        const uint32_t ring_saddr = (uint32_t)__cvta_generic_to_shared(ring);
         auto ring_bits = [&](uint32_t q, uint32_t nb) -> uint32_t {
-            uint32_t w = q >> 5;
-            return __funnelshift_r(ring[w & 255], ring[(w + 1) & 255], q & 31) & ((1u << nb) - 1u);
+            uint32_t a = ring_saddr + ((q >> 3) & 0x3fcu);
+            return __funnelshift_r(lds_u32(a), lds_u32_4(a), q & 31) & ~(0xffffffffu << nb);
         };
         uint32_t st0, st1;                                  // Decoder::new, fse.rs:349-352
         {
@@ -172,6 +200,7 @@ __global__ void __launch_bounds__(512, 2) k_decode64c_blocks(DecArgs a)
                 __syncwarp();
 #pragma unroll
                 for (int k = 0; k < 4; k++) ring[(lowq - 128 + lane + 32 * k) & 255] = pre[k];
+                if (lane == 0 && ((lowq - 128) & 255) == 0) ring[256] = pre[0];
                 lowq -= 128;
 #pragma unroll
                 for (int k = 0; k < 4; k++) pre[k] = (lowq >= 128) ? __ldg(origin + lowq - 128 + lane + 32 * k) : 0u;
@@ -181,7 +210,7 @@ __global__ void __launch_bounds__(512, 2) k_decode64c_blocks(DecArgs a)
             uint32_t y0 = sym[st0], y1 = sym[st1];
             uint32_t nb0 = e0 >> 12, nb1 = e1 >> 12;
             uint32_t nbs = nb0 + nb1;
-            uint32_t incl = warp_incl_add5(nbs, lane);
+            uint32_t incl = warp_incl_add_pred(nbs);
             uint32_t w = ring_bits(cur - incl, nbs);        // state 2l's bits are the upper part
             uint32_t tot = __shfl_sync(FULL, incl, 31);
             if (tot > cur - floor_bits) { bad = true; break; }
@@ -197,6 +226,7 @@ __global__ void __launch_bounds__(512, 2) k_decode64c_blocks(DecArgs a)
                 __syncwarp();
 #pragma unroll
                 for (int k = 0; k < 4; k++) ring[(lowq - 128 + lane + 32 * k) & 255] = pre[k];
+                if (lane == 0 && ((lowq - 128) & 255) == 0) ring[256] = pre[0];
                 lowq -= 128;
                 __syncwarp();
             }
