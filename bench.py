@@ -170,6 +170,7 @@ def run_ours(args, wl):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     stream = torch.cuda.Stream(device=dev)               # kernels, NCCL and the timing events share this stream
@@ -188,18 +189,20 @@ def run_ours(args, wl):
     out = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     totals = torch.zeros(world, dtype=torch.int64, device=dev)
 
+    from entropy_coders_b200 import sharding as S
+
     def global_table():
         counts = ctx.histogram_global(src)
-        if world > 1:
-            dist.all_reduce(counts)                      # NCCL: the only exchange of the global-table mode
+        S.allreduce_histogram(counts)                    # NCCL: the only exchange of the global-table mode
         return ctx.set_global_table(counts, tlog)
 
     def step():
         if tmode == 1:
             global_table()
         ctx.compress_blocks_async(src, p, dst, offsets, status)
-        if world > 1:                                    # place the output: exclusive scan of per-rank totals
-            dist.all_gather_into_tensor(totals, offsets[nb:nb + 1])
+        if world > 1:                                    # place the output: all-gather of the per-rank totals,
+            totals.copy_(S.gather_totals(offsets[nb:nb + 1], dev))   # exclusive scan -> this rank's base offset
+            S.base_offsets(totals)
         ctx.decompress_blocks_async(dst, cap, offsets, nb, p, out, nbytes, status_d)
 
     def barrier():
