@@ -72,6 +72,9 @@ struct fse_b200_ctx {
     std::vector<Span> spans;
     double t_ms[FSE_B200_NUM_KERNELS] = {0};
     uint64_t t_count[FSE_B200_NUM_KERNELS] = {0};
+    // copy streams of the pipelined host entry points
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    std::vector<cudaEvent_t> pipe_ev;
     // generator LUTs
     DevBuf lut[4];
     uint32_t lut_len[4] = {0, 0, 0, 0};
@@ -227,6 +230,9 @@ void fse_b200_destroy(fse_b200_ctx *ctx)
     for (DevBuf *b : bufs) b->release();
     ctx->pin.release();
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->pipe_ev) cudaEventDestroy(e);
+    if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
+    if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -646,6 +652,138 @@ static int worst_status(const int32_t *st, size_t nb)
     return FSE_B200_OK;
 }
 
+
+// ---------------------------------------------------------------------------------- pipelined host paths
+// Large host buffers are processed in chunks of whole blocks so that the H2D copy of chunk i+1, the
+// kernels of chunk i and the D2H copy of chunk i-1 overlap (PCIe is full duplex): three streams, events
+// between them, pinned scalars for the per-chunk totals.
+
+static const size_t PIPE_CHUNK_BYTES = 32u << 20;
+
+static int pipe_setup(fse_b200_ctx *ctx, size_t nchunks)
+{
+    if (!ctx->s_in) CK(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+    if (!ctx->s_out) CK(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+    while (ctx->pipe_ev.size() < 2 * nchunks + 2) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->pipe_ev.push_back(e);
+    }
+    return FSE_B200_OK;
+}
+
+static int compress_host_pipelined(fse_b200_ctx *ctx, const uint8_t *h_src, size_t n, const fse_b200_params *p, uint8_t *h_dst,
+                                   size_t dst_cap, uint64_t *h_offsets, int32_t *h_status, uint64_t *h_total)
+{
+    const size_t bs = p->block_size;
+    const size_t cblocks = std::max<size_t>(1, PIPE_CHUNK_BYTES / bs), cbytes = cblocks * bs;
+    const size_t nchunks = (n + cbytes - 1) / cbytes;
+    const size_t nb = fse_b200_num_blocks(n, p->block_size);
+    const size_t cbound = fse_b200_compress_blocks_bound(cbytes, p);
+    int rc = pipe_setup(ctx, nchunks);
+    if (rc) return rc;
+    CK(ctx->stage_in.reserve(n + 16));
+    CK(ctx->stage_out.reserve(nchunks * cbound));
+    CK(ctx->stage_off.reserve(nchunks * (cblocks + 1) * 8));
+    CK(ctx->stage_status.reserve((nb + 1) * 4));
+    CK(ctx->pin.reserve(nchunks * 8));
+    uint64_t *h_tot = reinterpret_cast<uint64_t *>(ctx->pin.p);
+    std::vector<uint64_t> loc((cblocks + 1) * nchunks);
+    std::vector<int32_t> st(nb);
+    // an event orders the copy streams after whatever the caller queued on the compute stream
+    CK(cudaEventRecord(ctx->pipe_ev[2 * nchunks], ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->s_in, ctx->pipe_ev[2 * nchunks], 0));
+    for (size_t c = 0; c < nchunks; c++) {
+        size_t o = c * cbytes, len = std::min(cbytes, n - o);
+        CK(cudaMemcpyAsync(ctx->stage_in.as<uint8_t>() + o, h_src + o, len, cudaMemcpyHostToDevice, ctx->s_in));
+        CK(cudaEventRecord(ctx->pipe_ev[2 * c], ctx->s_in));
+    }
+    for (size_t c = 0; c < nchunks; c++) {
+        size_t o = c * cbytes, len = std::min(cbytes, n - o), cnb = fse_b200_num_blocks(len, p->block_size);
+        uint64_t *d_off = ctx->stage_off.as<uint64_t>() + c * (cblocks + 1);
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->pipe_ev[2 * c], 0));
+        rc = fse_b200_compress_blocks_async(ctx, ctx->stage_in.as<uint8_t>() + o, len, p, ctx->stage_out.as<uint8_t>() + c * cbound,
+                                            cbound, d_off, ctx->stage_status.as<int32_t>() + c * cblocks);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(h_tot + c, d_off + cnb, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaEventRecord(ctx->pipe_ev[2 * c + 1], ctx->stream));
+    }
+    uint64_t run = 0;
+    int ret = FSE_B200_OK;
+    for (size_t c = 0; c < nchunks; c++) {
+        size_t o = c * cbytes, len = std::min(cbytes, n - o), cnb = fse_b200_num_blocks(len, p->block_size);
+        CK(cudaEventSynchronize(ctx->pipe_ev[2 * c + 1]));
+        uint64_t tot = h_tot[c];
+        CK(cudaStreamWaitEvent(ctx->s_out, ctx->pipe_ev[2 * c + 1], 0));
+        if (run + tot > dst_cap) ret = FSE_B200_ERR_CAPACITY;
+        else CK(cudaMemcpyAsync(h_dst + run, ctx->stage_out.as<uint8_t>() + c * cbound, tot, cudaMemcpyDeviceToHost, ctx->s_out));
+        CK(cudaMemcpyAsync(loc.data() + c * (cblocks + 1), ctx->stage_off.as<uint64_t>() + c * (cblocks + 1), (cnb + 1) * 8,
+                           cudaMemcpyDeviceToHost, ctx->s_out));
+        run += tot;
+    }
+    if (nb) CK(cudaMemcpyAsync(st.data(), ctx->stage_status.p, nb * 4, cudaMemcpyDeviceToHost, ctx->s_out));
+    CK(cudaStreamSynchronize(ctx->s_out));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *h_total = run;
+    if (ret) return fail(ctx, ret, "compress_host: dst_cap too small");
+    if (h_offsets) {
+        uint64_t base = 0;
+        for (size_t c = 0; c < nchunks; c++) {
+            size_t o = c * cbytes, len = std::min(cbytes, n - o), cnb = fse_b200_num_blocks(len, p->block_size);
+            const uint64_t *l = loc.data() + c * (cblocks + 1);
+            for (size_t b = 0; b < cnb; b++) h_offsets[c * cblocks + b] = base + l[b];
+            base += l[cnb];
+        }
+        h_offsets[nb] = base;
+    }
+    if (h_status && nb) memcpy(h_status, st.data(), nb * 4);
+    return worst_status(st.data(), nb);
+}
+
+static int decompress_host_pipelined(fse_b200_ctx *ctx, const uint8_t *h_comp, size_t comp_bytes, const uint64_t *h_offsets,
+                                     size_t nblocks, const fse_b200_params *p, uint8_t *h_dst, size_t n, int32_t *h_status)
+{
+    const size_t bs = p->block_size;
+    const size_t cblocks = std::max<size_t>(1, PIPE_CHUNK_BYTES / bs), cbytes = cblocks * bs;
+    const size_t nchunks = (nblocks + cblocks - 1) / cblocks;
+    int rc = pipe_setup(ctx, nchunks);
+    if (rc) return rc;
+    if (h_offsets[nblocks] > comp_bytes) return fail(ctx, FSE_B200_ERR_ARG, "decompress_host: offsets exceed comp_bytes");
+    CK(ctx->stage_out.reserve(comp_bytes + 16));
+    CK(ctx->stage_in.reserve(n + 16));
+    CK(ctx->stage_off.reserve((nblocks + 1) * 8));
+    CK(ctx->stage_status.reserve((nblocks + 1) * 4));
+    std::vector<int32_t> st(nblocks);
+    CK(cudaEventRecord(ctx->pipe_ev[2 * nchunks], ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->s_in, ctx->pipe_ev[2 * nchunks], 0));
+    CK(cudaMemcpyAsync(ctx->stage_off.p, h_offsets, (nblocks + 1) * 8, cudaMemcpyHostToDevice, ctx->s_in));
+    for (size_t c = 0; c < nchunks; c++) {
+        size_t b0 = c * cblocks, b1 = std::min(nblocks, b0 + cblocks);
+        for (size_t b = b0; b < b1; b++)
+            if (h_offsets[b + 1] < h_offsets[b]) return fail(ctx, FSE_B200_ERR_ARG, "decompress_host: offsets not monotone");
+        uint64_t o0 = h_offsets[b0], o1 = h_offsets[b1];
+        if (o1 > o0) CK(cudaMemcpyAsync(ctx->stage_out.as<uint8_t>() + o0, h_comp + o0, o1 - o0, cudaMemcpyHostToDevice, ctx->s_in));
+        CK(cudaEventRecord(ctx->pipe_ev[2 * c], ctx->s_in));
+    }
+    for (size_t c = 0; c < nchunks; c++) {
+        size_t b0 = c * cblocks, b1 = std::min(nblocks, b0 + cblocks);
+        size_t o = b0 * bs, len = std::min(cbytes, n - o);
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->pipe_ev[2 * c], 0));
+        rc = fse_b200_decompress_blocks_async(ctx, ctx->stage_out.as<uint8_t>(), comp_bytes, ctx->stage_off.as<uint64_t>() + b0, b1 - b0,
+                                              p, ctx->stage_in.as<uint8_t>() + o, len, ctx->stage_status.as<int32_t>() + b0);
+        if (rc) return rc;
+        CK(cudaEventRecord(ctx->pipe_ev[2 * c + 1], ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->s_out, ctx->pipe_ev[2 * c + 1], 0));
+        CK(cudaMemcpyAsync(h_dst + o, ctx->stage_in.as<uint8_t>() + o, len, cudaMemcpyDeviceToHost, ctx->s_out));
+    }
+    CK(cudaStreamWaitEvent(ctx->s_out, ctx->pipe_ev[2 * (nchunks - 1) + 1], 0));
+    if (nblocks) CK(cudaMemcpyAsync(st.data(), ctx->stage_status.p, nblocks * 4, cudaMemcpyDeviceToHost, ctx->s_out));
+    CK(cudaStreamSynchronize(ctx->s_out));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (h_status && nblocks) memcpy(h_status, st.data(), nblocks * 4);
+    return worst_status(st.data(), nblocks);
+}
+
 int fse_b200_compress_host(fse_b200_ctx *ctx, const uint8_t *h_src, size_t n, const fse_b200_params *p, uint8_t *h_dst,
                            size_t dst_cap, uint64_t *h_offsets, int32_t *h_status, uint64_t *h_total)
 {
@@ -653,6 +791,8 @@ int fse_b200_compress_host(fse_b200_ctx *ctx, const uint8_t *h_src, size_t n, co
     if (rc) return rc;
     if ((!h_src && n) || !h_dst || !h_total) return fail(ctx, FSE_B200_ERR_ARG, "compress_host: null pointer");
     CK(cudaSetDevice(ctx->device));
+    if (n > 2 * PIPE_CHUNK_BYTES && p->block_size <= PIPE_CHUNK_BYTES)
+        return compress_host_pipelined(ctx, h_src, n, p, h_dst, dst_cap, h_offsets, h_status, h_total);
     const size_t nb = fse_b200_num_blocks(n, p->block_size);
     const size_t bound = fse_b200_compress_blocks_bound(n, p);
     CK(ctx->stage_in.reserve(n + 16));
@@ -685,6 +825,9 @@ int fse_b200_decompress_host(fse_b200_ctx *ctx, const uint8_t *h_comp, size_t co
     if (rc) return rc;
     if (!h_comp || !h_offsets || (!h_dst && n)) return fail(ctx, FSE_B200_ERR_ARG, "decompress_host: null pointer");
     CK(cudaSetDevice(ctx->device));
+    if (nblocks != fse_b200_num_blocks(n, p->block_size)) return fail(ctx, FSE_B200_ERR_ARG, "nblocks does not match n / block_size");
+    if (n > 2 * PIPE_CHUNK_BYTES && p->block_size <= PIPE_CHUNK_BYTES)
+        return decompress_host_pipelined(ctx, h_comp, comp_bytes, h_offsets, nblocks, p, h_dst, n, h_status);
     CK(ctx->stage_out.reserve(comp_bytes + 16));
     CK(ctx->stage_in.reserve(n + 16));
     CK(ctx->stage_off.reserve((nblocks + 1) * 8));

@@ -465,3 +465,23 @@ def test_crate_hist_verify():
     assert len(et.table) == 512 and len(dt.table) == 512
     with pytest.raises(E.HistError):
         E.NormHistogram.read(bytes([0x0F, 0, 0, 0]))
+
+
+def test_host_buffer_api_pipelined(ctx):
+    """inputs above 64 MiB take the chunked, copy/compute-overlapped host path: same bytes, same offsets"""
+    import torch
+    n = (70 << 20) + 1234
+    src = ctx.generate("text", 31, n)
+    hsrc = src.cpu().numpy()
+    d, off, st, total = ctx.compress_blocks(src, 65536, 0, 64)
+    hd, hoff, hst, htotal = ctx.compress_host(hsrc, 65536, 0, 64)
+    assert htotal == total and np.array_equal(hoff.astype(np.int64), off.cpu().numpy())
+    assert np.array_equal(hd[:htotal], d[:total].cpu().numpy()) and np.array_equal(hst, st.cpu().numpy())
+    out, st2 = ctx.decompress_host(hd, htotal, hoff, n, 65536, 0, 64)
+    assert (st2 >= 0).all() and np.array_equal(out, hsrc)
+    # pinned torch buffers (what bench.py uses)
+    psrc = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    psrc.copy_(src)
+    pdst = torch.empty(htotal + 64, dtype=torch.uint8, pin_memory=True)
+    _, poff, _, ptotal = ctx.compress_host(psrc, 65536, 0, 64, dst=pdst)
+    assert ptotal == total and torch.equal(pdst[:total], d[:total].cpu())
