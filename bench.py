@@ -251,6 +251,9 @@ def run_ours(args, wl):
     dom_ms = tm[dom][0] / max(tm[dom][1], 1)
     alg_bytes = nbytes + total
     achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this
+    # workload (profiles/r1_ncu_full_c2_n64.txt); only meaningful for the configuration that was profiled
+    traffic = {"encode": 273.05e6 + 141.99e6, "decode": 178.01e6 + 226.23e6}[dom] if (wl == "c2" and N_STATES == 64) else None
 
     # e2e: host buffers through the host entry points, copies inside the timed region (rank-local data)
     e2e = None
@@ -308,7 +311,7 @@ def run_ours(args, wl):
             "compressed_ratio": total / nbytes,
             "kernel_ms_per_step": {k: tm[k][0] / args.steps for k in tm},
             "roofline": {"bound": "hbm", "kernel": "k_%s_blocks" % dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "note": "N + C per launch (uncompressed + compressed bytes of one rank) / mean launch time of the dominant kernel"},
             "e2e": e2e, "cpu_baseline": cpu, "gpu_launches": int(launches), "clocks": clocks,

@@ -1,11 +1,12 @@
 // fse_b200.cu -- C ABI of libfse_b200.so (see include/fse_b200.h).  Host orchestration only;
 // all arithmetic runs in the kernels of fse_kernels.cuh.  There is no CPU fallback.
 #include "../../include/fse_b200.h"
-#include "fse_decode64c.cuh"
+#include "fse_decode64w.cuh"
 #include "fse_hist16.cuh"
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -211,6 +212,7 @@ int fse_b200_create(int device, void *stream, fse_b200_ctx **out)
     cudaFuncSetAttribute(k_encode64_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
     cudaFuncSetAttribute(k_decode64_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
     cudaFuncSetAttribute(k_decode64c_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
+    cudaFuncSetAttribute(k_decode64w_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
     cudaFuncSetAttribute(k_build_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { fse_b200_destroy(ctx); return FSE_B200_ERR_CUDA; }
@@ -584,15 +586,20 @@ int fse_b200_decompress_blocks_async(fse_b200_ctx *ctx, const uint8_t *d_comp, s
     a.g.log2 = ctx->g_log2; a.g.table_len = ctx->g_table_len;
     a.g.enc_table = ctx->g_enc_table.as<uint16_t>(); a.g.enc_tt = ctx->g_enc_tt.as<uint2>(); a.g.dec_table = ctx->g_dec_table.as<uint32_t>();
     if (p->n_states == 64 && tlmax > 13) return fail(ctx, FSE_B200_ERR_UNSUPPORTED, "n_states 64 needs table_log <= 13");
-    if (p->n_states == 64 && tlmax <= 12) {
-        // compact layout: two CTAs per SM, each with half of the SM's shared memory
-        const Dec64cLayout lay = dec64c_layout(tlmax);
+    const char *variant = getenv("FSE_B200_DECODE64");      // development switch: "c" compact, "w" wide entries
+    const bool use_wide = variant ? variant[0] == 'w' : false;   // measured: compact 0.49 ms vs wide 0.70 ms on c2
+    if (p->n_states == 64 && (tlmax <= 12 || use_wide)) {
+        // two CTAs per SM, each with half of the SM's shared memory
         const size_t half = (ctx->smem_per_sm - 2048) / 2 - 1024;   // 1 KiB per CTA is reserved by the runtime
-        int wpc = pick_warps(nblocks, ctx->num_sms * 2, lay.total, std::min(half, ctx->smem_optin), 16);
+        const size_t per_warp = (use_wide || tlmax > 12) ? dec64w_layout(tlmax).total : dec64c_layout(tlmax).total;
+        int wpc = pick_warps(nblocks, ctx->num_sms * 2, per_warp, std::min(half, ctx->smem_optin), 16);
+        int ctas = 2;
+        if (wpc < 1) { wpc = pick_warps(nblocks, ctx->num_sms, per_warp, ctx->smem_optin, 16); ctas = 1; }
         if (wpc < 1) return fail(ctx, FSE_B200_ERR_UNSUPPORTED, "table_log too large for shared memory");
-        int grid = (int)std::min<size_t>((nblocks + wpc - 1) / wpc, (size_t)ctx->num_sms * 2);
+        int grid = (int)std::min<size_t>((nblocks + wpc - 1) / wpc, (size_t)ctx->num_sms * ctas);
         Timed t(ctx, FSE_B200_K_DECODE);
-        k_decode64c_blocks<<<grid, wpc * 32, (size_t)wpc * lay.total, ctx->stream>>>(a);
+        if (use_wide || tlmax > 12) k_decode64w_blocks<<<grid, wpc * 32, (size_t)wpc * per_warp, ctx->stream>>>(a);
+        else k_decode64c_blocks<<<grid, wpc * 32, (size_t)wpc * per_warp, ctx->stream>>>(a);
     } else {
         const DecLayout lay = dec_layout(tlmax);
         int wpc = pick_warps(nblocks, ctx->num_sms, lay.total, ctx->smem_optin, 16);
