@@ -59,7 +59,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -310,7 +310,7 @@ def run_ours(args, wl):
             "encode_GBps": nbytes / (enc_ms * 1e-3) / 1e9, "decode_GBps": nbytes / (dec_ms * 1e-3) / 1e9,
             "compressed_ratio": total / nbytes,
             "kernel_ms_per_step": {k: tm[k][0] / args.steps for k in tm},
-            "roofline": {"bound": "hbm", "kernel": "k_%s_blocks" % dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": {"encode": "k_encode64_blocks", "decode": "k_decode64c_blocks"}[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "note": "N + C per launch (uncompressed + compressed bytes of one rank) / mean launch time of the dominant kernel"},

@@ -9,6 +9,9 @@
 // table_log 11, i.e. 28 warps (blocks in flight) per SM instead of 14.
 #pragma once
 #include "fse_kernels64.cuh"
+#ifndef FSE_DEC_SCAN
+#define FSE_DEC_SCAN 0   /* 1 = ballot+popc prefix: measured slower (0.59 vs 0.49 ms on c2) */
+#endif
 
 namespace fsed {
 
@@ -210,7 +213,11 @@ __global__ void __launch_bounds__(512, 2) k_decode64c_blocks(DecArgs a)
             uint32_t y0 = sym[st0], y1 = sym[st1];
             uint32_t nb0 = e0 >> 12, nb1 = e1 >> 12;
             uint32_t nbs = nb0 + nb1;
+#if FSE_DEC_SCAN == 1
+            uint32_t incl = warp_incl_add5(nbs, lane);      // ballots + popc: no shared-memory crossbar traffic
+#else
             uint32_t incl = warp_incl_add_pred(nbs);
+#endif
             uint32_t w = ring_bits(cur - incl, nbs);        // state 2l's bits are the upper part
             uint32_t tot = __shfl_sync(FULL, incl, 31);
             if (tot > cur - floor_bits) { bad = true; break; }
