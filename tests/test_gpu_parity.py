@@ -485,3 +485,69 @@ def test_host_buffer_api_pipelined(ctx):
     pdst = torch.empty(htotal + 64, dtype=torch.uint8, pin_memory=True)
     _, poff, _, ptotal = ctx.compress_host(psrc, 65536, 0, 64, dst=pdst)
     assert ptotal == total and torch.equal(pdst[:total], d[:total].cpu())
+
+
+@pytest.mark.parametrize("n_states", [1, 2])
+def test_exhaust_decode_matches_reference_termination(ctx, n_states):
+    """fse_decompress / fse_decompress2 stop when the bit stack cannot supply num_bits (lib.rs:198,228-241);
+    with final states that need 0 bits they over-produce.  The exhaust-mode kernel must yield
+    exactly what the oracle's exhaustion decoder yields, byte for byte, including the surplus."""
+    import torch
+    cases = [("geo", 5000), ("text", 4097), ("few", 3000), ("few", 777), ("uniform", 2048), ("geo", 33)]
+    streams, expect = [], []
+    for i, (kind, n) in enumerate(cases):
+        src = O.generate(kind, 900 + i, n).tobytes()
+        comp = O.compress_n(src, 0, n_states)[0]
+        try:
+            exp = O.decompress_n_exhaust(comp, n_states, 4 * n + 64)
+        except ValueError:
+            exp = None                                   # ran past the capacity: the reference never terminates
+        streams.append(comp)
+        expect.append((src, exp))
+    cap = max(4 * n + 64 for _, n in cases)
+    off = np.zeros(len(streams) + 1, np.int64)
+    off[1:] = np.cumsum([len(s) for s in streams])
+    comp = np.frombuffer(b"".join(streams), np.uint8).copy()
+    out, out_len, st = ctx.decompress_exhaust(dev(ctx, comp), comp.size, dev(ctx, off), len(streams), cap, 15, n_states)
+    out, out_len, st = out.cpu().numpy(), out_len.cpu().numpy(), st.cpu().numpy()
+    surplus = 0
+    for i, (src, exp) in enumerate(expect):
+        if exp is None or len(exp) > cap:
+            assert st[i] == -2, i
+            continue
+        assert st[i] == 0 and out_len[i] == len(exp), (i, st[i], out_len[i], len(exp))
+        assert out[i, :len(exp)].tobytes() == exp
+        assert exp[:len(src)] == src
+        surplus += len(exp) - len(src)
+    if n_states == 1:
+        assert surplus >= 0
+
+
+def test_histogram_large_blocks_take_the_32bit_path(ctx):
+    """blocks above 1 MiB use 32-bit counter columns (k_hist_blocks)"""
+    src = O.generate("geo", 3, (5 << 20) + 99)
+    counts, tlen = ctx.histogram_blocks(dev(ctx, src), 2 << 20)
+    counts = counts.cpu().numpy().view(np.uint32)
+    for b in range(counts.shape[0]):
+        assert np.array_equal(counts[b], np.bincount(src[b * (2 << 20):(b + 1) * (2 << 20)], minlength=256))
+
+
+def test_argument_errors(ctx):
+    import torch
+    import entropy_coders_b200 as E
+    src = dev(ctx, O.generate("geo", 1, 70000))
+    with pytest.raises(E.FseError):
+        ctx.compress_blocks(src, 65536, 0, 3)            # n_states must be a power of two
+    with pytest.raises(E.FseError):
+        ctx.compress_blocks(src, 65536, 14, 64)          # 64 states need table_log <= 13
+    with pytest.raises(E.FseError):
+        ctx.compress_blocks(src, 0, 0, 32)
+    small = torch.empty(10, dtype=torch.uint8, device=ctx.device)
+    off = torch.zeros(3, dtype=torch.int64, device=ctx.device)
+    st = torch.zeros(2, dtype=torch.int32, device=ctx.device)
+    with pytest.raises(E.FseError):
+        ctx.compress_blocks(src, 65536, 0, 32, out=(small, off, st))     # dst_cap below the bound
+    fresh = E.Context(0)
+    with pytest.raises(E.FseError):
+        fresh.compress_blocks(src, 65536, 11, 32, table_mode=1)         # global table not installed
+    fresh.close()
