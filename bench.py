@@ -170,8 +170,19 @@ def run_ours(args, wl):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep stdout to the one JSON line
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL prints its version banner on stdout when the first communicator is made: send it to stderr so
+        # that stdout carries exactly one JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.all_reduce(torch.zeros(1, device=torch.device("cuda", local)))
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     dev = torch.device("cuda", local)
     stream = torch.cuda.Stream(device=dev)               # kernels, NCCL and the timing events share this stream
     torch.cuda.set_stream(stream)
@@ -196,14 +207,23 @@ def run_ours(args, wl):
         S.allreduce_histogram(counts)                    # NCCL: the only exchange of the global-table mode
         return ctx.set_global_table(counts, tlog)
 
+    side = torch.cuda.Stream(device=dev)                 # the tiny exchange runs beside the decode kernel
+    ev_c, ev_x = torch.cuda.Event(), torch.cuda.Event()
+
     def step():
         if tmode == 1:
             global_table()
         ctx.compress_blocks_async(src, p, dst, offsets, status)
         if world > 1:                                    # place the output: all-gather of the per-rank totals,
-            totals.copy_(S.gather_totals(offsets[nb:nb + 1], dev))   # exclusive scan -> this rank's base offset
-            S.base_offsets(totals)
+            ev_c.record(stream)                          # exclusive scan -> this rank's base offset
+            with torch.cuda.stream(side):
+                side.wait_event(ev_c)
+                totals.copy_(S.gather_totals(offsets[nb:nb + 1], dev))
+                S.base_offsets(totals)
+                ev_x.record(side)
         ctx.decompress_blocks_async(dst, cap, offsets, nb, p, out, nbytes, status_d)
+        if world > 1:
+            stream.wait_event(ev_x)                      # the step is complete when both are
 
     def barrier():
         torch.cuda.synchronize()
