@@ -37,7 +37,7 @@ WORKLOADS = {
     "c4": ("geo", 0xC0FFEE04, 1 << 30, 131072, 0, 0, "skewed (geometric 0.2) bytes, 128 KiB blocks, block-range sharded, 1 GiB per GPU"),
     "c5": ("geo", 0xC0FFEE05, 1 << 30, 131072, 11, 1, "skewed bytes, 128 KiB blocks, one global table via histogram all-reduce, 1 GiB per GPU"),
 }
-N_STATES = 64
+N_STATES = 128
 
 
 def peaks():

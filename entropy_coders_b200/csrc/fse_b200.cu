@@ -1,7 +1,7 @@
 // fse_b200.cu -- C ABI of libfse_b200.so (see include/fse_b200.h).  Host orchestration only;
 // all arithmetic runs in the kernels of fse_kernels.cuh.  There is no CPU fallback.
 #include "../../include/fse_b200.h"
-#include "fse_decode64w.cuh"
+#include "fse_encode128.cuh"
 #include "fse_hist16.cuh"
 
 #include <algorithm>
@@ -131,8 +131,8 @@ int check_params(fse_b200_ctx *ctx, const fse_b200_params *p)
 {
     if (!ctx || !p) return FSE_B200_ERR_ARG;
     if (p->block_size == 0 || p->block_size > (1u << 30)) return fail(ctx, FSE_B200_ERR_ARG, "block_size must be in 1..2^30");
-    if (!pow2(p->n_states) || p->n_states > 64) return fail(ctx, FSE_B200_ERR_ARG, "n_states must be 1, 2, 4, 8, 16, 32 or 64");
-    if (p->n_states == 64 && p->table_log > 13) return fail(ctx, FSE_B200_ERR_UNSUPPORTED, "n_states 64 needs table_log <= 13");
+    if (!pow2(p->n_states) || p->n_states > 128) return fail(ctx, FSE_B200_ERR_ARG, "n_states must be a power of two up to 128");
+    if (p->n_states >= 64 && p->table_log > 13) return fail(ctx, FSE_B200_ERR_UNSUPPORTED, "n_states 64 / 128 need table_log <= 13");
     if (p->table_log != 0 && (p->table_log < 5 || p->table_log > 15)) return fail(ctx, FSE_B200_ERR_ARG, "table_log must be 0 or 5..15");
     if (p->table_mode > 1) return fail(ctx, FSE_B200_ERR_ARG, "table_mode");
     return 0;
@@ -213,6 +213,8 @@ int fse_b200_create(int device, void *stream, fse_b200_ctx **out)
     cudaFuncSetAttribute(k_decode64_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
     cudaFuncSetAttribute(k_decode64c_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
     cudaFuncSetAttribute(k_decode64w_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
+    cudaFuncSetAttribute(k_decode128_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
+    cudaFuncSetAttribute(k_encode128_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
     cudaFuncSetAttribute(k_build_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { fse_b200_destroy(ctx); return FSE_B200_ERR_CUDA; }
@@ -528,15 +530,16 @@ int fse_b200_compress_blocks_async(fse_b200_ctx *ctx, const uint8_t *d_src, size
     a.global_mode = global ? 1 : 0;
     a.g.log2 = ctx->g_log2; a.g.table_len = ctx->g_table_len;
     a.g.enc_table = ctx->g_enc_table.as<uint16_t>(); a.g.enc_tt = ctx->g_enc_tt.as<uint2>(); a.g.dec_table = ctx->g_dec_table.as<uint32_t>();
-    const bool wide = p->n_states == 64;
-    if (wide && tlmax > 13) return fail(ctx, FSE_B200_ERR_UNSUPPORTED, "n_states 64 needs table_log <= 13");
+    const bool wide = p->n_states >= 64;
+    if (wide && tlmax > 13) return fail(ctx, FSE_B200_ERR_UNSUPPORTED, "n_states 64 / 128 need table_log <= 13");
     const size_t per_warp = wide ? enc64_layout(tlmax).total : enc_layout(tlmax).total;
     int wpc = pick_warps(nb, ctx->num_sms, per_warp, ctx->smem_optin, 16);
     if (wpc < 1) return fail(ctx, FSE_B200_ERR_UNSUPPORTED, "table_log too large for shared memory");
     int grid = (int)std::min<size_t>((nb + wpc - 1) / wpc, (size_t)ctx->num_sms);
     {
         Timed t(ctx, FSE_B200_K_ENCODE);
-        if (wide) k_encode64_blocks<<<grid, wpc * 32, (size_t)wpc * per_warp, ctx->stream>>>(a);
+        if (p->n_states == 128) k_encode128_blocks<<<grid, wpc * 32, (size_t)wpc * per_warp, ctx->stream>>>(a);
+        else if (wide) k_encode64_blocks<<<grid, wpc * 32, (size_t)wpc * per_warp, ctx->stream>>>(a);
         else k_encode_blocks<<<grid, wpc * 32, (size_t)wpc * per_warp, ctx->stream>>>(a);
     }
     {
@@ -586,6 +589,21 @@ int fse_b200_decompress_blocks_async(fse_b200_ctx *ctx, const uint8_t *d_comp, s
     a.g.log2 = ctx->g_log2; a.g.table_len = ctx->g_table_len;
     a.g.enc_table = ctx->g_enc_table.as<uint16_t>(); a.g.enc_tt = ctx->g_enc_tt.as<uint2>(); a.g.dec_table = ctx->g_dec_table.as<uint32_t>();
     if (p->n_states == 64 && tlmax > 13) return fail(ctx, FSE_B200_ERR_UNSUPPORTED, "n_states 64 needs table_log <= 13");
+    if (p->n_states == 128) {
+        if (tlmax > 13) return fail(ctx, FSE_B200_ERR_UNSUPPORTED, "n_states 128 needs table_log <= 13");
+        const size_t half = (ctx->smem_per_sm - 2048) / 2 - 1024;
+        const size_t per_warp = dec64w_layout(tlmax).total;
+        int wpc = pick_warps(nblocks, ctx->num_sms * 2, per_warp, std::min(half, ctx->smem_optin), 16);
+        int ctas = 2;
+        if (wpc < 1) { wpc = pick_warps(nblocks, ctx->num_sms, per_warp, ctx->smem_optin, 16); ctas = 1; }
+        if (wpc < 1) return fail(ctx, FSE_B200_ERR_UNSUPPORTED, "table_log too large for shared memory");
+        if (const char *o = getenv("FSE_B200_WPC")) wpc = atoi(o);   // development override
+        int grid = (int)std::min<size_t>((nblocks + wpc - 1) / wpc, (size_t)ctx->num_sms * ctas);
+        Timed t(ctx, FSE_B200_K_DECODE);
+        k_decode128_blocks<<<grid, wpc * 32, (size_t)wpc * per_warp, ctx->stream>>>(a);
+        CK(cudaGetLastError());
+        return FSE_B200_OK;
+    }
     const char *variant = getenv("FSE_B200_DECODE64");      // development switch: "c" compact, "w" wide entries
     const bool use_wide = variant ? variant[0] == 'w' : false;   // measured: compact 0.49 ms vs wide 0.70 ms on c2
     if (p->n_states == 64 && (tlmax <= 12 || use_wide)) {

@@ -1,0 +1,238 @@
+// fse_encode128.cuh -- 128-state encode: four adjacent states per lane (see fse_kernels128.cuh).
+//
+// Per chunk of 16 rounds (2 048 symbols): pass 1 runs four independent state chains per lane from one
+// 32-bit symbol load per round and stores the quad's two merged pair fields with one 64-bit store; pass 2
+// and the placement are those of the 64-state path (32 merged pair fields per lane, lane order == stream
+// order): lane L serialises the half row (round L>>1, half L&1).
+#pragma once
+#include "fse_kernels128.cuh"
+
+namespace fsed {
+
+// element classes of a symbol index for N = 128 (cf. enc_element_checked)
+__device__ __forceinline__ void enc_element_checked128(const uint8_t *__restrict__ bsrc, int32_t i, int32_t bn, uint32_t tt_saddr,
+                                                       uint32_t &state, uint32_t &v, uint32_t &bo)
+{
+    v = 0; bo = 0;
+    if (i < 0 || i >= bn) return;
+    uint32_t sym = __ldg(bsrc + i);
+    if (i >= bn - 128) state = enc_first64(tt_saddr, sym);
+    else enc_step(tt_saddr, sym, state, v, bo);
+}
+
+__device__ void encode128_payload_warp(const uint8_t *__restrict__ bsrc, uint32_t bn, uint32_t log2, uint32_t tt_saddr,
+                                       uint32_t *fld, uint32_t *rows, uint32_t *pay, uint32_t cap_words, int lane,
+                                       uint32_t &bits_out, bool &overflow)
+{
+    const int32_t Q = (int32_t)((bn + 3) >> 2);                    // quads (4m+3 .. 4m)
+    const uint32_t kcol = (uint32_t)(Q - 1 - lane) & 31;           // my quad's stream position in a round
+    const int32_t mtop = Q - 1 - (int32_t)kcol;                    // my quad in round 0
+    const uint32_t G = (uint32_t)(Q + 31) >> 5;                    // rounds of 32 quads
+    const bool aligned4 = (((uintptr_t)bsrc) & 3) == 0;
+    uint32_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;                       // states 4*lane .. 4*lane+3
+    uint32_t cw = 0, cb = 0, wdone = 0;
+    uint32_t *myrow = rows + lane * ROW_STRIDE64;
+    uint32_t *obuf = fld;
+    overflow = false;
+    // staging tile: 16 rows x 64 pair fields; 16-byte chunk c of row r lives at c ^ (((r & 3) << 1) | (c >> 3)) (low 3 bits)
+    const uint32_t wchunk = kcol >> 1, whalf = kcol >> 4;
+    const uint32_t rrow = (uint32_t)lane >> 1, rhalf = (uint32_t)lane & 1, rkey = ((rrow & 3) << 1) | rhalf;
+
+    uint32_t sy[16];
+    auto plain = [&](uint32_t g0) -> bool { return g0 >= 16 && (uint32_t)Q >= (g0 + 16) * 32; };
+    auto fetch = [&](uint32_t g0) {
+        if (plain(g0) && aligned4) {
+            const uint32_t *p32 = reinterpret_cast<const uint32_t *>(bsrc) + (mtop - (int32_t)(g0 << 5));
+#pragma unroll
+            for (int r = 0; r < 16; r++) sy[r] = __ldg(p32 - 32 * r);
+        } else {
+#pragma unroll
+            for (int r = 0; r < 16; r++) {
+                int32_t m = mtop - (int32_t)((g0 + r) << 5);
+                uint32_t s = 0;
+                if (m >= 0) {
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        if (4 * m + k < (int32_t)bn) s |= (uint32_t)__ldg(bsrc + 4 * m + k) << (8 * k);
+                }
+                sy[r] = s;
+            }
+        }
+    };
+    fetch(0);
+    for (uint32_t g0 = 0; g0 < G; g0 += 16) {
+        if (plain(g0)) {
+#pragma unroll
+            for (int r = 0; r < 16; r++) {
+                uint32_t v3, b3, v2, b2, v1, b1, v0, b0;
+                const uint32_t x = sy[r];
+                enc_step(tt_saddr, x >> 24, s3, v3, b3);           // decreasing index order: 4m+3 first
+                enc_step(tt_saddr, (x >> 16) & 0xff, s2, v2, b2);
+                enc_step(tt_saddr, (x >> 8) & 0xff, s1, v1, b1);
+                enc_step(tt_saddr, x & 0xff, s0, v0, b0);
+                uint2 f;
+                f.x = (v3 | (v2 << b3)) | ((b3 + b2) << PAIR_LEN_SHIFT);
+                f.y = (v1 | (v0 << b1)) | ((b1 + b0) << PAIR_LEN_SHIFT);
+                const uint32_t key = ((r & 3) << 1) | whalf;
+                *reinterpret_cast<uint2 *>(fld + r * 64 + ((wchunk ^ key) << 2) + ((kcol & 1) << 1)) = f;
+            }
+        } else {
+            for (int r = 0; r < 16; r++) {
+                int32_t m = mtop - (int32_t)((g0 + r) << 5);
+                int32_t i = m < 0 ? -8 : 4 * m;
+                uint32_t v3, b3, v2, b2, v1, b1, v0, b0;
+                enc_element_checked128(bsrc, i + 3, (int32_t)bn, tt_saddr, s3, v3, b3);
+                enc_element_checked128(bsrc, i + 2, (int32_t)bn, tt_saddr, s2, v2, b2);
+                enc_element_checked128(bsrc, i + 1, (int32_t)bn, tt_saddr, s1, v1, b1);
+                enc_element_checked128(bsrc, i, (int32_t)bn, tt_saddr, s0, v0, b0);
+                uint2 f;
+                f.x = (v3 | (v2 << b3)) | ((b3 + b2) << PAIR_LEN_SHIFT);
+                f.y = (v1 | (v0 << b1)) | ((b1 + b0) << PAIR_LEN_SHIFT);
+                const uint32_t key = ((r & 3) << 1) | whalf;
+                *reinterpret_cast<uint2 *>(fld + r * 64 + ((wchunk ^ key) << 2) + ((kcol & 1) << 1)) = f;
+            }
+        }
+        if (g0 + 16 < G) fetch(g0 + 16);
+        __syncwarp();
+        // pass 2: lane L serialises half a round: 32 merged pairs that are consecutive in the stream
+        BitRow br;
+        br.init(myrow, lane == 0 ? cw : 0u, lane == 0 ? cb : 0u);
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            uint4 x = *reinterpret_cast<const uint4 *>(fld + rrow * 64 + (((rhalf << 3) | (q ^ rkey)) << 2));
+            br.put(x.x & PAIR_VAL_MASK, x.x >> PAIR_LEN_SHIFT);
+            br.put(x.y & PAIR_VAL_MASK, x.y >> PAIR_LEN_SHIFT);
+            br.put(x.z & PAIR_VAL_MASK, x.z >> PAIR_LEN_SHIFT);
+            br.put(x.w & PAIR_VAL_MASK, x.w >> PAIR_LEN_SHIFT);
+        }
+        uint32_t tot = br.finish();
+        __syncwarp();
+        uint32_t nw = warp_place(myrow, tot, obuf, 1024, lane, cw, cb, overflow);
+        __syncwarp();
+        if (wdone + nw > cap_words) { overflow = true; nw = 0; }
+        for (uint32_t j = lane; j < nw; j += 32) pay[wdone + j] = obuf[j];
+        wdone += nw;
+        __syncwarp();
+    }
+    // final states 127 .. 0 (fse.rs:248-250), then the marker bit (lib.rs:141,181):
+    // stream position L holds states 127-4L .. 124-4L, all owned by lane 31-L
+    {
+        uint32_t t3 = __shfl_sync(FULL, s3, 31 - lane), t2 = __shfl_sync(FULL, s2, 31 - lane);
+        uint32_t t1 = __shfl_sync(FULL, s1, 31 - lane), t0 = __shfl_sync(FULL, s0, 31 - lane);
+        const uint32_t mask = (1u << log2) - 1u;
+        BitRow br;
+        br.init(myrow, lane == 0 ? cw : 0u, lane == 0 ? cb : 0u);
+        br.put(t3 & mask, log2);
+        br.put(t2 & mask, log2);
+        br.put(t1 & mask, log2);
+        br.put(t0 & mask, log2);
+        if (lane == 31) br.put(1, 1);
+        uint32_t tot = br.finish();
+        __syncwarp();
+        wdone += warp_place(myrow, tot, pay + wdone, cap_words > wdone ? cap_words - wdone : 0, lane, cw, cb, overflow);
+        __syncwarp();
+    }
+    if (cb) {
+        if (wdone < cap_words) { if (lane == 0) pay[wdone] = cw; }
+        else overflow = true;
+    }
+    bits_out = wdone * 32 + cb;
+}
+
+__global__ void __launch_bounds__(512) k_encode128_blocks(EncArgs a)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    const Enc64Layout lay = enc64_layout(a.tlmax);
+    uint8_t *my = smem_raw + (size_t)warp * lay.total;
+    uint16_t *tab = reinterpret_cast<uint16_t *>(my + lay.tab);
+    uint2 *tt = reinterpret_cast<uint2 *>(my + lay.tt);
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(my + lay.work);
+    int32_t *norm = reinterpret_cast<int32_t *>(my + lay.work + 1024);
+    uint32_t *cum = reinterpret_cast<uint32_t *>(my + lay.work + 2048);
+    uint8_t *spread = my + lay.work + 3072;
+    uint32_t *fld = reinterpret_cast<uint32_t *>(my + lay.work);
+    uint32_t *rows = reinterpret_cast<uint32_t *>(my + lay.rows);
+    const uint32_t tab_saddr = (uint32_t)__cvta_generic_to_shared(tab);
+    const uint32_t tt_saddr = (uint32_t)__cvta_generic_to_shared(tt);
+    const uint32_t N = 128;
+
+    uint32_t glog2 = 0;
+    if (a.global_mode) {
+        glog2 = a.g.log2;
+        for (uint32_t i = lane; i < (1u << glog2); i += 32) tab[i] = a.g.enc_table[i];
+        for (uint32_t i = lane; i < 256; i += 32) {
+            uint2 t = a.g.enc_tt[i];
+            t.y = tab_saddr + 2u * t.y;
+            tt[i] = t;
+        }
+        __syncwarp();
+    }
+
+    for (uint32_t b = blockIdx.x * wpc + warp; b < a.nblocks; b += gridDim.x * wpc) {
+        const size_t off = (size_t)b * a.block_size;
+        const uint32_t bn = (uint32_t)min((size_t)a.block_size, a.n - off);
+        const uint8_t *bsrc = a.src + off;
+        uint8_t *bs = a.scratch + (size_t)b * a.stride;
+        uint32_t *hdr_words = reinterpret_cast<uint32_t *>(bs);
+        uint32_t *pay = reinterpret_cast<uint32_t *>(bs + HDR_RESERVE);
+        uint32_t log2 = glog2, hbytes = 0;
+        int st = ST_OK;
+
+        if (!a.global_mode) {
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 8; k++) cnt[k * 32 + lane] = a.counts[(size_t)b * 256 + k * 32 + lane];
+            __syncwarp();
+            uint32_t table_len;
+            int rc = warp_normalize(cnt, (uint64_t)bn, a.req_log2, norm, lane, log2, table_len);
+            if (rc < 0) {
+                if (table_len <= 1) {
+                    if (lane == 0) { bs[0] = 0x0E; bs[1] = 0x00; a.hlen[b] = 2; a.plen[b] = 0; a.status[b] = 2; }
+                } else if (bn <= 4) {
+                    if (lane == 0) {
+                        bs[0] = 0x0F;
+                        for (uint32_t i = 0; i < bn; i++) bs[1 + i] = bsrc[i];
+                        a.hlen[b] = 1 + bn; a.plen[b] = 0; a.status[b] = 1;
+                    }
+                } else if (lane == 0) { a.hlen[b] = 0; a.plen[b] = 0; a.status[b] = rc; }
+                continue;
+            }
+            if (bn < N) {                        // fewer symbols than states: stored raw
+                for (uint32_t i = lane; i < bn; i += 32) bs[1 + i] = bsrc[i];
+                if (lane == 0) { bs[0] = 0x0F; a.hlen[b] = 1 + bn; a.plen[b] = 0; a.status[b] = 1; }
+                continue;
+            }
+            if (log2 > a.tlmax || log2 > 13) {
+                if (lane == 0) { a.hlen[b] = 0; a.plen[b] = 0; a.status[b] = ST_UNSUPPORTED; }
+                continue;
+            }
+            uint32_t hbits = warp_ncount_write(norm, log2, table_len, rows, hdr_words, lane);
+            hbytes = (hbits + 7) >> 3;
+            warp_spread(norm, log2, table_len, spread, cum, tab, lane);
+            warp_build_encode(norm, log2, table_len, spread, cum, tab, tt, lane);
+#pragma unroll
+            for (int k = 0; k < 8; k++) {        // pre-scale find_state to a shared-memory byte address
+                uint2 t = tt[k * 32 + lane];
+                t.y = tab_saddr + 2u * t.y;
+                tt[k * 32 + lane] = t;
+            }
+            __syncwarp();
+        } else if (bn < N) {
+            for (uint32_t i = lane; i < bn; i += 32) bs[i] = bsrc[i];
+            if (lane == 0) { a.hlen[b] = bn; a.plen[b] = 0; a.status[b] = 1; }
+            continue;
+        }
+        uint32_t pbits;
+        bool ovf;
+        encode128_payload_warp(bsrc, bn, log2, tt_saddr, fld, rows, pay, a.pay_cap_words, lane, pbits, ovf);
+        if (ovf) st = ST_CAPACITY;
+        if (lane == 0) {
+            a.hlen[b] = ovf ? 0 : hbytes;
+            a.plen[b] = ovf ? 0 : (pbits + 7) >> 3;
+            a.status[b] = st;
+        }
+    }
+}
+
+}  // namespace fsed

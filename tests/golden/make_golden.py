@@ -68,7 +68,7 @@ def one(name, src, table_log=0, note=""):
     pd = M.DecodeTable(ph)
     assert [x[0] for x in pd.table] == [dt.table[i].new_state for i in range(size)]
     ent["payload"] = {}
-    for n_states in (1, 2, 4, 32, 64):
+    for n_states in (1, 2, 4, 32, 64, 128):
         if len(src) < n_states:
             continue
         pay, pbits = O.encode_payload(et, src, n_states)
