@@ -139,6 +139,63 @@ __device__ void encode128_payload_warp(const uint8_t *__restrict__ bsrc, uint32_
     bits_out = wdone * 32 + cb;
 }
 
+// warp-level byte copy with 4-byte aligned destination stores (src is 4-byte aligned)
+__device__ __forceinline__ void warp_copy_bytes(uint8_t *dst, const uint8_t *src, uint32_t len, int lane)
+{
+    uint32_t head = (uint32_t)((4 - ((uintptr_t)dst & 3)) & 3);
+    if (head > len) head = len;
+    if ((uint32_t)lane < head) dst[lane] = src[lane];
+    const uint32_t nwords = (len - head) >> 2;
+    const uint32_t *sw = reinterpret_cast<const uint32_t *>(src);
+    uint32_t *dw = reinterpret_cast<uint32_t *>(dst + head);
+    const uint32_t sh = head * 8;
+    for (uint32_t k = lane; k < nwords; k += 32) {
+        uint32_t w0 = sw[k], w1 = sh ? sw[k + 1] : 0u;
+        dw[k] = __funnelshift_r(w0, w1, sh);
+    }
+    const uint32_t t0 = head + (nwords << 2);
+    if (t0 + lane < len) dst[t0 + lane] = src[t0 + lane];
+}
+
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_volatile_u64(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.volatile.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+
+// Sum of the sizes of all blocks before b (decoupled look-back over the descriptor array).  Every earlier
+// block was handed out before b (ticket order), so its owner is running and will publish.
+__device__ __forceinline__ unsigned long long lookback_exclusive(unsigned long long *desc, uint32_t b, int lane, unsigned int *err)
+{
+    unsigned long long excl = 0;
+    long long j = (long long)b - 1;
+    uint32_t polls = 0;
+    while (j >= 0) {
+        const long long idx = j - lane;
+        unsigned long long d;
+        for (;;) {
+            d = idx >= 0 ? ld_volatile_u64(desc + idx) : 2ull;           // before block 0: prefix 0
+            if (!__any_sync(FULL, (d & 3) == 0)) break;
+            if (++polls > (1u << 22)) { if (lane == 0) atomicExch(err, 1u); return excl; }   // never hang the GPU
+            __nanosleep(64);
+        }
+        const uint32_t pm = __ballot_sync(FULL, (d & 3) == 2);
+        const int upto = pm ? (__ffs((int)pm) - 1) : 31;
+        unsigned long long v = lane <= upto ? (d >> 2) : 0ull;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+        excl += v;
+        if (pm) break;
+        j -= 32;
+    }
+    return excl;
+}
+
 __global__ void __launch_bounds__(512) k_encode128_blocks(EncArgs a)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -169,69 +226,88 @@ __global__ void __launch_bounds__(512) k_encode128_blocks(EncArgs a)
         __syncwarp();
     }
 
-    for (uint32_t b = blockIdx.x * wpc + warp; b < a.nblocks; b += gridDim.x * wpc) {
+    uint32_t bstatic = blockIdx.x * wpc + warp;
+    for (;;) {
+        uint32_t b;
+        if (a.fused) {                                       // blocks in index order, whoever is free takes the next
+            b = 0;
+            if (lane == 0) b = atomicAdd(a.ticket, 1u);
+            b = __shfl_sync(FULL, b, 0);
+        } else {
+            b = bstatic;
+            bstatic += gridDim.x * wpc;
+        }
+        if (b >= a.nblocks) break;
         const size_t off = (size_t)b * a.block_size;
         const uint32_t bn = (uint32_t)min((size_t)a.block_size, a.n - off);
         const uint8_t *bsrc = a.src + off;
         uint8_t *bs = a.scratch + (size_t)b * a.stride;
         uint32_t *hdr_words = reinterpret_cast<uint32_t *>(bs);
         uint32_t *pay = reinterpret_cast<uint32_t *>(bs + HDR_RESERVE);
-        uint32_t log2 = glog2, hbytes = 0;
+        uint32_t log2 = glog2;
+        uint32_t hl = 0, pl = 0;                             // header / payload bytes of this block (warp uniform)
         int st = ST_OK;
-
-        if (!a.global_mode) {
-            __syncwarp();
+        __syncwarp();
+        do {
+            if (!a.global_mode) {
 #pragma unroll
-            for (int k = 0; k < 8; k++) cnt[k * 32 + lane] = a.counts[(size_t)b * 256 + k * 32 + lane];
-            __syncwarp();
-            uint32_t table_len;
-            int rc = warp_normalize(cnt, (uint64_t)bn, a.req_log2, norm, lane, log2, table_len);
-            if (rc < 0) {
-                if (table_len <= 1) {
-                    if (lane == 0) { bs[0] = 0x0E; bs[1] = 0x00; a.hlen[b] = 2; a.plen[b] = 0; a.status[b] = 2; }
-                } else if (bn <= 4) {
-                    if (lane == 0) {
-                        bs[0] = 0x0F;
-                        for (uint32_t i = 0; i < bn; i++) bs[1 + i] = bsrc[i];
-                        a.hlen[b] = 1 + bn; a.plen[b] = 0; a.status[b] = 1;
-                    }
-                } else if (lane == 0) { a.hlen[b] = 0; a.plen[b] = 0; a.status[b] = rc; }
-                continue;
-            }
-            if (bn < N) {                        // fewer symbols than states: stored raw
-                for (uint32_t i = lane; i < bn; i += 32) bs[1 + i] = bsrc[i];
-                if (lane == 0) { bs[0] = 0x0F; a.hlen[b] = 1 + bn; a.plen[b] = 0; a.status[b] = 1; }
-                continue;
-            }
-            if (log2 > a.tlmax || log2 > 13) {
-                if (lane == 0) { a.hlen[b] = 0; a.plen[b] = 0; a.status[b] = ST_UNSUPPORTED; }
-                continue;
-            }
-            uint32_t hbits = warp_ncount_write(norm, log2, table_len, rows, hdr_words, lane);
-            hbytes = (hbits + 7) >> 3;
-            warp_spread(norm, log2, table_len, spread, cum, tab, lane);
-            warp_build_encode(norm, log2, table_len, spread, cum, tab, tt, lane);
+                for (int k = 0; k < 8; k++) cnt[k * 32 + lane] = a.counts[(size_t)b * 256 + k * 32 + lane];
+                __syncwarp();
+                uint32_t table_len;
+                int rc = warp_normalize(cnt, (uint64_t)bn, a.req_log2, norm, lane, log2, table_len);
+                if (rc < 0) {
+                    // blocks the reference panics on: stored with an escape byte (include/fse_b200.h)
+                    if (table_len <= 1) { if (lane == 0) { bs[0] = 0x0E; bs[1] = 0x00; } hl = 2; st = 2; }
+                    else if (bn <= 4) { if ((uint32_t)lane < bn) bs[1 + lane] = bsrc[lane]; if (lane == 0) bs[0] = 0x0F; hl = 1 + bn; st = 1; }
+                    else st = rc;
+                    break;
+                }
+                if (bn < N) {                                // fewer symbols than states: stored raw
+                    for (uint32_t i = lane; i < bn; i += 32) bs[1 + i] = bsrc[i];
+                    if (lane == 0) bs[0] = 0x0F;
+                    hl = 1 + bn; st = 1;
+                    break;
+                }
+                if (log2 > a.tlmax || log2 > 13) { st = ST_UNSUPPORTED; break; }
+                uint32_t hbits = warp_ncount_write(norm, log2, table_len, rows, hdr_words, lane);
+                hl = (hbits + 7) >> 3;
+                warp_spread(norm, log2, table_len, spread, cum, tab, lane);
+                warp_build_encode(norm, log2, table_len, spread, cum, tab, tt, lane);
 #pragma unroll
-            for (int k = 0; k < 8; k++) {        // pre-scale find_state to a shared-memory byte address
-                uint2 t = tt[k * 32 + lane];
-                t.y = tab_saddr + 2u * t.y;
-                tt[k * 32 + lane] = t;
+                for (int k = 0; k < 8; k++) {                // pre-scale find_state to a shared-memory byte address
+                    uint2 t = tt[k * 32 + lane];
+                    t.y = tab_saddr + 2u * t.y;
+                    tt[k * 32 + lane] = t;
+                }
+                __syncwarp();
+            } else if (bn < N) {                             // global mode: a short tail is stored raw, no escape
+                for (uint32_t i = lane; i < bn; i += 32) bs[i] = bsrc[i];
+                hl = bn; st = 1;
+                break;
             }
-            __syncwarp();
-        } else if (bn < N) {
-            for (uint32_t i = lane; i < bn; i += 32) bs[i] = bsrc[i];
-            if (lane == 0) { a.hlen[b] = bn; a.plen[b] = 0; a.status[b] = 1; }
+            uint32_t pbits;
+            bool ovf;
+            encode128_payload_warp(bsrc, bn, log2, tt_saddr, fld, rows, pay, a.pay_cap_words, lane, pbits, ovf);
+            if (ovf) { st = ST_CAPACITY; hl = 0; pl = 0; }
+            else pl = (pbits + 7) >> 3;
+        } while (0);
+        __syncwarp();
+        if (lane == 0) a.status[b] = st;
+        if (!a.fused) {
+            if (lane == 0) { a.hlen[b] = hl; a.plen[b] = pl; }
             continue;
         }
-        uint32_t pbits;
-        bool ovf;
-        encode128_payload_warp(bsrc, bn, log2, tt_saddr, fld, rows, pay, a.pay_cap_words, lane, pbits, ovf);
-        if (ovf) st = ST_CAPACITY;
+        const unsigned long long size = (unsigned long long)hl + pl;
+        if (lane == 0) st_volatile_u64(a.desc + b, (size << 2) | 1ull);
+        const unsigned long long excl = lookback_exclusive(a.desc, b, lane, a.ticket + 1);
         if (lane == 0) {
-            a.hlen[b] = ovf ? 0 : hbytes;
-            a.plen[b] = ovf ? 0 : (pbits + 7) >> 3;
-            a.status[b] = st;
+            st_volatile_u64(a.desc + b, ((excl + size) << 2) | 2ull);
+            a.offsets[b] = excl;
+            if (b == a.nblocks - 1) a.offsets[a.nblocks] = excl + size;
         }
+        __syncwarp();
+        warp_copy_bytes(a.dst + excl, bs, hl, lane);
+        warp_copy_bytes(a.dst + excl + hl, bs + HDR_RESERVE, pl, lane);
     }
 }
 

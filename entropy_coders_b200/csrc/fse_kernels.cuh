@@ -167,6 +167,14 @@ struct EncArgs {
     int32_t *status;
     GlobalTable g;
     int global_mode;
+    // fused placement (128-state kernel): blocks are handed out by a ticket counter in index order, each warp
+    // publishes its block's size, obtains the sum of all earlier sizes by decoupled look-back and copies its
+    // own (L2-hot) stream to its final position: no separate scan + gather pass
+    int fused;
+    unsigned long long *desc;     // [nblocks], zeroed: value << 2 | status (1 = own size, 2 = inclusive prefix)
+    unsigned int *ticket;         // zeroed; ticket[1] is an error flag (look-back gave up)
+    uint8_t *dst;
+    unsigned long long *offsets;  // [nblocks + 1]
 };
 
 // fse.rs:210-218
