@@ -2,6 +2,7 @@
 // all arithmetic runs in the kernels of fse_kernels.cuh.  There is no CPU fallback.
 #include "../../include/fse_b200.h"
 #include "fse_encode128.cuh"
+#include "fse_decode128c.cuh"
 #include "fse_hist16.cuh"
 
 #include <algorithm>
@@ -214,6 +215,7 @@ int fse_b200_create(int device, void *stream, fse_b200_ctx **out)
     cudaFuncSetAttribute(k_decode64c_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
     cudaFuncSetAttribute(k_decode64w_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
     cudaFuncSetAttribute(k_decode128_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
+    cudaFuncSetAttribute(k_decode128c_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
     cudaFuncSetAttribute(k_encode128_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
     cudaFuncSetAttribute(k_build_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
     cudaError_t e = cudaGetLastError();
@@ -610,7 +612,9 @@ int fse_b200_decompress_blocks_async(fse_b200_ctx *ctx, const uint8_t *d_comp, s
     if (p->n_states == 128) {
         if (tlmax > 13) return fail(ctx, FSE_B200_ERR_UNSUPPORTED, "n_states 128 needs table_log <= 13");
         const size_t half = (ctx->smem_per_sm - 2048) / 2 - 1024;
-        const size_t per_warp = dec64w_layout(tlmax).total;
+        const char *dv = getenv("FSE_B200_DECODE128");          // development switch: "c" compact tables, "w" wide entries
+        const bool compact = tlmax <= 12 && !(dv && dv[0] == 'w');
+        const size_t per_warp = compact ? dec64c_layout(tlmax).total : dec64w_layout(tlmax).total;
         int wpc = pick_warps(nblocks, ctx->num_sms * 2, per_warp, std::min(half, ctx->smem_optin), 16);
         int ctas = 2;
         if (wpc < 1) { wpc = pick_warps(nblocks, ctx->num_sms, per_warp, ctx->smem_optin, 16); ctas = 1; }
@@ -618,7 +622,8 @@ int fse_b200_decompress_blocks_async(fse_b200_ctx *ctx, const uint8_t *d_comp, s
         if (const char *o = getenv("FSE_B200_WPC")) wpc = atoi(o);   // development override
         int grid = (int)std::min<size_t>((nblocks + wpc - 1) / wpc, (size_t)ctx->num_sms * ctas);
         Timed t(ctx, FSE_B200_K_DECODE);
-        k_decode128_blocks<<<grid, wpc * 32, (size_t)wpc * per_warp, ctx->stream>>>(a);
+        if (compact) k_decode128c_blocks<<<grid, wpc * 32, (size_t)wpc * per_warp, ctx->stream>>>(a);
+        else k_decode128_blocks<<<grid, wpc * 32, (size_t)wpc * per_warp, ctx->stream>>>(a);
         CK(cudaGetLastError());
         return FSE_B200_OK;
     }

@@ -1,0 +1,206 @@
+// fse_decode128c.cuh -- 128-state decode over the compact tables of fse_decode64c.cuh (u16 entry + symbol
+// array, 8 KiB per warp at table_log 11 = 28 blocks in flight per SM); table_log <= 12.
+#pragma once
+#include "fse_kernels128.cuh"
+
+namespace fsed {
+
+__device__ __forceinline__ uint32_t lds_u8(uint32_t saddr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+
+__global__ void __launch_bounds__(512, 2) k_decode128c_blocks(DecArgs a)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    const Dec64cLayout lay = dec64c_layout(a.tlmax);
+    uint8_t *my = smem_raw + (size_t)warp * lay.total;
+    uint16_t *tab = reinterpret_cast<uint16_t *>(my + lay.tab);
+    uint8_t *sym = my + lay.sym;                            // the spread = the symbol of every cell
+    int32_t *norm = reinterpret_cast<int32_t *>(my + lay.scratch);
+    uint32_t *ctr = reinterpret_cast<uint32_t *>(my + lay.scratch + 1024);
+    uint32_t *ring = reinterpret_cast<uint32_t *>(my + lay.scratch);   // 256 words + 2 mirror words
+    const uint32_t tab_saddr = (uint32_t)__cvta_generic_to_shared(tab);
+    const uint32_t sym_saddr = (uint32_t)__cvta_generic_to_shared(sym);
+    const uint32_t N = 128;
+
+    uint32_t glog2 = 0;
+    if (a.global_mode) {
+        glog2 = a.g.log2;
+        for (uint32_t i = lane; i < (1u << glog2); i += 32) {
+            uint32_t e = a.g.dec_table[i];
+            tab[i] = (uint16_t)((e & 0xfffu) | ((e >> 24) << 12));
+            sym[i] = (uint8_t)(e >> 16);
+        }
+        __syncwarp();
+    }
+
+    for (uint32_t b = blockIdx.x * wpc + warp; b < a.nblocks; b += gridDim.x * wpc) {
+        const size_t off = (size_t)b * a.block_size;
+        const uint32_t bn = (uint32_t)min((size_t)a.block_size, a.n - off);
+        uint8_t *out = a.dst + off;
+        const unsigned long long o0 = a.offsets[b], o1 = a.offsets[b + 1];
+        int st = ST_OK;
+        if (o1 < o0 || o1 > a.comp_bytes || o1 - o0 > 0xffffffffull) {
+            if (lane == 0) a.status[b] = ST_LENGTH;
+            continue;
+        }
+        const uint8_t *cs = a.comp + o0;
+        const uint32_t clen = (uint32_t)(o1 - o0);
+        uint32_t log2 = glog2, consumed = 0;
+        __syncwarp();
+        if (!a.global_mode) {
+            if (clen == 0) { if (lane == 0) a.status[b] = ST_PANIC; continue; }
+            uint32_t first = cs[0];
+            if ((first & 0x0f) == 0x0f) {
+                if (clen != 1 + bn) { if (lane == 0) a.status[b] = ST_LENGTH; continue; }
+                for (uint32_t i = lane; i < bn; i += 32) out[i] = cs[1 + i];
+                if (lane == 0) a.status[b] = 1;
+                continue;
+            }
+            if ((first & 0x0f) == 0x0e) {
+                if (clen != 2) { if (lane == 0) a.status[b] = ST_LENGTH; continue; }
+                uint8_t v = cs[1];
+                for (uint32_t i = lane; i < bn; i += 32) out[i] = v;
+                if (lane == 0) a.status[b] = 2;
+                continue;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) norm[k * 32 + lane] = 0;
+            __syncwarp();
+            uint32_t table_len = 0;
+            int rc = 0;
+            if (lane == 0) rc = ncount_read_serial(cs, clen, norm, log2, table_len, consumed);
+            rc = __shfl_sync(FULL, rc, 0);
+            log2 = __shfl_sync(FULL, log2, 0);
+            table_len = __shfl_sync(FULL, table_len, 0);
+            consumed = __shfl_sync(FULL, consumed, 0);
+            __syncwarp();
+            if (rc < 0) { if (lane == 0) a.status[b] = rc; continue; }
+            if (log2 > a.tlmax || log2 > 12) { if (lane == 0) a.status[b] = ST_UNSUPPORTED; continue; }
+            warp_spread(norm, log2, table_len, sym, ctr, tab, lane);
+            warp_build_decode16(norm, log2, table_len, sym, ctr, tab, lane);
+        } else if (bn < N) {
+            if (clen != bn) { if (lane == 0) a.status[b] = ST_LENGTH; continue; }
+            for (uint32_t i = lane; i < bn; i += 32) out[i] = cs[i];
+            if (lane == 0) a.status[b] = 1;
+            continue;
+        }
+        if (bn < N) { if (lane == 0) a.status[b] = ST_LENGTH; continue; }
+        const uint8_t *pay = cs + consumed;
+        const uint32_t plen = clen - consumed;
+        if (plen == 0 || pay[plen - 1] == 0) { if (lane == 0) a.status[b] = ST_NO_MARKER; continue; }
+        const uint32_t bias = (uint32_t)((uintptr_t)pay & 3);
+        const uint32_t *origin = reinterpret_cast<const uint32_t *>(pay - bias);
+        uint32_t cur = (plen - 1) * 8 + ilog2u(pay[plen - 1]) + 8 * bias;
+        const uint32_t floor_bits = 8 * bias;
+        if (cur - floor_bits < N * log2) { if (lane == 0) a.status[b] = ST_LENGTH; continue; }
+        const uint32_t topq = cur >> 5;
+        uint32_t lowq = (topq & ~127u) >= 128 ? (topq & ~127u) - 128 : 0;
+        __syncwarp();                                       // the build scratch becomes the ring
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            uint32_t w = lowq + lane + 32 * k;
+            if (w <= topq) {
+                uint32_t x = __ldg(origin + w);
+                ring[w & 255] = x;
+                if ((w & 255) < 2) ring[256 + (w & 255)] = x;   // mirror: ring[256..257] == ring[0..1]
+            }
+        }
+        uint32_t pre[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) pre[k] = (lowq >= 128) ? __ldg(origin + lowq - 128 + lane + 32 * k) : 0u;
+        __syncwarp();
+        const uint32_t ring_saddr = (uint32_t)__cvta_generic_to_shared(ring);
+        // up to 52 bits at stream position q (three ring words, 64-bit funnel)
+        auto ring_bits64 = [&](uint32_t q) -> uint64_t {
+            uint32_t ad = ring_saddr + ((q >> 3) & 0x3fcu);
+            uint32_t w0, w1, w2;
+            asm volatile("ld.shared.u32 %0, [%3];\n\tld.shared.u32 %1, [%3+4];\n\tld.shared.u32 %2, [%3+8];"
+                         : "=r"(w0), "=r"(w1), "=r"(w2) : "r"(ad));
+            uint32_t s = q & 31;
+            return ((uint64_t)__funnelshift_r(w1, w2, s) << 32) | __funnelshift_r(w0, w1, s);
+        };
+        auto refill = [&]() {
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 4; k++) ring[(lowq - 128 + lane + 32 * k) & 255] = pre[k];
+            if (lane < 2 && ((lowq - 128) & 255) == 0) ring[256 + lane] = pre[0];
+            lowq -= 128;
+#pragma unroll
+            for (int k = 0; k < 4; k++) pre[k] = (lowq >= 128) ? __ldg(origin + lowq - 128 + lane + 32 * k) : 0u;
+            __syncwarp();
+        };
+        // Decoder::new, fse.rs:349-352: states are read 0, 1, 2, ... from the top of the stack
+        uint32_t s0, s1, s2, s3;
+        {
+            const uint32_t m = (1u << log2) - 1u;
+            uint64_t w = ring_bits64(cur - (4 * lane + 4) * log2);
+            s3 = (uint32_t)w & m;
+            s2 = (uint32_t)(w >> log2) & m;
+            s1 = (uint32_t)(w >> (2 * log2)) & m;
+            s0 = (uint32_t)(w >> (3 * log2)) & m;
+        }
+        cur -= N * log2;
+        const uint32_t body = bn - N;
+        const bool out_aligned = (((uintptr_t)out) & 3) == 0;
+        bool bad = false;
+        uint32_t i0 = 0;
+        for (; i0 + 128 <= body; i0 += 128) {
+            if ((cur >> 5) < lowq + 56 && lowq) refill();   // a round takes at most 52 words
+            uint32_t e0 = lds_u16(tab_saddr + s0 * 2), e1 = lds_u16(tab_saddr + s1 * 2);   // fse.rs:363-373, four chains
+            uint32_t e2 = lds_u16(tab_saddr + s2 * 2), e3 = lds_u16(tab_saddr + s3 * 2);
+            uint32_t y0 = lds_u8(sym_saddr + s0), y1 = lds_u8(sym_saddr + s1), y2 = lds_u8(sym_saddr + s2), y3 = lds_u8(sym_saddr + s3);
+            uint32_t n0 = e0 >> 12, n1 = e1 >> 12, n2 = e2 >> 12, n3 = e3 >> 12;
+            uint32_t n23 = n2 + n3, n123 = n1 + n23, nbs = n0 + n123;
+            uint32_t incl = warp_incl_add_pred(nbs);
+            uint64_t w = ring_bits64(cur - incl);           // state 4l's bits are the uppermost of the lane's window
+            uint32_t tot = __shfl_sync(FULL, incl, 31);
+            if (tot > cur - floor_bits) { bad = true; break; }
+            s0 = (e0 & 0xfffu) + ((uint32_t)(w >> n123) & ~(0xffffffffu << n0));
+            s1 = (e1 & 0xfffu) + ((uint32_t)(w >> n23) & ~(0xffffffffu << n1));
+            s2 = (e2 & 0xfffu) + ((uint32_t)(w >> n3) & ~(0xffffffffu << n2));
+            s3 = (e3 & 0xfffu) + ((uint32_t)w & ~(0xffffffffu << n3));
+            uint32_t sy = y0 | (y1 << 8) | (y2 << 16) | (y3 << 24);
+            if (out_aligned) *reinterpret_cast<uint32_t *>(out + i0 + 4 * lane) = sy;
+            else {
+                out[i0 + 4 * lane] = (uint8_t)sy; out[i0 + 4 * lane + 1] = (uint8_t)(sy >> 8);
+                out[i0 + 4 * lane + 2] = (uint8_t)(sy >> 16); out[i0 + 4 * lane + 3] = (uint8_t)(sy >> 24);
+            }
+            cur -= tot;
+        }
+        if (!bad && i0 < body) {                            // last partial round
+            if ((cur >> 5) < lowq + 56 && lowq) refill();
+            uint32_t ia = i0 + 4 * lane;
+            uint32_t e0 = tab[s0], e1 = tab[s1], e2 = tab[s2], e3 = tab[s3];
+            uint32_t n0 = ia < body ? (e0 >> 12) : 0u, n1 = ia + 1 < body ? (e1 >> 12) : 0u;
+            uint32_t n2 = ia + 2 < body ? (e2 >> 12) : 0u, n3 = ia + 3 < body ? (e3 >> 12) : 0u;
+            uint32_t n23 = n2 + n3, n123 = n1 + n23, nbs = n0 + n123;
+            uint32_t incl = warp_incl_add_pred(nbs);
+            uint32_t tot = __shfl_sync(FULL, incl, 31);
+            if (tot > cur - floor_bits) bad = true;
+            else {
+                uint64_t w = ring_bits64(cur - incl);
+                if (ia < body) { out[ia] = sym[s0]; s0 = (e0 & 0xfffu) + ((uint32_t)(w >> n123) & ~(0xffffffffu << n0)); }
+                if (ia + 1 < body) { out[ia + 1] = sym[s1]; s1 = (e1 & 0xfffu) + ((uint32_t)(w >> n23) & ~(0xffffffffu << n1)); }
+                if (ia + 2 < body) { out[ia + 2] = sym[s2]; s2 = (e2 & 0xfffu) + ((uint32_t)(w >> n3) & ~(0xffffffffu << n2)); }
+                if (ia + 3 < body) { out[ia + 3] = sym[s3]; s3 = (e3 & 0xfffu) + ((uint32_t)w & ~(0xffffffffu << n3)); }
+                cur -= tot;
+            }
+        }
+        if (!bad) {                                         // Decoder::finish, fse.rs:383-385: i in [body, bn), state i % 128
+            out[body + ((4 * lane - body) & 127)] = sym[s0];
+            out[body + ((4 * lane + 1 - body) & 127)] = sym[s1];
+            out[body + ((4 * lane + 2 - body) & 127)] = sym[s2];
+            out[body + ((4 * lane + 3 - body) & 127)] = sym[s3];
+        }
+        cur -= floor_bits;
+        if (bad || cur != 0) st = ST_LENGTH;
+        if (lane == 0) a.status[b] = st;
+    }
+}
+
+}  // namespace fsed

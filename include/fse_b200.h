@@ -74,7 +74,7 @@ typedef struct {
     uint32_t block_size;  /* bytes per block (> 0) */
     uint32_t table_log;   /* 0 = Histogram::optimal_log2 per table (src/histogram.rs:264-277); else the
                              value handed to Histogram::normalize (src/histogram.rs:95), 5..15 */
-    uint32_t n_states;    /* interleaved states per block: 1, 2, 4, 8, 16, 32 or 64 (64: table_log <= 13) */
+    uint32_t n_states;    /* interleaved states per block: 1, 2, 4, 8, 16, 32, 64 or 128 (64 / 128: table_log <= 13) */
     uint32_t table_mode;  /* FSE_B200_TABLE_PER_BLOCK or FSE_B200_TABLE_GLOBAL */
 } fse_b200_params;
 
