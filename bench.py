@@ -272,8 +272,8 @@ def run_ours(args, wl):
     alg_bytes = nbytes + total
     achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this
-    # workload (profiles/r1_ncu_full_c2_n64.txt); only meaningful for the configuration that was profiled
-    traffic = {"encode": 273.05e6 + 141.99e6, "decode": 178.01e6 + 226.23e6}[dom] if (wl == "c2" and N_STATES == 64) else None
+    # workload (profiles/r1_ncu_full_c2_n128.txt); only meaningful for the configuration that was profiled
+    traffic = {"encode": 273.04e6 + 141.73e6, "decode": 178.26e6 + 219.60e6}[dom] if (wl == "c2" and N_STATES == 128) else None
 
     # e2e: host buffers through the host entry points, copies inside the timed region (rank-local data)
     e2e = None
@@ -330,7 +330,7 @@ def run_ours(args, wl):
             "encode_GBps": nbytes / (enc_ms * 1e-3) / 1e9, "decode_GBps": nbytes / (dec_ms * 1e-3) / 1e9,
             "compressed_ratio": total / nbytes,
             "kernel_ms_per_step": {k: tm[k][0] / args.steps for k in tm},
-            "roofline": {"bound": "hbm", "kernel": {"encode": "k_encode64_blocks", "decode": "k_decode64c_blocks"}[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": {"encode": "k_encode128_blocks", "decode": "k_decode128c_blocks"}[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "note": "N + C per launch (uncompressed + compressed bytes of one rank) / mean launch time of the dominant kernel"},
