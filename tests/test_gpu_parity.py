@@ -552,3 +552,49 @@ def test_argument_errors(ctx):
     with pytest.raises(E.FseError):
         fresh.compress_blocks(src, 65536, 11, 32, table_mode=1)         # global table not installed
     fresh.close()
+
+
+def _structured(rng, n, style):
+    if style == 0:      # long runs
+        out = np.repeat(rng.integers(0, 256, n // 37 + 1, dtype=np.uint8), 37)[:n]
+    elif style == 1:    # one dominant symbol (p ~ 0.99): most transitions cost 0 bits
+        out = np.where(rng.random(n) < 0.99, 65, rng.integers(0, 256, n)).astype(np.uint8)
+    elif style == 2:    # two symbols
+        out = rng.integers(0, 2, n, dtype=np.uint8) * 200 + 3
+    elif style == 3:    # sawtooth over the whole alphabet
+        out = (np.arange(n) % 251).astype(np.uint8)
+    elif style == 4:    # sparse alphabet with big holes (zero runs in the header)
+        out = rng.choice(np.array([0, 1, 30, 31, 32, 100, 200, 255], dtype=np.uint8), n)
+    else:               # mixture of segments
+        out = np.concatenate([O.generate(k, int(rng.integers(1 << 30)), n // 3 + 1) for k in ("geo", "uniform", "few")])[:n]
+    return np.ascontiguousarray(out)
+
+
+def test_randomised_differential(ctx):
+    """seeded sweep over data styles, block sizes, state counts and table_log: every block either is the
+    oracle's bytes or is one the reference panics on (then it carries an escape); decode always round-trips"""
+    rng = np.random.default_rng(20261018)
+    checked = 0
+    for trial in range(48):
+        n_states = int(rng.choice([1, 2, 4, 8, 16, 32, 64, 128]))
+        bs = int(rng.choice([130, 257, 1000, 4096, 5000, 20000, 65536]))
+        if n_states <= 2:
+            bs = min(bs, 5000)                              # the one-lane paths are for parity, not speed
+        n = int(bs * rng.integers(1, 5) + rng.integers(0, bs))
+        tl = int(rng.choice([0, 0, 5, 7, 9, 11, 12, 13]))
+        src = _structured(rng, n, trial % 6)
+        blocks, st, (d, off, total) = gpu_blocks(ctx, src, bs, tl, n_states)
+        for b, g in enumerate(blocks):
+            blk = src[b * bs:(b + 1) * bs]
+            try:
+                e = O.compress_n(blk, tl, n_states)[0]
+            except ValueError:
+                e = None
+            if e is None:
+                assert st[b] in (1, 2) and g[0] in (0x0E, 0x0F), (trial, b, st[b])
+            else:
+                assert st[b] == 0 and g == e, (trial, b, n_states, bs, tl)
+                checked += 1
+        out, dst_ = ctx.decompress_blocks(d, total, dev(ctx, off), n, bs, tl, n_states)
+        assert (dst_.cpu().numpy() >= 0).all() and np.array_equal(out.cpu().numpy(), src), (trial, n_states, bs, tl)
+    assert checked > 100
