@@ -268,6 +268,38 @@ class Context:
         return dst[:n], status[:nb]
 
 
+    # ------------------------------------------------------------------ self-describing frame
+    def frame_compress(self, src, block_size=65536, table_log=0, n_states=128, table_mode=TABLE_PER_BLOCK):
+        """host uint8 array -> numpy uint8 frame (parameters, offsets and payload in one buffer)"""
+        import numpy as np
+        p = self.params(block_size, table_log, n_states, table_mode)
+        n = int(src.size if hasattr(src, "size") and not callable(src.size) else src.numel())
+        frame = np.empty(int(self._L.fse_b200_frame_bound(n, C.byref(p))), dtype=np.uint8)
+        nbytes = C.c_size_t()
+        rc = self._L.fse_b200_frame_compress_host(self._h, _host_ptr(src), n, C.byref(p), _host_ptr(frame), frame.size, C.byref(nbytes))
+        if rc not in (0, -11):
+            self._ck(rc)
+        return frame[: nbytes.value]
+
+    def frame_info(self, frame):
+        p = Params()
+        n = C.c_size_t()
+        rc = self._L.fse_b200_frame_info(_host_ptr(frame), _host_len(frame), C.byref(p), C.byref(n))
+        if rc != 0:
+            raise FseError(rc, "bad frame")
+        return {"block_size": p.block_size, "table_log": p.table_log, "n_states": p.n_states, "table_mode": p.table_mode, "n": n.value}
+
+    def frame_decompress(self, frame):
+        import numpy as np
+        n = self.frame_info(frame)["n"]
+        dst = np.empty(max(n, 1), dtype=np.uint8)
+        got = C.c_size_t()
+        rc = self._L.fse_b200_frame_decompress_host(self._h, _host_ptr(frame), _host_len(frame), _host_ptr(dst), dst.size, C.byref(got))
+        if rc not in (0, -11):
+            self._ck(rc)
+        return dst[: got.value]
+
+
 def _host_ptr(a):
     if hasattr(a, "ctypes"):
         return C.c_void_p(a.ctypes.data)

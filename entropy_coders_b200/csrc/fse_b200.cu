@@ -893,6 +893,110 @@ int fse_b200_decompress_host(fse_b200_ctx *ctx, const uint8_t *h_comp, size_t co
     return worst_status(st.data(), nblocks);
 }
 
+// ---------------------------------------------------------------------------------- frame (container)
+
+namespace {
+struct FrameHeader {            // 48 bytes, little endian
+    uint32_t magic;
+    uint16_t version, n_states;
+    uint32_t block_size, table_log, table_mode, global_header_bytes;
+    uint64_t n, nblocks, payload_bytes;
+};
+static_assert(sizeof(FrameHeader) == 48, "frame header layout");
+size_t pad8(size_t v) { return (v + 7) & ~(size_t)7; }
+}  // namespace
+
+size_t fse_b200_frame_bound(size_t n, const fse_b200_params *p)
+{
+    if (!p || !p->block_size) return 0;
+    size_t nb = fse_b200_num_blocks(n, p->block_size);
+    return sizeof(FrameHeader) + 512 + (nb + 1) * 8 + fse_b200_compress_blocks_bound(n, p);
+}
+
+int fse_b200_frame_info(const uint8_t *h_frame, size_t frame_bytes, fse_b200_params *p_out, size_t *n_out)
+{
+    if (!h_frame || frame_bytes < sizeof(FrameHeader)) return FSE_B200_ERR_ARG;
+    FrameHeader h;
+    memcpy(&h, h_frame, sizeof(h));
+    if (h.magic != FSE_B200_FRAME_MAGIC || h.version != 1) return FSE_B200_ERR_ARG;
+    if (h.block_size == 0 || h.nblocks != fse_b200_num_blocks(h.n, h.block_size) || h.global_header_bytes > 512) return FSE_B200_ERR_ARG;
+    size_t need = sizeof(FrameHeader) + pad8(h.global_header_bytes) + (h.nblocks + 1) * 8 + h.payload_bytes;
+    if (need > frame_bytes) return FSE_B200_ERR_CAPACITY;
+    if (p_out) { p_out->block_size = h.block_size; p_out->table_log = h.table_log; p_out->n_states = h.n_states; p_out->table_mode = h.table_mode; }
+    if (n_out) *n_out = h.n;
+    return FSE_B200_OK;
+}
+
+int fse_b200_frame_compress_host(fse_b200_ctx *ctx, const uint8_t *h_src, size_t n, const fse_b200_params *p,
+                                 uint8_t *h_frame, size_t frame_cap, size_t *h_frame_bytes)
+{
+    int rc = check_params(ctx, p);
+    if (rc) return rc;
+    if ((!h_src && n) || !h_frame || !h_frame_bytes) return fail(ctx, FSE_B200_ERR_ARG, "frame_compress_host: null pointer");
+    CK(cudaSetDevice(ctx->device));
+    const size_t nb = fse_b200_num_blocks(n, p->block_size);
+    FrameHeader h;
+    memset(&h, 0, sizeof(h));
+    h.magic = FSE_B200_FRAME_MAGIC; h.version = 1; h.n_states = (uint16_t)p->n_states;
+    h.block_size = p->block_size; h.table_log = p->table_log; h.table_mode = p->table_mode;
+    h.n = n; h.nblocks = nb;
+    uint8_t ghdr[512];
+    size_t gbytes = 0;
+    if (p->table_mode == FSE_B200_TABLE_GLOBAL) {
+        // one table for the whole frame: histogram of the input on the device, normalise, keep the header
+        CK(ctx->stage_in.reserve(n + 16));
+        CK(ctx->g_meta.reserve(64));
+        CK(ctx->misc.reserve(256 * 8 + 16));
+        CK(cudaMemcpyAsync(ctx->stage_in.p, h_src, n, cudaMemcpyHostToDevice, ctx->stream));
+        rc = hist_global_async(ctx, ctx->stage_in.as<uint8_t>(), n, ctx->misc.as<uint64_t>());
+        if (rc) return rc;
+        gbytes = sizeof(ghdr);
+        uint32_t l2 = 0;
+        rc = fse_b200_set_global_table(ctx, ctx->misc.as<uint64_t>(), p->table_log, ghdr, &gbytes, &l2);
+        if (rc) return rc;
+        h.global_header_bytes = (uint32_t)gbytes;
+    }
+    const size_t off_pos = sizeof(FrameHeader) + pad8(gbytes);
+    const size_t pay_pos = off_pos + (nb + 1) * 8;
+    if (frame_cap < pay_pos) return fail(ctx, FSE_B200_ERR_CAPACITY, "frame_compress_host: frame_cap too small");
+    std::vector<uint64_t> off(nb + 1);
+    uint64_t total = 0;
+    rc = fse_b200_compress_host(ctx, h_src, n, p, h_frame + pay_pos, frame_cap - pay_pos, off.data(), nullptr, &total);
+    if (rc != FSE_B200_OK && rc != FSE_B200_ERR_BLOCK) return rc;
+    h.payload_bytes = total;
+    memcpy(h_frame, &h, sizeof(h));
+    if (gbytes) { memset(h_frame + sizeof(FrameHeader), 0, pad8(gbytes)); memcpy(h_frame + sizeof(FrameHeader), ghdr, gbytes); }
+    memcpy(h_frame + off_pos, off.data(), (nb + 1) * 8);
+    *h_frame_bytes = pay_pos + total;
+    return rc;
+}
+
+int fse_b200_frame_decompress_host(fse_b200_ctx *ctx, const uint8_t *h_frame, size_t frame_bytes, uint8_t *h_dst,
+                                   size_t dst_cap, size_t *h_n)
+{
+    if (!ctx || !h_n) return FSE_B200_ERR_ARG;
+    fse_b200_params p;
+    size_t n = 0;
+    int rc = fse_b200_frame_info(h_frame, frame_bytes, &p, &n);
+    if (rc) return fail(ctx, rc, "frame_decompress_host: bad frame");
+    rc = check_params(ctx, &p);
+    if (rc) return rc;
+    if (n > dst_cap || (!h_dst && n)) return fail(ctx, FSE_B200_ERR_CAPACITY, "frame_decompress_host: dst_cap too small");
+    FrameHeader h;
+    memcpy(&h, h_frame, sizeof(h));
+    if (p.table_mode == FSE_B200_TABLE_GLOBAL) {
+        uint32_t l2 = 0;
+        rc = fse_b200_set_global_table_from_header(ctx, h_frame + sizeof(FrameHeader), h.global_header_bytes, &l2);
+        if (rc) return rc;
+    }
+    const size_t off_pos = sizeof(FrameHeader) + pad8(h.global_header_bytes);
+    std::vector<uint64_t> off(h.nblocks + 1);
+    memcpy(off.data(), h_frame + off_pos, (h.nblocks + 1) * 8);     // the frame may be unaligned
+    if (off[h.nblocks] != h.payload_bytes) return fail(ctx, FSE_B200_ERR_ARG, "frame_decompress_host: offsets do not match payload size");
+    *h_n = n;
+    return fse_b200_decompress_host(ctx, h_frame + off_pos + (h.nblocks + 1) * 8, h.payload_bytes, off.data(), h.nblocks, &p, h_dst, n, nullptr);
+}
+
 // ---------------------------------------------------------------------------------- generators
 
 static uint32_t build_lut(int kind, std::vector<uint8_t> &lut)

@@ -212,6 +212,23 @@ int fse_b200_decompress_host(fse_b200_ctx *ctx, const uint8_t *h_comp, size_t co
                              const uint64_t *h_offsets, size_t nblocks, const fse_b200_params *p,
                              uint8_t *h_dst, size_t n, int32_t *h_status);
 
+/* ---- self-describing frame (the container the reference does not have) ------- */
+/* Layout (little endian):  "FSEB" | u16 version = 1 | u16 n_states | u32 block_size | u32 table_log |
+ * u32 table_mode | u32 global_header_bytes | u64 n | u64 nblocks | u64 payload_bytes |
+ * global NCount header (table_mode 1 only, padded to 8 bytes) | u64 offsets[nblocks + 1] | payload.
+ * Everything a decoder needs travels with the data; the payload is the dense block streams above. */
+#define FSE_B200_FRAME_MAGIC 0x42455346u /* "FSEB" */
+size_t fse_b200_frame_bound(size_t n, const fse_b200_params *p);
+/* Compress h_src into one frame.  In FSE_B200_TABLE_GLOBAL mode the table is built here from the
+ * whole-buffer histogram (p->table_log).  *h_frame_bytes out. */
+int fse_b200_frame_compress_host(fse_b200_ctx *ctx, const uint8_t *h_src, size_t n, const fse_b200_params *p,
+                                 uint8_t *h_frame, size_t frame_cap, size_t *h_frame_bytes);
+/* Parse a frame header: parameters and the uncompressed size (host only, no GPU work). */
+int fse_b200_frame_info(const uint8_t *h_frame, size_t frame_bytes, fse_b200_params *p_out, size_t *n_out);
+/* Decompress a frame into h_dst (capacity dst_cap >= n).  *h_n out. */
+int fse_b200_frame_decompress_host(fse_b200_ctx *ctx, const uint8_t *h_frame, size_t frame_bytes, uint8_t *h_dst,
+                                   size_t dst_cap, size_t *h_n);
+
 /* Synthetic byte streams of SURVEY.md section 8(d), generated on the device (bench input).
  * kind: 0 geometric(0.2) (the crate's gen_sequence, src/lib.rs:255-278), 1 text-like, 2 few-symbol,
  * 3 uniform.  Byte i depends only on (seed, first_index + i). */

@@ -598,3 +598,26 @@ def test_randomised_differential(ctx):
         out, dst_ = ctx.decompress_blocks(d, total, dev(ctx, off), n, bs, tl, n_states)
         assert (dst_.cpu().numpy() >= 0).all() and np.array_equal(out.cpu().numpy(), src), (trial, n_states, bs, tl)
     assert checked > 100
+
+
+def test_frame_container(ctx):
+    """a self-describing frame carries parameters, offsets and payload; both table modes"""
+    import entropy_coders_b200 as E
+    for kind, n, bs, mode, tl in [("text", 5 * 65536 + 321, 65536, 0, 0), ("geo", 300000, 16384, 1, 11), ("few", 1000, 300, 0, 9)]:
+        src = O.generate(kind, 55, n)
+        frame = ctx.frame_compress(src, bs, tl, 128, mode)
+        info = ctx.frame_info(frame)
+        assert info == {"block_size": bs, "table_log": tl, "n_states": 128, "table_mode": mode, "n": n}
+        fresh = E.Context(0)                                  # nothing but the frame is needed to decode
+        assert np.array_equal(fresh.frame_decompress(frame), src)
+        fresh.close()
+        if mode == 0:                                         # the payload is the dense block streams
+            exp = b"".join(e if e is not None else bytes([0x0F]) + src[i * bs:(i + 1) * bs].tobytes()
+                           for i, e in enumerate(oracle_blocks(src, bs, tl, 128)))
+            assert frame[-len(exp):].tobytes() == exp
+    bad = frame.copy()
+    bad[0] ^= 0xFF
+    with pytest.raises(E.FseError):
+        ctx.frame_info(bad)
+    with pytest.raises(E.FseError):
+        ctx.frame_info(frame[:40])
