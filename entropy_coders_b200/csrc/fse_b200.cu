@@ -611,7 +611,7 @@ int fse_b200_decompress_blocks_async(fse_b200_ctx *ctx, const uint8_t *d_comp, s
     if (p->n_states == 64 && tlmax > 13) return fail(ctx, FSE_B200_ERR_UNSUPPORTED, "n_states 64 needs table_log <= 13");
     if (p->n_states == 128) {
         if (tlmax > 13) return fail(ctx, FSE_B200_ERR_UNSUPPORTED, "n_states 128 needs table_log <= 13");
-        const size_t half = (ctx->smem_per_sm - 2048) / 2 - 1024;
+        const size_t half = ctx->smem_per_sm / 2 - 1024;
         const char *dv = getenv("FSE_B200_DECODE128");          // development switch: "c" compact tables, "w" wide entries
         const bool compact = tlmax <= 12 && !(dv && dv[0] == 'w');
         const size_t per_warp = compact ? dec64c_layout(tlmax).total : dec64w_layout(tlmax).total;
@@ -631,7 +631,7 @@ int fse_b200_decompress_blocks_async(fse_b200_ctx *ctx, const uint8_t *d_comp, s
     const bool use_wide = variant ? variant[0] == 'w' : false;   // measured: compact 0.49 ms vs wide 0.70 ms on c2
     if (p->n_states == 64 && (tlmax <= 12 || use_wide)) {
         // two CTAs per SM, each with half of the SM's shared memory
-        const size_t half = (ctx->smem_per_sm - 2048) / 2 - 1024;   // 1 KiB per CTA is reserved by the runtime
+        const size_t half = ctx->smem_per_sm / 2 - 1024;            // 1 KiB per CTA is reserved by the runtime
         const size_t per_warp = (use_wide || tlmax > 12) ? dec64w_layout(tlmax).total : dec64c_layout(tlmax).total;
         int wpc = pick_warps(nblocks, ctx->num_sms * 2, per_warp, std::min(half, ctx->smem_optin), 16);
         int ctas = 2;

@@ -5,6 +5,35 @@
 
 namespace fsed {
 
+#ifndef FSE_DEC_TMA
+#define FSE_DEC_TMA 1   /* stage the payload ring with cp.async.bulk (TMA) + mbarrier instead of register-prefetched loads */
+#endif
+
+// ---- 1-D bulk async copy (TMA) global -> shared with mbarrier completion (SASS: UBLKCP / SYNCS) ----
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_saddr, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // earlier generic reads of the slot are done
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst_saddr), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// bounded: a copy that never lands must not hang the GPU
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity)
+{
+    for (uint32_t spin = 0; spin < (1u << 24); spin++) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) return true;
+    }
+    return false;
+}
+
 __device__ __forceinline__ uint32_t lds_u8(uint32_t saddr)
 {
     uint32_t v;
@@ -25,6 +54,12 @@ __global__ void __launch_bounds__(512, 2) k_decode128c_blocks(DecArgs a)
     uint32_t *ring = reinterpret_cast<uint32_t *>(my + lay.scratch);   // 256 words + 2 mirror words
     const uint32_t tab_saddr = (uint32_t)__cvta_generic_to_shared(tab);
     const uint32_t sym_saddr = (uint32_t)__cvta_generic_to_shared(sym);
+#if FSE_DEC_TMA
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(my + lay.total - 16);   // one mbarrier per warp, lives across blocks
+    if (lane == 0) mbar_init(bar, 1);
+    __syncwarp();
+    uint32_t par = 0;
+#endif
     const uint32_t N = 128;
 
     uint32_t glog2 = 0;
@@ -93,7 +128,11 @@ __global__ void __launch_bounds__(512, 2) k_decode128c_blocks(DecArgs a)
         const uint8_t *pay = cs + consumed;
         const uint32_t plen = clen - consumed;
         if (plen == 0 || pay[plen - 1] == 0) { if (lane == 0) a.status[b] = ST_NO_MARKER; continue; }
+#if FSE_DEC_TMA
+        const uint32_t bias = (uint32_t)((uintptr_t)pay & 15);     // bulk copies need 16-byte aligned global chunks
+#else
         const uint32_t bias = (uint32_t)((uintptr_t)pay & 3);
+#endif
         const uint32_t *origin = reinterpret_cast<const uint32_t *>(pay - bias);
         uint32_t cur = (plen - 1) * 8 + ilog2u(pay[plen - 1]) + 8 * bias;
         const uint32_t floor_bits = 8 * bias;
@@ -110,9 +149,11 @@ __global__ void __launch_bounds__(512, 2) k_decode128c_blocks(DecArgs a)
                 if ((w & 255) < 2) ring[256 + (w & 255)] = x;   // mirror: ring[256..257] == ring[0..1]
             }
         }
+#if !FSE_DEC_TMA
         uint32_t pre[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) pre[k] = (lowq >= 128) ? __ldg(origin + lowq - 128 + lane + 32 * k) : 0u;
+#endif
         __syncwarp();
         const uint32_t ring_saddr = (uint32_t)__cvta_generic_to_shared(ring);
         // up to 52 bits at stream position q (three ring words, 64-bit funnel)
@@ -124,6 +165,29 @@ __global__ void __launch_bounds__(512, 2) k_decode128c_blocks(DecArgs a)
             uint32_t s = q & 31;
             return ((uint64_t)__funnelshift_r(w1, w2, s) << 32) | __funnelshift_r(w0, w1, s);
         };
+#if FSE_DEC_TMA
+        // The ring holds words [lowq, lowq+256).  As soon as the upper half is dead, one lane starts a 512-byte
+        // bulk copy of the next lower 128 words into it; the warp waits on the mbarrier only when it gets there.
+        bool pending = false, tma_ok = true;
+        auto stage = [&]() {
+            if (!pending && lowq && (cur >> 5) + 3 < lowq + 128) {
+                __syncwarp();
+                if (lane == 0) bulk_g2s(ring_saddr + (((lowq - 128) & 255) << 2), origin + (lowq - 128), 512, bar);
+                pending = true;
+            }
+            if (pending && (cur >> 5) < lowq + 56) {               // a round takes at most 52 words
+                tma_ok = tma_ok && mbar_wait(bar, par);
+                par ^= 1;
+                lowq -= 128;
+                pending = false;
+                if ((lowq & 255) == 0) {                            // slots 0 and 1 changed: refresh their mirror
+                    __syncwarp();
+                    if (lane < 2) ring[256 + lane] = ring[lane];
+                }
+                __syncwarp();
+            }
+        };
+#else
         auto refill = [&]() {
             __syncwarp();
 #pragma unroll
@@ -134,6 +198,8 @@ __global__ void __launch_bounds__(512, 2) k_decode128c_blocks(DecArgs a)
             for (int k = 0; k < 4; k++) pre[k] = (lowq >= 128) ? __ldg(origin + lowq - 128 + lane + 32 * k) : 0u;
             __syncwarp();
         };
+        auto stage = [&]() { if ((cur >> 5) < lowq + 56 && lowq) refill(); };   // a round takes at most 52 words
+#endif
         // Decoder::new, fse.rs:349-352: states are read 0, 1, 2, ... from the top of the stack
         uint32_t s0, s1, s2, s3;
         {
@@ -150,7 +216,7 @@ __global__ void __launch_bounds__(512, 2) k_decode128c_blocks(DecArgs a)
         bool bad = false;
         uint32_t i0 = 0;
         for (; i0 + 128 <= body; i0 += 128) {
-            if ((cur >> 5) < lowq + 56 && lowq) refill();   // a round takes at most 52 words
+            stage();
             uint32_t e0 = lds_u16(tab_saddr + s0 * 2), e1 = lds_u16(tab_saddr + s1 * 2);   // fse.rs:363-373, four chains
             uint32_t e2 = lds_u16(tab_saddr + s2 * 2), e3 = lds_u16(tab_saddr + s3 * 2);
             uint32_t y0 = lds_u8(sym_saddr + s0), y1 = lds_u8(sym_saddr + s1), y2 = lds_u8(sym_saddr + s2), y3 = lds_u8(sym_saddr + s3);
@@ -173,7 +239,7 @@ __global__ void __launch_bounds__(512, 2) k_decode128c_blocks(DecArgs a)
             cur -= tot;
         }
         if (!bad && i0 < body) {                            // last partial round
-            if ((cur >> 5) < lowq + 56 && lowq) refill();
+            stage();
             uint32_t ia = i0 + 4 * lane;
             uint32_t e0 = tab[s0], e1 = tab[s1], e2 = tab[s2], e3 = tab[s3];
             uint32_t n0 = ia < body ? (e0 >> 12) : 0u, n1 = ia + 1 < body ? (e1 >> 12) : 0u;
@@ -197,6 +263,13 @@ __global__ void __launch_bounds__(512, 2) k_decode128c_blocks(DecArgs a)
             out[body + ((4 * lane + 2 - body) & 127)] = sym[s2];
             out[body + ((4 * lane + 3 - body) & 127)] = sym[s3];
         }
+#if FSE_DEC_TMA
+        if (pending) {                                      // never leave a copy in flight into memory the next block reuses
+            tma_ok = tma_ok && mbar_wait(bar, par);
+            par ^= 1;
+        }
+        if (!tma_ok) bad = true;
+#endif
         cur -= floor_bits;
         if (bad || cur != 0) st = ST_LENGTH;
         if (lane == 0) a.status[b] = st;

@@ -28,7 +28,7 @@ __host__ __device__ inline Dec64cLayout dec64c_layout(uint32_t tlmax)
     l.tab = 0;
     l.sym = size * 2;
     l.scratch = size * 3;
-    l.total = size * 3 + 2048;
+    l.total = size * 3 + 2048 + 16;     // + one mbarrier per warp (fse_decode128c.cuh)
     return l;
 }
 
