@@ -359,7 +359,8 @@ def test_output_lands_at_arbitrary_byte_offsets(ctx):
     assert np.array_equal(out.cpu().numpy(), src)
 
 
-def test_global_table_mode(ctx):
+@pytest.mark.parametrize("n_states", [32, 64, 128])
+def test_global_table_mode(ctx, n_states):
     """BASELINE config 5 on one GPU: one table from the whole-buffer histogram; blocks are
     header-less payloads (fse.rs:394-421); the header equals the oracle's for the u64 counts"""
     n, bs = 40 * 16384 + 5, 16384
@@ -370,19 +371,19 @@ def test_global_table_mode(ctx):
     h = O.histogram(src)
     rc, nh = O.normalize(h, 11)
     assert rc >= 0 and log2 == nh.log2 and header == O.ncount_write(nh)[0]
-    d, off, st, total = ctx.compress_blocks(dsrc, bs, 11, 32, table_mode=1)
+    d, off, st, total = ctx.compress_blocks(dsrc, bs, 11, n_states, table_mode=1)
     offh = off.cpu().numpy()
     buf = d[:total].cpu().numpy().tobytes()
     et = O.enc_table(nh)
     for b in range(len(offh) - 1):
         blk = src[b * bs:(b + 1) * bs]
-        exp = blk.tobytes() if len(blk) < 32 else O.encode_payload(et, blk, 32)[0]
+        exp = blk.tobytes() if len(blk) < n_states else O.encode_payload(et, blk, n_states)[0]
         assert buf[offh[b]:offh[b + 1]] == exp, b
     # a fresh context decodes from the stored header alone
     import entropy_coders_b200 as E
     c2 = E.Context(0)
     assert c2.set_global_table_from_header(header) == log2
-    out, dst_ = c2.decompress_blocks(d, total, off, n, bs, 11, 32, table_mode=1)
+    out, dst_ = c2.decompress_blocks(d, total, off, n, bs, 11, n_states, table_mode=1)
     assert (dst_.cpu().numpy() >= 0).all() and np.array_equal(out.cpu().numpy(), src)
     c2.close()
 
