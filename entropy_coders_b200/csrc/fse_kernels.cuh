@@ -385,19 +385,22 @@ __global__ void __launch_bounds__(1024) k_scan_sizes(const uint32_t *__restrict_
 // byte copy with 4-byte aligned destination stores and funnel-shifted source words
 __device__ __forceinline__ void block_copy_bytes(uint8_t *dst, const uint8_t *src /*4-aligned*/, uint32_t len, int tid, int nthr)
 {
-    uint32_t head = (uint32_t)((4 - ((uintptr_t)dst & 3)) & 3);
+    // destination stores are whole aligned 16-byte vectors; the source words are funnel-shifted into place
+    uint32_t head = (uint32_t)((16 - ((uintptr_t)dst & 15)) & 15);
     if (head > len) head = len;
     if (tid < (int)head) dst[tid] = src[tid];
-    uint32_t nwords = (len - head) >> 2;
-    const uint32_t *sw = reinterpret_cast<const uint32_t *>(src);  // word k of dst body = src bytes head+4k..
-    uint32_t *dw = reinterpret_cast<uint32_t *>(dst + head);
-    uint32_t sh = head * 8;
-    for (uint32_t k = tid; k < nwords; k += nthr) {
-        uint32_t w0 = sw[k], w1 = sh ? sw[k + 1] : 0u;
-        dw[k] = __funnelshift_r(w0, w1, sh);
+    const uint32_t nvec = (len - head) >> 4;
+    const uint32_t *sw = reinterpret_cast<const uint32_t *>(src) + (head >> 2);   // vector k = src bytes head+16k ..
+    uint4 *dv = reinterpret_cast<uint4 *>(dst + head);
+    const uint32_t sh = (head & 3) * 8;
+    for (uint32_t k = tid; k < nvec; k += nthr) {
+        const uint32_t *w = sw + 4 * k;
+        uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = sh ? w[4] : 0u;
+        dv[k] = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh),
+                           __funnelshift_r(w3, w4, sh));
     }
-    uint32_t t0 = head + (nwords << 2);
-    if (t0 + tid < len) dst[t0 + tid] = src[t0 + tid];
+    const uint32_t t0 = head + (nvec << 4);
+    if (t0 + tid < len) dst[t0 + tid] = src[t0 + tid];    // tail < 16 bytes <= nthr
 }
 
 // K6: gather header || payload of every block to its scanned offset
