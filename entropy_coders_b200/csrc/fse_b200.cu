@@ -537,6 +537,7 @@ int fse_b200_compress_blocks_async(fse_b200_ctx *ctx, const uint8_t *d_src, size
     const size_t per_warp = wide ? enc64_layout(tlmax).total : enc_layout(tlmax).total;
     int wpc = pick_warps(nb, ctx->num_sms, per_warp, ctx->smem_optin, 16);
     if (wpc < 1) return fail(ctx, FSE_B200_ERR_UNSUPPORTED, "table_log too large for shared memory");
+    if (const char *o = getenv("FSE_B200_ENC_WPC")) wpc = std::max(1, std::min(wpc, atoi(o)));   // development override
     int grid = (int)std::min<size_t>((nb + wpc - 1) / wpc, (size_t)ctx->num_sms);
     a.fused = 0; a.desc = nullptr; a.ticket = nullptr; a.dst = d_dst;
     a.offsets = reinterpret_cast<unsigned long long *>(d_offsets);

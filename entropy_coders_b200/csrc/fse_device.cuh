@@ -465,17 +465,22 @@ __device__ int ncount_read_serial(const uint8_t *src, uint32_t nbytes, int32_t *
 // position = (position + step) & mask is (j*step)&mask for the k-th j whose cell is
 // <= high_threshold; it receives the k-th entry of the symbols expanded by positive counts;
 // low-probability symbols (-1) take the cells size-1, size-2, ... in symbol order.
+// The fill runs over ranks, 32 per step: the first rank of every present symbol is flagged in bit 15 of
+// the rank -> cell map, so a ballot and a running popcount give each rank the index of its symbol in
+// the list of present symbols (independent of how many symbols there are or how small they are).
 //   spread  : uint8[size] out (cell -> symbol)
-//   cum     : uint32[256] out: exclusive prefix of |norm| (EncodeTable's cumul / symbol_tt total)
-//   posmap  : uint16[size] scratch (only touched when low-probability symbols exist)
+//   cum     : uint32[256] out: exclusive prefix of |norm| (EncodeTable's cumul / symbol_tt total);
+//             its storage holds the list of present symbols until the end of the call
+//   posmap  : uint16[size] scratch (rank -> cell, bit 15 = a symbol starts here)
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void warp_spread(const int32_t *norm, uint32_t log2, uint32_t table_len, uint8_t *spread,
                                             uint32_t *cum, uint16_t *posmap, int lane)
 {
     const uint32_t size = 1u << log2, mask = size - 1, step = table_step(size);
+    uint8_t *psym = reinterpret_cast<uint8_t *>(cum);
     int32_t x[8];
     uint32_t apre[8], ppre[8];
-    uint32_t asum = 0, psum = 0, lsum = 0;
+    uint32_t asum = 0, psum = 0, lsum = 0, nsum = 0;
 #pragma unroll
     for (int k = 0; k < 8; k++) {
         int i = lane * 8 + k;
@@ -484,20 +489,18 @@ __device__ __forceinline__ void warp_spread(const int32_t *norm, uint32_t log2, 
         asum += (uint32_t)abs(x[k]);
         psum += (uint32_t)max(x[k], 0);
         lsum += (x[k] < 0) ? 1u : 0u;
+        nsum += (x[k] > 0) ? 1u : 0u;
     }
     uint32_t packed = warp_incl_add((asum << 16) | psum, lane);  // sums <= 2^15 each
     uint32_t abase = (packed >> 16) - asum, pbase = (packed & 0xffff) - psum;
-    uint32_t lincl = warp_incl_add(lsum, lane);
-    uint32_t lbase = lincl - lsum;
-    uint32_t L = __shfl_sync(FULL, lincl, 31);
-    const uint32_t high_threshold = size - 1 - L;
+    uint32_t packed2 = warp_incl_add((lsum << 16) | nsum, lane); // <= 256 each
+    uint32_t lbase = (packed2 >> 16) - lsum, nbase = (packed2 & 0xffff) - nsum;
+    const uint32_t L = __shfl_sync(FULL, packed2, 31) >> 16;
+    const uint32_t high_threshold = size - 1 - L, P = size - L;   // P cells go to positive counts
     uint32_t lrank = lbase;
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-        int i = lane * 8 + k;
-        cum[i] = abase + apre[k];
-        if (x[k] < 0) { spread[size - 1 - lrank] = (uint8_t)i; lrank++; }  // fse.rs:122-125
-    }
+    for (int k = 0; k < 8; k++)
+        if (x[k] < 0) { spread[size - 1 - lrank] = (uint8_t)(lane * 8 + k); lrank++; }  // fse.rs:122-125
     if (L) {  // rank -> cell map of the accepted positions
         uint32_t base = 0;
         for (uint32_t j0 = 0; j0 < size; j0 += 32) {
@@ -507,24 +510,30 @@ __device__ __forceinline__ void warp_spread(const int32_t *norm, uint32_t log2, 
             if (acc) posmap[base + __popc(b & lt_mask(lane))] = (uint16_t)pos;
             base += __popc(b);
         }
-        __syncwarp();
+    } else {
+        for (uint32_t j = lane; j < size; j += 32) posmap[j] = (uint16_t)((j * step) & mask);
     }
+    __syncwarp();
+    uint32_t nrank = nbase;
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-        uint32_t m = __ballot_sync(FULL, x[k] > 0);
-        while (m) {
-            int src = __ffs((int)m) - 1;
-            m &= m - 1;
-            uint32_t c = (uint32_t)__shfl_sync(FULL, x[k], src);
-            uint32_t a = __shfl_sync(FULL, pbase + ppre[k], src);
-            uint8_t s = (uint8_t)(src * 8 + k);
-            for (uint32_t q = lane; q < c; q += 32) {
-                uint32_t rank = a + q;
-                uint32_t pos = L ? (uint32_t)posmap[rank] : ((rank * step) & mask);
-                spread[pos] = s;
-            }
+    for (int k = 0; k < 8; k++)
+        if (x[k] > 0) {
+            psym[nrank++] = (uint8_t)(lane * 8 + k);
+            posmap[pbase + ppre[k]] |= 0x8000u;
         }
+    __syncwarp();
+    uint32_t run = 0;
+    for (uint32_t j0 = 0; j0 < P; j0 += 32) {
+        const uint32_t r = j0 + lane;
+        const uint32_t v = r < P ? (uint32_t)posmap[r] : 0u;
+        const uint32_t b = __ballot_sync(FULL, (v & 0x8000u) != 0);
+        const uint32_t kk = run + __popc(b & (lt_mask(lane) | (1u << lane)));   // symbols started up to this rank
+        run += __popc(b);
+        if (r < P) spread[v & 0x7fffu] = psym[kk - 1];
     }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 8; k++) cum[lane * 8 + k] = abase + apre[k];
     __syncwarp();
 }
 
