@@ -70,7 +70,10 @@ __device__ void encode128_payload_warp(const uint8_t *__restrict__ bsrc, uint32_
     const uint32_t rrow = (uint32_t)lane >> 1, rhalf = (uint32_t)lane & 1, rkey = ((rrow & 3) << 1) | rhalf;
 
     uint32_t sy[16];
-    auto plain = [&](uint32_t g0) -> bool { return g0 >= 16 && (uint32_t)Q >= (g0 + 16) * 32; };
+    // a chunk whose 16 rounds are all inside the block runs without per-element checks; chunk 0 qualifies when
+    // the block length is a multiple of 4, so that round 0 is exactly the 128 state-initialising symbols
+    const bool first_plain = (bn & 3) == 0;
+    auto plain = [&](uint32_t g0) -> bool { return (g0 >= 16 || first_plain) && (uint32_t)Q >= (g0 + 16) * 32; };
     // only plain chunks read sy[] (the checked path loads its own bytes): one 32-bit load per quad when the
     // block is 4-byte aligned, four byte loads otherwise
     auto fetch = [&](uint32_t g0) {
@@ -95,10 +98,18 @@ __device__ void encode128_payload_warp(const uint8_t *__restrict__ bsrc, uint32_
             for (int r = 0; r < 16; r++) {
                 uint32_t v3, b3, v2, b2, v1, b1, v0, b0;
                 const uint32_t x = sy[r];
-                enc_step(tt_saddr, x >> 24, s3, v3, b3);           // decreasing index order: 4m+3 first
-                enc_step(tt_saddr, (x >> 16) & 0xff, s2, v2, b2);
-                enc_step(tt_saddr, (x >> 8) & 0xff, s1, v1, b1);
-                enc_step(tt_saddr, x & 0xff, s0, v0, b0);
+                if (r == 0 && g0 == 0) {                           // Encoder::new_first_symbol: no bits
+                    s3 = enc_first64(tt_saddr, x >> 24);
+                    s2 = enc_first64(tt_saddr, (x >> 16) & 0xff);
+                    s1 = enc_first64(tt_saddr, (x >> 8) & 0xff);
+                    s0 = enc_first64(tt_saddr, x & 0xff);
+                    v3 = v2 = v1 = v0 = b3 = b2 = b1 = b0 = 0;
+                } else {
+                    enc_step(tt_saddr, x >> 24, s3, v3, b3);       // decreasing index order: 4m+3 first
+                    enc_step(tt_saddr, (x >> 16) & 0xff, s2, v2, b2);
+                    enc_step(tt_saddr, (x >> 8) & 0xff, s1, v1, b1);
+                    enc_step(tt_saddr, x & 0xff, s0, v0, b0);
+                }
                 uint2 f;
                 f.x = (v3 | (v2 << b3)) | ((b3 + b2) << PAIR_LEN_SHIFT);
                 f.y = (v1 | (v0 << b1)) | ((b1 + b0) << PAIR_LEN_SHIFT);
@@ -139,7 +150,14 @@ __device__ void encode128_payload_warp(const uint8_t *__restrict__ bsrc, uint32_
         uint32_t nw = warp_place(myrow, tot, obuf, 1024, lane, cw, cb, overflow);
         __syncwarp();
         if (wdone + nw > cap_words) { overflow = true; nw = 0; }
-        for (uint32_t j = lane; j < nw; j += 32) pay[wdone + j] = obuf[j];
+        {
+            uint32_t j = lane;
+            for (; j + 96 < nw; j += 128) {                    // whole 128-byte lines, four in flight
+                uint32_t w0 = obuf[j], w1 = obuf[j + 32], w2 = obuf[j + 64], w3 = obuf[j + 96];
+                pay[wdone + j] = w0; pay[wdone + j + 32] = w1; pay[wdone + j + 64] = w2; pay[wdone + j + 96] = w3;
+            }
+            for (; j < nw; j += 32) pay[wdone + j] = obuf[j];
+        }
         wdone += nw;
         __syncwarp();
     }
