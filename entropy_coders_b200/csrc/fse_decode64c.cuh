@@ -140,13 +140,7 @@ __global__ void __launch_bounds__(512, 2) k_decode64c_blocks(DecArgs a)
             for (int k = 0; k < 8; k++) norm[k * 32 + lane] = 0;
             __syncwarp();
             uint32_t table_len = 0;
-            int rc = 0;
-            if (lane == 0) rc = ncount_read_serial(cs, clen, norm, log2, table_len, consumed);
-            rc = __shfl_sync(FULL, rc, 0);
-            log2 = __shfl_sync(FULL, log2, 0);
-            table_len = __shfl_sync(FULL, table_len, 0);
-            consumed = __shfl_sync(FULL, consumed, 0);
-            __syncwarp();
+            const int rc = warp_ncount_read(cs, clen, reinterpret_cast<uint32_t *>(tab), norm, lane, log2, table_len, consumed);
             if (rc < 0) { if (lane == 0) a.status[b] = rc; continue; }
             if (log2 > a.tlmax || log2 > 12) { if (lane == 0) a.status[b] = ST_UNSUPPORTED; continue; }
             warp_spread(norm, log2, table_len, sym, ctr, tab, lane);     // sym is the spread; tab doubles as posmap

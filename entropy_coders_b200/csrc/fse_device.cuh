@@ -401,12 +401,48 @@ struct FwdBits {
     }
 };
 
+// The same reader over a word-aligned shared-memory copy of the header (warp_stage_header): one funnel shift
+// per peek instead of four byte loads from global memory.  w[] must be readable one word past the data.
+struct SmemBits {
+    const uint32_t *w;
+    uint32_t nbytes, pos, bias;  // pos in bits from the first header byte; bias = bit offset of that byte in w[0]
+    __device__ __forceinline__ bool peek(uint32_t n, uint32_t &out) const
+    {
+        if (pos + n > nbytes * 8) return false;
+        const uint32_t q = pos + bias, i = q >> 5;
+        out = __funnelshift_r(w[i], w[i + 1], q & 31) & ((1u << n) - 1u);
+        return true;
+    }
+};
+
+constexpr uint32_t HDR_STAGE_BYTES = 508;   // NormHistogram::write_bound is at most 483 bytes (histogram.rs:330-337)
+constexpr uint32_t HDR_STAGE_WORDS = 129;
+
+// Copies the first min(nbytes, HDR_STAGE_BYTES) bytes at src (any alignment) into hw[0 .. HDR_STAGE_WORDS) with
+// aligned 32-bit loads; returns the number of bytes staged.  Reads stay inside the 4-byte words that hold the data.
+__device__ __forceinline__ uint32_t warp_stage_header(const uint8_t *src, uint32_t nbytes, uint32_t *hw, int lane, uint32_t &bias_bits)
+{
+    const uint32_t bias = (uint32_t)((uintptr_t)src & 3);
+    const uint32_t *origin = reinterpret_cast<const uint32_t *>(src - bias);
+    const uint32_t staged = min(nbytes, HDR_STAGE_BYTES);
+    const uint32_t nwords = (bias + staged + 3) >> 2;          // <= 128
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint32_t w = lane + 32 * k;
+        hw[w] = w < nwords ? __ldg(origin + w) : 0u;
+    }
+    if (lane == 0) hw[128] = 0;
+    bias_bits = bias * 8;
+    __syncwarp();
+    return staged;
+}
+
 // NormHistogram::read, src/histogram.rs:436-505.  Serial on the calling lane.  norm must be zeroed.
-__device__ int ncount_read_serial(const uint8_t *src, uint32_t nbytes, int32_t *norm, uint32_t &log2_out,
-                                  uint32_t &table_len_out, uint32_t &consumed_out)
+template <typename Reader>
+__device__ __forceinline__ int ncount_read_impl(Reader r, uint32_t nbytes, int32_t *norm, uint32_t &log2_out,
+                                                uint32_t &table_len_out, uint32_t &consumed_out)
 {
     if (nbytes == 0) return ST_PANIC;  // stream_reader.rs:17
-    FwdBits r{src, nbytes, 0};
     uint32_t v;
     if (!r.peek(4, v)) return ST_IO;
     r.pos += 4;
@@ -466,6 +502,37 @@ __device__ int ncount_read_serial(const uint8_t *src, uint32_t nbytes, int32_t *
     table_len_out = symbol;
     consumed_out = (r.pos + 7) >> 3;
     return 0;
+}
+__device__ int ncount_read_serial(const uint8_t *src, uint32_t nbytes, int32_t *norm, uint32_t &log2_out,
+                                  uint32_t &table_len_out, uint32_t &consumed_out)
+{
+    return ncount_read_impl(FwdBits{src, nbytes, 0}, nbytes, norm, log2_out, table_len_out, consumed_out);
+}
+// Header parse for the decode kernels: the warp stages the header in shared memory (hw: HDR_STAGE_WORDS words),
+// lane 0 parses it there.  A stream that runs past the staged bytes (no valid header does) is re-parsed from
+// global memory so that the error codes stay those of the reference reader.  norm must be zeroed; all lanes call.
+__device__ __forceinline__ int warp_ncount_read(const uint8_t *src, uint32_t nbytes, uint32_t *hw, int32_t *norm, int lane,
+                                                uint32_t &log2_out, uint32_t &table_len_out, uint32_t &consumed_out)
+{
+    uint32_t bias_bits;
+    const uint32_t staged = warp_stage_header(src, nbytes, hw, lane, bias_bits);
+    int rc = 0;
+    uint32_t log2 = 0, table_len = 0, consumed = 0;
+    if (lane == 0) rc = ncount_read_impl(SmemBits{hw, staged, 0, bias_bits}, staged, norm, log2, table_len, consumed);
+    rc = __shfl_sync(FULL, rc, 0);
+    if (rc == ST_IO && staged < nbytes) {
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 8; k++) norm[k * 32 + lane] = 0;
+        __syncwarp();
+        if (lane == 0) rc = ncount_read_serial(src, nbytes, norm, log2, table_len, consumed);
+        rc = __shfl_sync(FULL, rc, 0);
+    }
+    log2_out = __shfl_sync(FULL, log2, 0);
+    table_len_out = __shfl_sync(FULL, table_len, 0);
+    consumed_out = __shfl_sync(FULL, consumed, 0);
+    __syncwarp();
+    return rc;
 }
 
 // ------------------------------------------------------------------------------------------
