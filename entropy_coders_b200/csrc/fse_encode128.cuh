@@ -22,6 +22,9 @@ __device__ __forceinline__ void enc_element_checked128(const uint8_t *__restrict
 
 // BitRow with the word emission written as predicated PTX: 9 instructions per field instead of the 13 the
 // compiler makes of the C++ version (it materialises every conditional update as add + move).
+constexpr uint32_t QUAD_LEN_SHIFT = 26;              // a quad field: 52 value bits, 6 length bits
+constexpr uint32_t QUAD_HI_MASK = (1u << QUAD_LEN_SHIFT) - 1u;
+
 struct BitRowS {
     uint32_t base, wp, lo, pos;      // shared byte addresses of the row start / next word, accumulator, bits held
     __device__ __forceinline__ void init(uint32_t *row, uint32_t carry_word, uint32_t carry_bits)
@@ -43,6 +46,27 @@ struct BitRowS {
                      "@p mov.u32 %0, h;\n\t"
                      "and.b32 %1, %1, 31;\n\t}"
                      : "+r"(lo), "+r"(pos), "+r"(wp) : "r"(v), "r"(nb) : "memory");
+    }
+    // a quad field: value (fhi:flo) < 2^nb, nb <= 52, pos < 32.  Both candidate words are stored every time (the row
+    // has two words of slack) and the accumulator is selected by the number of completed words (0, 1 or 2).
+    __device__ __forceinline__ void put64(uint32_t flo, uint32_t fhi, uint32_t nb)
+    {
+        asm volatile("{\n\t.reg .pred p1, p2;\n\t.reg .u32 t, w1, w2, np, c;\n\t"
+                     "shl.b32 t, %3, %1;\n\t"
+                     "or.b32 %0, %0, t;\n\t"
+                     "shf.l.clamp.b32 w1, %3, %4, %1;\n\t"
+                     "shf.l.clamp.b32 w2, %4, 0, %1;\n\t"
+                     "st.shared.u32 [%2], %0;\n\t"
+                     "st.shared.u32 [%2+4], w1;\n\t"
+                     "add.u32 np, %1, %5;\n\t"
+                     "shr.u32 c, np, 5;\n\t"
+                     "mad.lo.u32 %2, c, 4, %2;\n\t"
+                     "setp.eq.u32 p1, c, 1;\n\t"
+                     "setp.eq.u32 p2, c, 2;\n\t"
+                     "@p1 mov.u32 %0, w1;\n\t"
+                     "@p2 mov.u32 %0, w2;\n\t"
+                     "and.b32 %1, np, 31;\n\t}"
+                     : "+r"(lo), "+r"(pos), "+r"(wp) : "r"(flo), "r"(fhi), "r"(nb) : "memory");
     }
     __device__ __forceinline__ uint32_t finish()
     {
@@ -111,8 +135,11 @@ __device__ void encode128_payload_warp(const uint8_t *__restrict__ bsrc, uint32_
                     enc_step(tt_saddr, x & 0xff, s0, v0, b0);
                 }
                 uint2 f;
-                f.x = (v3 | (v2 << b3)) | ((b3 + b2) << PAIR_LEN_SHIFT);
-                f.y = (v1 | (v0 << b1)) | ((b1 + b0) << PAIR_LEN_SHIFT);
+                {                                                  // the quad as one field of <= 52 bits: (hi:lo), length in hi[26..31]
+                    const uint32_t p1 = v3 | (v2 << b3), n1 = b3 + b2, p0 = v1 | (v0 << b1);
+                    f.x = p1 | (p0 << n1);
+                    f.y = __funnelshift_l(p0, 0u, n1) | ((n1 + b1 + b0) << QUAD_LEN_SHIFT);
+                }
                 const uint32_t key = ((r & 3) << 1) | whalf;
                 *reinterpret_cast<uint2 *>(fld + r * 64 + ((wchunk ^ key) << 2) + ((kcol & 1) << 1)) = f;
             }
@@ -126,8 +153,11 @@ __device__ void encode128_payload_warp(const uint8_t *__restrict__ bsrc, uint32_
                 enc_element_checked128(bsrc, i + 1, (int32_t)bn, tt_saddr, s1, v1, b1);
                 enc_element_checked128(bsrc, i, (int32_t)bn, tt_saddr, s0, v0, b0);
                 uint2 f;
-                f.x = (v3 | (v2 << b3)) | ((b3 + b2) << PAIR_LEN_SHIFT);
-                f.y = (v1 | (v0 << b1)) | ((b1 + b0) << PAIR_LEN_SHIFT);
+                {                                                  // the quad as one field of <= 52 bits: (hi:lo), length in hi[26..31]
+                    const uint32_t p1 = v3 | (v2 << b3), n1 = b3 + b2, p0 = v1 | (v0 << b1);
+                    f.x = p1 | (p0 << n1);
+                    f.y = __funnelshift_l(p0, 0u, n1) | ((n1 + b1 + b0) << QUAD_LEN_SHIFT);
+                }
                 const uint32_t key = ((r & 3) << 1) | whalf;
                 *reinterpret_cast<uint2 *>(fld + r * 64 + ((wchunk ^ key) << 2) + ((kcol & 1) << 1)) = f;
             }
@@ -140,10 +170,8 @@ __device__ void encode128_payload_warp(const uint8_t *__restrict__ bsrc, uint32_
 #pragma unroll 2
         for (int q = 0; q < 8; q++) {
             uint4 x = *reinterpret_cast<const uint4 *>(fld + rrow * 64 + (((rhalf << 3) | (q ^ rkey)) << 2));
-            br.put(x.x & PAIR_VAL_MASK, x.x >> PAIR_LEN_SHIFT);
-            br.put(x.y & PAIR_VAL_MASK, x.y >> PAIR_LEN_SHIFT);
-            br.put(x.z & PAIR_VAL_MASK, x.z >> PAIR_LEN_SHIFT);
-            br.put(x.w & PAIR_VAL_MASK, x.w >> PAIR_LEN_SHIFT);
+            br.put64(x.x, x.y & QUAD_HI_MASK, x.y >> QUAD_LEN_SHIFT);
+            br.put64(x.z, x.w & QUAD_HI_MASK, x.w >> QUAD_LEN_SHIFT);
         }
         uint32_t tot = br.finish();
         __syncwarp();
