@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libfse_b200.so")
+SO_PATH = os.environ.get("FSE_B200_LIB") or os.path.join(HERE, "libfse_b200.so")   # env: development builds
 
 STATUS = {0: "OK", -1: "ERR_ARG", -2: "ERR_CAPACITY", -3: "ERR_TABLE_LOG", -4: "ERR_TOO_MANY", -5: "ERR_IO",
           -6: "ERR_NO_MARKER", -7: "ERR_LENGTH", -8: "ERR_PANIC", -9: "ERR_UNSUPPORTED", -10: "ERR_CUDA",

@@ -47,8 +47,7 @@ struct BitRowS {
                      "and.b32 %1, %1, 31;\n\t}"
                      : "+r"(lo), "+r"(pos), "+r"(wp) : "r"(v), "r"(nb) : "memory");
     }
-    // a quad field: value (fhi:flo) < 2^nb, nb <= 52, pos < 32.  Both candidate words are stored every time (the row
-    // has two words of slack) and the accumulator is selected by the number of completed words (0, 1 or 2).
+    // a quad field: value (fhi:flo) < 2^nb, nb <= 52, pos < 32: 0, 1 or 2 words are completed per call
     __device__ __forceinline__ void put64(uint32_t flo, uint32_t fhi, uint32_t nb)
     {
         asm volatile("{\n\t.reg .pred p1, p2;\n\t.reg .u32 t, w1, w2, np, c;\n\t"
@@ -56,13 +55,13 @@ struct BitRowS {
                      "or.b32 %0, %0, t;\n\t"
                      "shf.l.clamp.b32 w1, %3, %4, %1;\n\t"
                      "shf.l.clamp.b32 w2, %4, 0, %1;\n\t"
-                     "st.shared.u32 [%2], %0;\n\t"
-                     "st.shared.u32 [%2+4], w1;\n\t"
                      "add.u32 np, %1, %5;\n\t"
                      "shr.u32 c, np, 5;\n\t"
-                     "mad.lo.u32 %2, c, 4, %2;\n\t"
-                     "setp.eq.u32 p1, c, 1;\n\t"
+                     "setp.ne.u32 p1, c, 0;\n\t"
                      "setp.eq.u32 p2, c, 2;\n\t"
+                     "@p1 st.shared.u32 [%2], %0;\n\t"
+                     "@p2 st.shared.u32 [%2+4], w1;\n\t"
+                     "mad.lo.u32 %2, c, 4, %2;\n\t"
                      "@p1 mov.u32 %0, w1;\n\t"
                      "@p2 mov.u32 %0, w2;\n\t"
                      "and.b32 %1, np, 31;\n\t}"
