@@ -308,15 +308,18 @@ int fse_b200_histogram_blocks(fse_b200_ctx *ctx, const uint8_t *d_src, size_t n,
 
 static int hist_global_async(fse_b200_ctx *ctx, const uint8_t *d_src, size_t n, uint64_t *d_counts64)
 {
-    // fixed 1 MiB pieces: counts per piece fit uint32 and the result does not depend on the caller's block size
-    const uint32_t piece = 1u << 20;
+    // Pieces of at most 1 MiB (their counts fit the 16-bit lane columns); sized so that the pieces fill four waves of
+    // the histogram kernel's warp slots.  Integer sums: the result does not depend on the piece size.
+    const size_t slots = (size_t)ctx->num_sms * HIST16_WARPS * 4;
+    size_t want = ((n + slots - 1) / slots + 15) & ~(size_t)15;
+    const uint32_t piece = (uint32_t)std::min<size_t>(std::max<size_t>(want, 32u << 10), 1u << 20);
     size_t nb = fse_b200_num_blocks(n, piece);
     CK(cudaMemsetAsync(d_counts64, 0, 256 * sizeof(uint64_t), ctx->stream));
     if (nb == 0) return FSE_B200_OK;
     CK(ctx->counts.reserve(nb * 256 * sizeof(uint32_t)));
     launch_hist(ctx, d_src, n, piece, nb, ctx->counts.as<uint32_t>(), nullptr);
     ctx->launches++;
-    k_hist_reduce<<<(int)std::min<size_t>(nb, 64), 256, 0, ctx->stream>>>(ctx->counts.as<uint32_t>(), (uint32_t)nb,
+    k_hist_reduce<<<(int)std::min<size_t>(nb, (size_t)ctx->num_sms * 2), 256, 0, ctx->stream>>>(ctx->counts.as<uint32_t>(), (uint32_t)nb,
                                                                           reinterpret_cast<unsigned long long *>(d_counts64));
     ctx->launches++;
     CK(cudaGetLastError());
@@ -417,12 +420,10 @@ int fse_b200_build_decode_tables(fse_b200_ctx *ctx, const int32_t *d_norm, const
 
 // ---------------------------------------------------------------------------------- global table
 
-static int install_global(fse_b200_ctx *ctx, uint32_t *h_log2)
+// meta = the first words of g_meta read back by the caller (log2, table_len, status): one synchronisation per set-up
+static int install_global(fse_b200_ctx *ctx, const uint32_t *meta, uint32_t *h_log2)
 {
-    // g_norm / g_meta (log2, table_len, status) are on the device; build both tables at the effective log2
-    uint32_t meta[4];
-    CK(cudaMemcpyAsync(meta, ctx->g_meta.p, sizeof(meta), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    // g_norm is on the device; build both tables at the effective log2 (no further synchronisation)
     int32_t st = (int32_t)meta[2];
     if (st < 0) return fail(ctx, st, "global table: normalisation failed");
     uint32_t log2 = meta[0];
@@ -435,7 +436,7 @@ static int install_global(fse_b200_ctx *ctx, uint32_t *h_log2)
                           ctx->g_enc_tt.as<uint2>(), nullptr, nullptr, reinterpret_cast<int32_t *>(m + 3), false);
     if (rc) return rc;
     rc = build_tables(ctx, ctx->g_norm.as<int32_t>(), m, m + 1, 1, log2, 1, nullptr, nullptr, nullptr,
-                      ctx->g_dec_table.as<uint32_t>(), reinterpret_cast<int32_t *>(m + 3), true);
+                      ctx->g_dec_table.as<uint32_t>(), reinterpret_cast<int32_t *>(m + 3), false);
     if (rc) return rc;
     ctx->g_log2 = log2;
     ctx->g_table_len = meta[1];
@@ -459,18 +460,23 @@ int fse_b200_set_global_table(fse_b200_ctx *ctx, const uint64_t *d_counts64, uin
                                            ctx->g_norm.as<int32_t>(), m, m + 1, reinterpret_cast<int32_t *>(m + 2));
     ctx->launches++;
     CK(cudaGetLastError());
-    int rc = install_global(ctx, h_log2);
-    if (rc) return rc;
-    if (h_header && h_header_bytes) {
+    const bool want_header = h_header && h_header_bytes;
+    uint32_t meta[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint8_t hdr[512];
+    if (want_header) {   // the header only needs the normalised counts: written before the one read-back below
         k_ncount_write<<<1, 32, 0, ctx->stream>>>(ctx->g_norm.as<int32_t>(), m, m + 1, 1, ctx->g_hdr.as<uint8_t>(), 512, m + 4, m + 5);
         ctx->launches++;
         CK(cudaGetLastError());
-        uint32_t hb[2];
-        CK(cudaMemcpyAsync(hb, m + 4, sizeof(hb), cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-        if (hb[0] > *h_header_bytes) return fail(ctx, FSE_B200_ERR_CAPACITY, "header buffer too small");
-        CK(cudaMemcpy(h_header, ctx->g_hdr.p, hb[0], cudaMemcpyDeviceToHost));
-        *h_header_bytes = hb[0];
+        CK(cudaMemcpyAsync(hdr, ctx->g_hdr.p, sizeof(hdr), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaMemcpyAsync(meta, m, sizeof(meta), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    int rc = install_global(ctx, meta, h_log2);
+    if (rc) return rc;
+    if (want_header) {
+        if (meta[4] > *h_header_bytes || meta[4] > sizeof(hdr)) return fail(ctx, FSE_B200_ERR_CAPACITY, "header buffer too small");
+        memcpy(h_header, hdr, meta[4]);
+        *h_header_bytes = meta[4];
     }
     return FSE_B200_OK;
 }
@@ -491,7 +497,10 @@ int fse_b200_set_global_table_from_header(fse_b200_ctx *ctx, const uint8_t *h_he
                                              reinterpret_cast<int32_t *>(m + 2));
     ctx->launches++;
     CK(cudaGetLastError());
-    return install_global(ctx, h_log2);
+    uint32_t meta[4];
+    CK(cudaMemcpyAsync(meta, m, sizeof(meta), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return install_global(ctx, meta, h_log2);
 }
 
 // ---------------------------------------------------------------------------------- pipelines
