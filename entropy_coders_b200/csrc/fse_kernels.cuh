@@ -438,18 +438,6 @@ struct DecArgs {
     uint32_t *out_len;
 };
 
-// value of stream bits [bitpos, bitpos+nb) of the bytes at `base` (nb <= 16); never loads a word
-// that starts at or after wend
-__device__ __forceinline__ uint32_t read_bits(const uint8_t *base, uint32_t bitpos, uint32_t nb, const uint32_t *wend)
-{
-    uintptr_t a = (uintptr_t)(base + (bitpos >> 3));
-    const uint32_t *w = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
-    uint32_t sh = (uint32_t)((a & 3) << 3) + (bitpos & 7);
-    uint32_t w0 = __ldg(w);
-    uint32_t w1 = (w + 1 < wend) ? __ldg(w + 1) : 0u;
-    return __funnelshift_r(w0, w1, sh) & ((1u << nb) - 1u);
-}
-
 __global__ void __launch_bounds__(512) k_decode_blocks(DecArgs a)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -462,7 +450,6 @@ __global__ void __launch_bounds__(512) k_decode_blocks(DecArgs a)
     uint8_t *spread = my + lay.spread;
     uint32_t *ring = reinterpret_cast<uint32_t *>(my + lay.ring);
     const uint32_t N = a.n_states;
-    const uint32_t *wend = reinterpret_cast<const uint32_t *>(((uintptr_t)(a.comp + a.comp_bytes) + 3) & ~(uintptr_t)3);
 
     uint32_t glog2 = 0;
     if (a.global_mode) {
