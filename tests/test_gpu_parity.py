@@ -197,6 +197,37 @@ def test_header_read_errors(ctx):
         assert st[i] == O.ncount_read(c)[0], i
 
 
+@pytest.mark.parametrize("n_states", [32, 64, 128])
+def test_header_errors_inside_the_decode_kernels(ctx, n_states):
+    """the decode kernels parse the header themselves (from a shared-memory copy for 64 / 128 states): a block whose
+    header is malformed reports exactly the oracle's NormHistogram::read error, the other blocks still decode"""
+    bs = 4096
+    src = O.generate("text", 5, bs * 3)
+    good = oracle_blocks(src, bs, 0, n_states)
+    hdr, _ = O.ncount_write(O.normalize(O.histogram(src[:bs]), 11)[1])
+    rng = np.random.default_rng(9)
+    bad_blocks = [hdr[:len(hdr) // 2],                                   # truncated -> Io
+                  bytes([0x0B]) + bytes(30),                             # table_log 16 -> TableLogTooLarge
+                  bytes([0x06]) + bytes([0xFF]) * 700,                   # long garbage
+                  bytes([0x0A]) + rng.integers(0, 256, 600, dtype=np.uint8).tobytes(),
+                  bytes([0x00]) * 40]
+    for bad in bad_blocks:
+        exp = O.ncount_read(bad)[0]
+        streams = [good[0], bad, good[2]]
+        off = np.zeros(4, np.int64)
+        off[1:] = np.cumsum([len(x) for x in streams])
+        comp = np.frombuffer(b"".join(streams), np.uint8).copy()
+        out, st = ctx.decompress_blocks(dev(ctx, comp), comp.size, dev(ctx, off), src.size, bs, 0, n_states)
+        st = st.cpu().numpy()
+        assert st[0] == 0 and st[2] == 0, st
+        if exp < 0:
+            assert st[1] == exp, (bad[:4], st[1], exp)
+        else:
+            assert st[1] < 0, (bad[:4], st[1])                           # a header parsed, the payload cannot fit
+        out = out.cpu().numpy()
+        assert np.array_equal(out[:bs], src[:bs]) and np.array_equal(out[2 * bs:], src[2 * bs:])
+
+
 # ------------------------------------------------------------------------------------ encoded bytes
 
 @pytest.mark.parametrize("k", KAT["kats"], ids=[k["name"] for k in KAT["kats"]])

@@ -1,0 +1,78 @@
+"""Hypothesis-driven differential tests, CUDA path (through the C ABI) against the CPU oracle:
+generated alphabets, skews, runs, block sizes, state counts and table_log; every block is either the oracle's bytes
+or one the reference panics on (then it carries an escape), and decode always returns the input."""
+import numpy as np
+import pytest
+from hypothesis import HealthCheck, given, settings, strategies as st
+
+import oracle_lib as O
+from test_gpu_parity import dev, gpu_blocks
+from test_oracle_properties import byte_strings
+
+pytestmark = pytest.mark.gpu
+
+COMMON = dict(deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large,
+                                                    HealthCheck.function_scoped_fixture])
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import entropy_coders_b200 as E
+    c = E.Context(0)
+    yield c
+    c.close()
+
+
+@settings(max_examples=120, **COMMON)
+@given(byte_strings(min_size=1, max_size=40000), st.sampled_from([1, 2, 4, 8, 16, 32, 64, 128]),
+       st.sampled_from([130, 257, 1000, 4096, 5000, 20000]), st.sampled_from([0, 0, 5, 9, 11, 12]))
+def test_blocks_equal_the_oracle_and_round_trip(ctx, data, n_states, bs, tl):
+    if n_states <= 2:
+        data = data[:6000]                                   # the one-lane paths are for parity, not speed
+    blocks, stat, (d, off, total) = gpu_blocks(ctx, data, bs, tl, n_states)
+    for b, g in enumerate(blocks):
+        blk = data[b * bs:(b + 1) * bs]
+        try:
+            e = O.compress_n(blk, tl, n_states)[0]
+        except ValueError:
+            e = None
+        if e is None:
+            assert stat[b] in (1, 2) and g[0] in (0x0E, 0x0F), (b, stat[b])
+        else:
+            assert stat[b] == 0 and g == e, (b, n_states, bs, tl)
+    out, dst_ = ctx.decompress_blocks(d, total, dev(ctx, off), data.size, bs, tl, n_states)
+    assert (dst_.cpu().numpy() >= 0).all() and np.array_equal(out.cpu().numpy(), data)
+
+
+@settings(max_examples=60, **COMMON)
+@given(byte_strings(min_size=300, max_size=30000), st.sampled_from([32, 64, 128]), st.sampled_from([9, 11, 12]))
+def test_stage_outputs_equal_the_oracle(ctx, data, n_states, tl):
+    """histogram -> normalise -> header -> tables through the stage entry points, one table"""
+    h = O.histogram(data)
+    if h.table_len <= 1:
+        return
+    rc, n = O.normalize(h, tl)
+    if rc < 0:
+        return
+    import torch
+    counts, table_len = ctx.histogram_blocks(dev(ctx, data), data.size)
+    assert np.array_equal(counts.cpu().numpy().view(np.uint32)[0], np.array(h.table[:256], dtype=np.uint32))
+    assert int(table_len.cpu()[0]) == h.table_len
+    norm, log2, tlen, status = ctx.normalize(counts.to(torch.int64) & 0xffffffff, tl)
+    assert int(status.cpu()[0]) == rc and int(log2.cpu()[0]) == n.log2 and int(tlen.cpu()[0]) == n.table_len
+    assert np.array_equal(norm.cpu().numpy()[0], np.array(n.table[:256], dtype=np.int32))
+    hdr, bits = O.ncount_write(n)
+    out, nbytes, nbits = ctx.ncount_write(norm, log2, tlen)
+    assert int(nbits.cpu()[0]) == bits and out.cpu().numpy()[0, :int(nbytes.cpu()[0])].tobytes() == hdr
+    size = 1 << n.log2
+    table, tt, sym, est = ctx.build_encode_tables(norm, log2, tlen, n.log2)
+    dtab, dst_ = ctx.build_decode_tables(norm, log2, tlen, n.log2)
+    assert int(est.cpu()[0]) == 0 and int(dst_.cpu()[0]) == 0
+    et, dt = O.enc_table(n), O.dec_table(n)
+    assert np.array_equal(sym.cpu().numpy()[0, :size], np.frombuffer(bytes(et.symbols)[:size], np.uint8))
+    assert np.array_equal(table.cpu().numpy().view(np.uint16)[0, :size], np.array(et.table[:size], dtype=np.uint16))
+    exp_tt = np.array([[et.symbol_tt[i].bits, et.symbol_tt[i].find_state & 0xFFFFFFFF] for i in range(256)], dtype=np.uint32)
+    assert np.array_equal(tt.cpu().numpy()[0].view(np.uint32), exp_tt)
+    exp_d = np.array([dt.table[i].new_state | (dt.table[i].symbol << 16) | (dt.table[i].num_bits << 24) for i in range(size)],
+                     dtype=np.uint32)
+    assert np.array_equal(dtab.cpu().numpy().view(np.uint32)[0, :size], exp_d)
