@@ -457,6 +457,27 @@ def test_full_size_roundtrip_256mib(ctx):
         assert d[offh[b]:offh[b + 1]].cpu().numpy().tobytes() == O.compress_n(blk, 0, 32)[0]
 
 
+def test_more_than_4gib_on_one_gpu(ctx):
+    """64-bit indexing end to end: 4.25 GiB of incompressible bytes (input offsets, compressed offsets and the dense
+    output all pass 2^32), 128 states, 128 KiB blocks; round trip plus oracle bytes for blocks on both sides of 2^32"""
+    import torch
+    n, bs, ns = (17 << 28) + 12345, 131072, 128
+    src = ctx.generate("uniform", 0xC0FFEE03, n)
+    d, off, st, total = ctx.compress_blocks(src, bs, 11, ns)
+    assert not st.cpu().numpy().any()
+    offh = off.cpu().numpy()
+    nb = len(offh) - 1
+    assert nb == (n + bs - 1) // bs and offh[-1] == total and total > (1 << 32) and (np.diff(offh) > 0).all()
+    for b in (0, nb // 2, int(np.searchsorted(offh, 1 << 32)) - 1, int(np.searchsorted(offh, 1 << 32)), nb - 2, nb - 1):
+        blk = src[b * bs:(b + 1) * bs].cpu().numpy()
+        assert d[int(offh[b]):int(offh[b + 1])].cpu().numpy().tobytes() == O.compress_n(blk, 11, ns)[0], b
+    out, dst_ = ctx.decompress_blocks(d, total, off, n, bs, 11, ns)
+    assert not dst_.cpu().numpy().any()
+    assert torch.equal(out, src)
+    del out, d, src
+    torch.cuda.empty_cache()
+
+
 # ------------------------------------------------------------------------------------ crate mirror
 
 def test_crate_compress_roundtrip():
