@@ -214,9 +214,9 @@ int fse_b200_create(int device, void *stream, fse_b200_ctx **out)
     cudaFuncSetAttribute(k_decode64_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
     cudaFuncSetAttribute(k_decode64c_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
     cudaFuncSetAttribute(k_decode64w_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
-    cudaFuncSetAttribute(k_decode128_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
-    cudaFuncSetAttribute(k_decode128c_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
-    cudaFuncSetAttribute(k_encode128_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
+    cudaFuncSetAttribute(k_decode128_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 64);   // 16 bytes of static shared memory (block queue)
+    cudaFuncSetAttribute(k_decode128c_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 64);   // 16 bytes of static shared memory (block queue)
+    cudaFuncSetAttribute(k_encode128_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 64);   // 16 bytes of static shared memory (block queue)
     cudaFuncSetAttribute(k_build_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { fse_b200_destroy(ctx); return FSE_B200_ERR_CUDA; }
@@ -545,9 +545,11 @@ int fse_b200_compress_blocks_async(fse_b200_ctx *ctx, const uint8_t *d_src, size
     if (wide && tlmax > 13) return fail(ctx, FSE_B200_ERR_UNSUPPORTED, "n_states 64 / 128 need table_log <= 13");
     const size_t per_warp = wide ? enc64_layout(tlmax).total : enc_layout(tlmax).total;
     int wpc = pick_warps(nb, ctx->num_sms, per_warp, ctx->smem_optin, 16);
+    if (p->n_states == 128) wpc = (int)std::min<size_t>(16, (ctx->smem_optin - 64) / per_warp);   // balanced CTA queues: no wave quantisation
     if (wpc < 1) return fail(ctx, FSE_B200_ERR_UNSUPPORTED, "table_log too large for shared memory");
     if (const char *o = getenv("FSE_B200_ENC_WPC")) wpc = std::max(1, std::min(wpc, atoi(o)));   // development override
     int grid = (int)std::min<size_t>((nb + wpc - 1) / wpc, (size_t)ctx->num_sms);
+    if (p->n_states == 128) grid = (int)std::min<size_t>(nb, (size_t)ctx->num_sms);
     a.fused = 0; a.desc = nullptr; a.ticket = nullptr; a.dst = d_dst;
     a.offsets = reinterpret_cast<unsigned long long *>(d_offsets);
     const char *fz = getenv("FSE_B200_FUSED");               // development switch, default off
@@ -625,12 +627,13 @@ int fse_b200_decompress_blocks_async(fse_b200_ctx *ctx, const uint8_t *d_comp, s
         const char *dv = getenv("FSE_B200_DECODE128");          // development switch: "c" compact tables, "w" wide entries
         const bool compact = tlmax <= 12 && !(dv && dv[0] == 'w');
         const size_t per_warp = compact ? dec64c_layout(tlmax).total : dec64w_layout(tlmax).total;
-        int wpc = pick_warps(nblocks, ctx->num_sms * 2, per_warp, std::min(half, ctx->smem_optin), 16);
+        // balanced CTA queues (every CTA gets nblocks / grid blocks): take every warp that fits, two CTAs per SM
+        int wpc = (int)std::min<size_t>(16, (std::min(half, ctx->smem_optin) - 64) / per_warp);
         int ctas = 2;
-        if (wpc < 1) { wpc = pick_warps(nblocks, ctx->num_sms, per_warp, ctx->smem_optin, 16); ctas = 1; }
+        if (wpc < 1) { wpc = (int)std::min<size_t>(16, (ctx->smem_optin - 64) / per_warp); ctas = 1; }
         if (wpc < 1) return fail(ctx, FSE_B200_ERR_UNSUPPORTED, "table_log too large for shared memory");
-        if (const char *o = getenv("FSE_B200_WPC")) wpc = atoi(o);   // development override
-        int grid = (int)std::min<size_t>((nblocks + wpc - 1) / wpc, (size_t)ctx->num_sms * ctas);
+        if (const char *o = getenv("FSE_B200_WPC")) wpc = std::max(1, std::min(wpc, atoi(o)));   // development override
+        int grid = (int)std::min<size_t>(nblocks, (size_t)ctx->num_sms * ctas);
         Timed t(ctx, FSE_B200_K_DECODE);
         if (compact) k_decode128c_blocks<<<grid, wpc * 32, (size_t)wpc * per_warp, ctx->stream>>>(a);
         else k_decode128_blocks<<<grid, wpc * 32, (size_t)wpc * per_warp, ctx->stream>>>(a);

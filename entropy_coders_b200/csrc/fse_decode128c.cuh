@@ -44,7 +44,7 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t saddr)
 __global__ void __launch_bounds__(512, 2) k_decode128c_blocks(DecArgs a)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const Dec64cLayout lay = dec64c_layout(a.tlmax);
     uint8_t *my = smem_raw + (size_t)warp * lay.total;
     uint16_t *tab = reinterpret_cast<uint16_t *>(my + lay.tab);
@@ -73,7 +73,18 @@ __global__ void __launch_bounds__(512, 2) k_decode128c_blocks(DecArgs a)
         __syncwarp();
     }
 
-    for (uint32_t b = blockIdx.x * wpc + warp; b < a.nblocks; b += gridDim.x * wpc) {
+    // blocks are split evenly over the CTAs (every SM gets the same share whatever the warp count is); inside a CTA
+    // the warps take the next block from a shared counter
+    __shared__ uint32_t cta_next;
+    const uint32_t cta_first = (uint32_t)(((unsigned long long)a.nblocks * blockIdx.x) / gridDim.x);
+    const uint32_t cta_last = (uint32_t)(((unsigned long long)a.nblocks * (blockIdx.x + 1)) / gridDim.x);
+    if (threadIdx.x == 0) cta_next = cta_first;
+    __syncthreads();
+    for (;;) {
+        uint32_t b = 0;
+        if (lane == 0) b = atomicAdd(&cta_next, 1u);
+        b = __shfl_sync(FULL, b, 0);
+        if (b >= cta_last) break;
         const size_t off = (size_t)b * a.block_size;
         const uint32_t bn = (uint32_t)min((size_t)a.block_size, a.n - off);
         uint8_t *out = a.dst + off;

@@ -273,7 +273,7 @@ __device__ __forceinline__ unsigned long long lookback_exclusive(unsigned long l
 __global__ void __launch_bounds__(512) k_encode128_blocks(EncArgs a)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const Enc64Layout lay = enc64_layout(a.tlmax);
     uint8_t *my = smem_raw + (size_t)warp * lay.total;
     uint16_t *tab = reinterpret_cast<uint16_t *>(my + lay.tab);
@@ -300,18 +300,19 @@ __global__ void __launch_bounds__(512) k_encode128_blocks(EncArgs a)
         __syncwarp();
     }
 
-    uint32_t bstatic = blockIdx.x * wpc + warp;
+    // blocks are split evenly over the CTAs (every SM gets the same share whatever the warp count is); inside a CTA
+    // the warps take the next block from a shared counter
+    __shared__ uint32_t cta_next;
+    const uint32_t cta_first = (uint32_t)(((unsigned long long)a.nblocks * blockIdx.x) / gridDim.x);
+    const uint32_t cta_last = a.fused ? a.nblocks : (uint32_t)(((unsigned long long)a.nblocks * (blockIdx.x + 1)) / gridDim.x);
+    if (threadIdx.x == 0) cta_next = cta_first;
+    __syncthreads();
     for (;;) {
-        uint32_t b;
-        if (a.fused) {                                       // blocks in index order, whoever is free takes the next
-            b = 0;
-            if (lane == 0) b = atomicAdd(a.ticket, 1u);
-            b = __shfl_sync(FULL, b, 0);
-        } else {
-            b = bstatic;
-            bstatic += gridDim.x * wpc;
-        }
-        if (b >= a.nblocks) break;
+        uint32_t b = 0;
+        if (lane == 0) b = a.fused ? atomicAdd(a.ticket, 1u)     // fused placement: global index order
+                                   : atomicAdd(&cta_next, 1u);
+        b = __shfl_sync(FULL, b, 0);
+        if (b >= cta_last) break;
         const size_t off = (size_t)b * a.block_size;
         const uint32_t bn = (uint32_t)min((size_t)a.block_size, a.n - off);
         const uint8_t *bsrc = a.src + off;
