@@ -348,9 +348,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--table-log", type=int, default=None, help="override the workload's table_log (BASELINE config 3 sweeps 9/11/12)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    if args.table_log is not None:
+        w = list(WORKLOADS[args.workload])
+        w[4] = args.table_log
+        WORKLOADS[args.workload] = tuple(w)
     if args.impl == "reference":
         run_reference(args, args.workload)
     else:
