@@ -17,13 +17,18 @@ constexpr uint32_t HIST16_MAX_BLOCK = 1u << 20;
 
 __device__ __forceinline__ void hist16_word(uint16_t *cnt, uint32_t w)
 {
-    uint32_t b0 = w & 0xff, b1 = (w >> 8) & 0xff, b2 = (w >> 16) & 0xff, b3 = w >> 24;
-    uint32_t c0 = cnt[b0 << 5], c1 = cnt[b1 << 5], c2 = cnt[b2 << 5], c3 = cnt[b3 << 5];
-    uint32_t i1 = (b1 == b0), i2 = (b2 == b0) + (b2 == b1), i3 = (b3 == b0) + (b3 == b1) + (b3 == b2);
-    cnt[b0 << 5] = (uint16_t)(c0 + 1);
-    cnt[b1 << 5] = (uint16_t)(c1 + 1 + i1);
-    cnt[b2 << 5] = (uint16_t)(c2 + 1 + i2);
-    cnt[b3 << 5] = (uint16_t)(c3 + 1 + i3);
+    // byte offsets of the four counters inside the lane's column (bin * 64): extracted once, also used as the keys
+    // of the duplicate test
+    const uint32_t a0 = (w << 6) & 0x3fc0u, a1 = (w >> 2) & 0x3fc0u, a2 = (w >> 10) & 0x3fc0u, a3 = (w >> 18) & 0x3fc0u;
+    uint8_t *col = reinterpret_cast<uint8_t *>(cnt);
+    uint16_t *p0 = reinterpret_cast<uint16_t *>(col + a0), *p1 = reinterpret_cast<uint16_t *>(col + a1);
+    uint16_t *p2 = reinterpret_cast<uint16_t *>(col + a2), *p3 = reinterpret_cast<uint16_t *>(col + a3);
+    uint32_t c0 = *p0, c1 = *p1, c2 = *p2, c3 = *p3;
+    uint32_t i1 = (a1 == a0), i2 = (a2 == a0) + (a2 == a1), i3 = (a3 == a0) + (a3 == a1) + (a3 == a2);
+    *p0 = (uint16_t)(c0 + 1);
+    *p1 = (uint16_t)(c1 + 1 + i1);
+    *p2 = (uint16_t)(c2 + 1 + i2);
+    *p3 = (uint16_t)(c3 + 1 + i3);
 }
 
 __global__ void __launch_bounds__(HIST16_WARPS * 32)
