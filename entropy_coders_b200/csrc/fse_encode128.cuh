@@ -9,15 +9,57 @@
 
 namespace fsed {
 
+// Two forms of the per-symbol transform table, chosen per block when its tables are built:
+//  * PK = 0: the reference's {bits, find_state} pair (fse.rs:80-84) with find_state pre-scaled to a shared byte address,
+//    one 64-bit load per look-up.  Best when few symbols dominate (most lanes read the same entry: a broadcast).
+//  * PK = 1 (table_log <= 12): bits = (mb << 16) - T with T = count << mb (fse.rs:178-186) packed with find_state as
+//    p = mb | T << 4 | find_state << 19, so that (bits + state) >> 16 == mb - (state < T) and (int)p >> 18 == 2 * find_state.
+//    One 32-bit load (a whole warp per wavefront instead of half a warp), two copies interleaved by lane parity to halve the
+//    lanes per bank; four more integer instructions per symbol.  Best when the alphabet is wide (text: -4 %, uniform
+//    bytes: -10 % of the encode kernel; geometric: +5 %, four symbols: +12 %, hence the choice per block).
+constexpr uint32_t TT_REPL_LOG2 = 1;
+__device__ __forceinline__ uint32_t tt_pack(uint2 t)
+{
+    const uint32_t mb = (t.x + 0xffffu) >> 16;
+    const uint32_t T = (mb << 16) - t.x;
+    return mb | (T << 4) | (t.y << 19);
+}
+struct Enc128Tab { uint32_t tt, tab; };    // shared byte addresses: transforms (this lane's copy when packed), next-state table
+template <int PK>
+__device__ __forceinline__ void enc128_step(const Enc128Tab &e, uint32_t sym, uint32_t &state, uint32_t &v, uint32_t &bo)
+{
+    if (PK) {
+        const uint32_t p = lds_u32(e.tt + (sym << (2 + TT_REPL_LOG2)));
+        bo = (p & 15u) - (((state << 4) < (p & 0x3fff0u)) ? 1u : 0u);
+        v = state & ((1u << bo) - 1u);
+        state = lds_u16(e.tab + (uint32_t)((int32_t)p >> 18) + ((state >> bo) << 1));
+    } else {
+        enc_step(e.tt, sym, state, v, bo);
+    }
+}
+template <int PK>
+__device__ __forceinline__ uint32_t enc128_first(const Enc128Tab &e, uint32_t sym)
+{
+    if (PK) {
+        const uint32_t p = lds_u32(e.tt + (sym << (2 + TT_REPL_LOG2)));
+        const uint32_t bits = ((p & 15u) << 16) - ((p >> 4) & 0x3fffu);
+        const uint32_t bo = (bits + (1u << 15)) >> 16;
+        const uint32_t value = (bo << 16) - bits;
+        return lds_u16(e.tab + (uint32_t)((int32_t)p >> 18) + ((value >> bo) << 1));
+    }
+    return enc_first64(e.tt, sym);
+}
+
 // element classes of a symbol index for N = 128 (cf. enc_element_checked)
-__device__ __forceinline__ void enc_element_checked128(const uint8_t *__restrict__ bsrc, int32_t i, int32_t bn, uint32_t tt_saddr,
+template <int PK>
+__device__ __forceinline__ void enc_element_checked128(const uint8_t *__restrict__ bsrc, int32_t i, int32_t bn, const Enc128Tab &tt_saddr,
                                                        uint32_t &state, uint32_t &v, uint32_t &bo)
 {
     v = 0; bo = 0;
     if (i < 0 || i >= bn) return;
     uint32_t sym = __ldg(bsrc + i);
-    if (i >= bn - 128) state = enc_first64(tt_saddr, sym);
-    else enc_step(tt_saddr, sym, state, v, bo);
+    if (i >= bn - 128) state = enc128_first<PK>(tt_saddr, sym);
+    else enc128_step<PK>(tt_saddr, sym, state, v, bo);
 }
 
 // BitRow with the word emission written as predicated PTX: 9 instructions per field instead of the 13 the
@@ -74,7 +116,8 @@ struct BitRowS {
     }
 };
 
-__device__ void encode128_payload_warp(const uint8_t *__restrict__ bsrc, uint32_t bn, uint32_t log2, uint32_t tt_saddr,
+template <int PK>
+__device__ void encode128_payload_warp(const uint8_t *__restrict__ bsrc, uint32_t bn, uint32_t log2, const Enc128Tab tt_saddr,
                                        uint32_t *fld, uint32_t *rows, uint32_t *pay, uint32_t cap_words, int lane,
                                        uint32_t &bits_out, bool &overflow)
 {
@@ -122,16 +165,16 @@ __device__ void encode128_payload_warp(const uint8_t *__restrict__ bsrc, uint32_
                 uint32_t v3, b3, v2, b2, v1, b1, v0, b0;
                 const uint32_t x = sy[r];
                 if (r == 0 && g0 == 0) {                           // Encoder::new_first_symbol: no bits
-                    s3 = enc_first64(tt_saddr, x >> 24);
-                    s2 = enc_first64(tt_saddr, (x >> 16) & 0xff);
-                    s1 = enc_first64(tt_saddr, (x >> 8) & 0xff);
-                    s0 = enc_first64(tt_saddr, x & 0xff);
+                    s3 = enc128_first<PK>(tt_saddr, x >> 24);
+                    s2 = enc128_first<PK>(tt_saddr, (x >> 16) & 0xff);
+                    s1 = enc128_first<PK>(tt_saddr, (x >> 8) & 0xff);
+                    s0 = enc128_first<PK>(tt_saddr, x & 0xff);
                     v3 = v2 = v1 = v0 = b3 = b2 = b1 = b0 = 0;
                 } else {
-                    enc_step(tt_saddr, x >> 24, s3, v3, b3);       // decreasing index order: 4m+3 first
-                    enc_step(tt_saddr, (x >> 16) & 0xff, s2, v2, b2);
-                    enc_step(tt_saddr, (x >> 8) & 0xff, s1, v1, b1);
-                    enc_step(tt_saddr, x & 0xff, s0, v0, b0);
+                    enc128_step<PK>(tt_saddr, x >> 24, s3, v3, b3);       // decreasing index order: 4m+3 first
+                    enc128_step<PK>(tt_saddr, (x >> 16) & 0xff, s2, v2, b2);
+                    enc128_step<PK>(tt_saddr, (x >> 8) & 0xff, s1, v1, b1);
+                    enc128_step<PK>(tt_saddr, x & 0xff, s0, v0, b0);
                 }
                 uint2 f;
                 {                                                  // the quad as one field of <= 52 bits: (hi:lo), length in hi[26..31]
@@ -147,10 +190,10 @@ __device__ void encode128_payload_warp(const uint8_t *__restrict__ bsrc, uint32_
                 int32_t m = mtop - (int32_t)((g0 + r) << 5);
                 int32_t i = m < 0 ? -8 : 4 * m;
                 uint32_t v3, b3, v2, b2, v1, b1, v0, b0;
-                enc_element_checked128(bsrc, i + 3, (int32_t)bn, tt_saddr, s3, v3, b3);
-                enc_element_checked128(bsrc, i + 2, (int32_t)bn, tt_saddr, s2, v2, b2);
-                enc_element_checked128(bsrc, i + 1, (int32_t)bn, tt_saddr, s1, v1, b1);
-                enc_element_checked128(bsrc, i, (int32_t)bn, tt_saddr, s0, v0, b0);
+                enc_element_checked128<PK>(bsrc, i + 3, (int32_t)bn, tt_saddr, s3, v3, b3);
+                enc_element_checked128<PK>(bsrc, i + 2, (int32_t)bn, tt_saddr, s2, v2, b2);
+                enc_element_checked128<PK>(bsrc, i + 1, (int32_t)bn, tt_saddr, s1, v1, b1);
+                enc_element_checked128<PK>(bsrc, i, (int32_t)bn, tt_saddr, s0, v0, b0);
                 uint2 f;
                 {                                                  // the quad as one field of <= 52 bits: (hi:lo), length in hi[26..31]
                     const uint32_t p1 = v3 | (v2 << b3), n1 = b3 + b2, p0 = v1 | (v0 << b1);
@@ -292,7 +335,7 @@ __global__ void __launch_bounds__(512) k_encode128_blocks(EncArgs a)
     if (a.global_mode) {
         glog2 = a.g.log2;
         for (uint32_t i = lane; i < (1u << glog2); i += 32) tab[i] = a.g.enc_table[i];
-        for (uint32_t i = lane; i < 256; i += 32) {
+        for (uint32_t i = lane; i < 256; i += 32) {          // global mode keeps the 64-bit form
             uint2 t = a.g.enc_tt[i];
             t.y = tab_saddr + 2u * t.y;
             tt[i] = t;
@@ -321,6 +364,7 @@ __global__ void __launch_bounds__(512) k_encode128_blocks(EncArgs a)
         uint32_t *pay = reinterpret_cast<uint32_t *>(bs + HDR_RESERVE);
         uint32_t log2 = glog2;
         uint32_t hl = 0, pl = 0;                             // header / payload bytes of this block (warp uniform)
+        bool packed = false;                                 // form of this block's symbol transforms
         int st = ST_OK;
         __syncwarp();
         do {
@@ -348,11 +392,32 @@ __global__ void __launch_bounds__(512) k_encode128_blocks(EncArgs a)
                 hl = (hbits + 7) >> 3;
                 warp_spread(norm, log2, table_len, spread, cum, tab, lane);
                 warp_build_encode(norm, log2, table_len, spread, cum, tab, tt, lane);
+                {
+                    // collision probability of the block's distribution: sum p^2 < 1/12 -> wide alphabet -> packed form
+                    uint32_t sq = 0;
 #pragma unroll
-                for (int k = 0; k < 8; k++) {                // pre-scale find_state to a shared-memory byte address
-                    uint2 t = tt[k * 32 + lane];
-                    t.y = tab_saddr + 2u * t.y;
-                    tt[k * 32 + lane] = t;
+                    for (int k = 0; k < 8; k++) { const int32_t x = norm[lane * 8 + k]; sq += (uint32_t)(x * x); }
+#pragma unroll
+                    for (int d = 16; d; d >>= 1) sq += __shfl_xor_sync(FULL, sq, d);
+                    packed = log2 <= 12 && (uint64_t)sq * 12u < ((uint64_t)1 << (2 * log2));
+                }
+                if (packed) {                                // two interleaved copies of the 32-bit form, in place
+                    uint32_t pk[8];
+#pragma unroll
+                    for (int k = 0; k < 8; k++) pk[k] = tt_pack(tt[k * 32 + lane]);
+                    __syncwarp();
+#pragma unroll
+                    for (int k = 0; k < 8; k++)
+#pragma unroll
+                        for (int r = 0; r < (1 << TT_REPL_LOG2); r++)
+                            reinterpret_cast<uint32_t *>(tt)[((k * 32 + lane) << TT_REPL_LOG2) + r] = pk[k];
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {            // pre-scale find_state to a shared-memory byte address
+                        uint2 t = tt[k * 32 + lane];
+                        t.y = tab_saddr + 2u * t.y;
+                        tt[k * 32 + lane] = t;
+                    }
                 }
                 __syncwarp();
             } else if (bn < N) {                             // global mode: a short tail is stored raw, no escape
@@ -362,7 +427,13 @@ __global__ void __launch_bounds__(512) k_encode128_blocks(EncArgs a)
             }
             uint32_t pbits;
             bool ovf;
-            encode128_payload_warp(bsrc, bn, log2, tt_saddr, fld, rows, pay, a.pay_cap_words, lane, pbits, ovf);
+                        if (packed) {
+                const Enc128Tab et{tt_saddr + 4u * ((uint32_t)lane & ((1u << TT_REPL_LOG2) - 1u)), tab_saddr};
+                encode128_payload_warp<1>(bsrc, bn, log2, et, fld, rows, pay, a.pay_cap_words, lane, pbits, ovf);
+            } else {
+                const Enc128Tab et{tt_saddr, tab_saddr};
+                encode128_payload_warp<0>(bsrc, bn, log2, et, fld, rows, pay, a.pay_cap_words, lane, pbits, ovf);
+            }
             if (ovf) { st = ST_CAPACITY; hl = 0; pl = 0; }
             else pl = (pbits + 7) >> 3;
         } while (0);
