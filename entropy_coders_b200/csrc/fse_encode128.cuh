@@ -12,27 +12,28 @@ namespace fsed {
 // Two forms of the per-symbol transform table, chosen per block when its tables are built:
 //  * PK = 0: the reference's {bits, find_state} pair (fse.rs:80-84) with find_state pre-scaled to a shared byte address,
 //    one 64-bit load per look-up.  Best when few symbols dominate (most lanes read the same entry: a broadcast).
-//  * PK = 1 (table_log <= 12): bits = (mb << 16) - T with T = count << mb (fse.rs:178-186) packed with find_state as
-//    p = mb | T << 4 | find_state << 19, so that (bits + state) >> 16 == mb - (state < T) and (int)p >> 18 == 2 * find_state.
-//    One 32-bit load (a whole warp per wavefront instead of half a warp), two copies interleaved by lane parity to halve the
-//    lanes per bank; four more integer instructions per symbol.  Best when the alphabet is wide (text: -4 %, uniform
-//    bytes: -10 % of the encode kernel; geometric: +5 %, four symbols: +12 %, hence the choice per block).
+//  * PK = 1 (table_log <= 11): p = bits | find_state << 20.  bits < 2^20 and bits + state never carries into bit 20, so
+//    t = p + state keeps find_state in the top 12 bits and (t >> 16) & 15 is the reference's (bits + state) >> 16
+//    (fse.rs:228).  One 32-bit load (a whole warp per wavefront instead of half a warp), two copies interleaved by lane
+//    parity to halve the lanes per bank; three more integer instructions per symbol.  Measured against PK = 0 on the
+//    encode kernel: text -8 %, uniform bytes -11 %, geometric -2 %, four symbols +0.6 % (there nearly every 64-bit
+//    load is a broadcast): hence the choice per block, by the collision probability of the normalised counts.
+#ifndef FSE_TT_THR
+#define FSE_TT_THR 2u     /* packed form iff sum p^2 < 1 / FSE_TT_THR */
+#endif
 constexpr uint32_t TT_REPL_LOG2 = 1;
-__device__ __forceinline__ uint32_t tt_pack(uint2 t)
-{
-    const uint32_t mb = (t.x + 0xffffu) >> 16;
-    const uint32_t T = (mb << 16) - t.x;
-    return mb | (T << 4) | (t.y << 19);
-}
+constexpr uint32_t TT_PACKED_MAX_LOG2 = 11;
+__device__ __forceinline__ uint32_t tt_pack(uint2 t) { return (t.x & 0xfffffu) | (t.y << 20); }
 struct Enc128Tab { uint32_t tt, tab; };    // shared byte addresses: transforms (this lane's copy when packed), next-state table
 template <int PK>
 __device__ __forceinline__ void enc128_step(const Enc128Tab &e, uint32_t sym, uint32_t &state, uint32_t &v, uint32_t &bo)
 {
     if (PK) {
-        const uint32_t p = lds_u32(e.tt + (sym << (2 + TT_REPL_LOG2)));
-        bo = (p & 15u) - (((state << 4) < (p & 0x3fff0u)) ? 1u : 0u);
-        v = state & ((1u << bo) - 1u);
-        state = lds_u16(e.tab + (uint32_t)((int32_t)p >> 18) + ((state >> bo) << 1));
+        const uint32_t t = lds_u32(e.tt + (sym << (2 + TT_REPL_LOG2))) + state;
+        bo = (t >> 16) & 15u;
+        const uint32_t q = state >> bo;
+        v = state - (q << bo);
+        state = lds_u16(e.tab + (((uint32_t)((int32_t)t >> 20) + q) << 1));
     } else {
         enc_step(e.tt, sym, state, v, bo);
     }
@@ -42,10 +43,10 @@ __device__ __forceinline__ uint32_t enc128_first(const Enc128Tab &e, uint32_t sy
 {
     if (PK) {
         const uint32_t p = lds_u32(e.tt + (sym << (2 + TT_REPL_LOG2)));
-        const uint32_t bits = ((p & 15u) << 16) - ((p >> 4) & 0x3fffu);
+        const uint32_t bits = p & 0xfffffu;
         const uint32_t bo = (bits + (1u << 15)) >> 16;
         const uint32_t value = (bo << 16) - bits;
-        return lds_u16(e.tab + (uint32_t)((int32_t)p >> 18) + ((value >> bo) << 1));
+        return lds_u16(e.tab + (((uint32_t)((int32_t)p >> 20) + (value >> bo)) << 1));
     }
     return enc_first64(e.tt, sym);
 }
@@ -393,13 +394,13 @@ __global__ void __launch_bounds__(512) k_encode128_blocks(EncArgs a)
                 warp_spread(norm, log2, table_len, spread, cum, tab, lane);
                 warp_build_encode(norm, log2, table_len, spread, cum, tab, tt, lane);
                 {
-                    // collision probability of the block's distribution: sum p^2 < 1/12 -> wide alphabet -> packed form
+                    // collision probability of the block's distribution: unless one symbol dominates (sum p^2 >= 1/2) -> packed form
                     uint32_t sq = 0;
 #pragma unroll
                     for (int k = 0; k < 8; k++) { const int32_t x = norm[lane * 8 + k]; sq += (uint32_t)(x * x); }
 #pragma unroll
                     for (int d = 16; d; d >>= 1) sq += __shfl_xor_sync(FULL, sq, d);
-                    packed = log2 <= 12 && (uint64_t)sq * 12u < ((uint64_t)1 << (2 * log2));
+                    packed = log2 <= TT_PACKED_MAX_LOG2 && (uint64_t)sq * FSE_TT_THR < ((uint64_t)1 << (2 * log2));
                 }
                 if (packed) {                                // two interleaved copies of the 32-bit form, in place
                     uint32_t pk[8];
