@@ -7,6 +7,11 @@
 #pragma once
 #include "fse_kernels128.cuh"
 
+// FSE_DIAG (development, tools/diag_enc.py): 1 = skip pass 2 / placement / output, 2 = skip the table look-ups of pass 1.
+// The output of such a build is garbage; only the kernel time is meaningful.
+#ifndef FSE_DIAG
+#define FSE_DIAG 0
+#endif
 namespace fsed {
 
 // Two forms of the per-symbol transform table, chosen per block when its tables are built:
@@ -172,10 +177,14 @@ __device__ void encode128_payload_warp(const uint8_t *__restrict__ bsrc, uint32_
                     s0 = enc128_first<PK>(tt_saddr, x & 0xff);
                     v3 = v2 = v1 = v0 = b3 = b2 = b1 = b0 = 0;
                 } else {
+#if FSE_DIAG == 2                                               // timing experiment: no table look-ups
+                    v3 = x >> 27; b3 = 5; v2 = (x >> 16) & 31; b2 = 5; v1 = (x >> 8) & 31; b1 = 5; v0 = x & 31; b0 = 6;
+#else
                     enc128_step<PK>(tt_saddr, x >> 24, s3, v3, b3);       // decreasing index order: 4m+3 first
                     enc128_step<PK>(tt_saddr, (x >> 16) & 0xff, s2, v2, b2);
                     enc128_step<PK>(tt_saddr, (x >> 8) & 0xff, s1, v1, b1);
                     enc128_step<PK>(tt_saddr, x & 0xff, s0, v0, b0);
+#endif
                 }
                 uint2 f;
                 {                                                  // the quad as one field of <= 52 bits: (hi:lo), length in hi[26..31]
@@ -207,6 +216,9 @@ __device__ void encode128_payload_warp(const uint8_t *__restrict__ bsrc, uint32_
         }
         if (g0 + 16 < G) fetch(g0 + 16);
         __syncwarp();
+#if FSE_DIAG == 1                                               // timing experiment: no transpose / placement / output
+        wdone += 300; continue;
+#endif
         // pass 2: lane L serialises half a round: 32 merged pairs that are consecutive in the stream
         BitRowS br;
         br.init(myrow, lane == 0 ? cw : 0u, lane == 0 ? cb : 0u);
