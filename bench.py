@@ -273,7 +273,7 @@ def run_ours(args, wl):
     achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this
     # workload (profiles/r1_ncu_full_c2_n128.txt); only meaningful for the configuration that was profiled
-    traffic = {"encode": 272.99e6 + 146.01e6, "decode": 179.75e6 + 219.48e6}[dom] if (wl == "c2" and N_STATES == 128) else None
+    traffic = {"encode": 272.98e6 + 143.34e6, "decode": 179.75e6 + 219.48e6}[dom] if (wl == "c2" and N_STATES == 128) else None
 
     # e2e: host buffers through the host entry points, copies inside the timed region (rank-local data)
     e2e = None
