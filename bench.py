@@ -31,6 +31,8 @@ sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
 
 WORKLOADS = {
     # name: (generator kind, seed, bytes per GPU, block size, table_log, table_mode, BASELINE.json config)
+    # c1 is the reference's own CPU case (benches/fse_benchmark.rs): one stream, two states; only --impl reference runs it
+    "c1": ("geo", 0xC0FFEE01, 1 << 20, 1 << 20, 11, 0, "1 MiB synthetic skewed bytes (geometric 0.2), one stream, table_log 11, fse_compress2 + fse_decompress2"),
     "c2": ("text", 0xC0FFEE02, 256 << 20, 65536, 0, 0, "256 MiB synthetic text-like bytes, 64 KiB blocks, per-block tables"),
     "c3few": ("few", 0xC0FFEE03, 1 << 30, 65536, 11, 0, "1 GiB low-entropy (few-symbol) bytes, 64 KiB blocks"),
     "c3uni": ("uniform", 0xC0FFEE03, 1 << 30, 65536, 11, 0, "1 GiB near-uniform random bytes, 64 KiB blocks"),
@@ -134,6 +136,8 @@ def run_reference(args, wl):
         return
     threads = os.cpu_count() or 1
     sample = 64 << 20
+    if wl == "c1":                                            # a single stream is serial: one core, the whole MiB
+        threads, sample = 1, nbytes
     vals = []
     for _ in range(args.warmup):
         cpu_port_throughput(kind, seed, bs, sample, threads)
@@ -358,6 +362,9 @@ def main():
         WORKLOADS[args.workload] = tuple(w)
     if args.impl == "reference":
         run_reference(args, args.workload)
+    elif args.workload == "c1":
+        sys.exit("c1 is the reference's single-stream CPU case: run it with --impl reference (the GPU path codes it "
+                 "bit-exactly in tests/test_gpu_parity.py::test_crate_compress_roundtrip, one lane, not a throughput case)")
     else:
         run_ours(args, args.workload)
 
