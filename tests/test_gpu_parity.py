@@ -457,6 +457,19 @@ def test_full_size_roundtrip_256mib(ctx):
         assert d[offh[b]:offh[b + 1]].cpu().numpy().tobytes() == O.compress_n(blk, 0, 32)[0]
 
 
+@pytest.mark.parametrize("n_states", [32, 128])
+def test_blocks_of_4_mib(ctx, n_states):
+    """blocks beyond the 16-bit histogram kernel's 1 MiB (32-bit counter columns, one CTA per block) and far beyond one
+    chunk of the encoder: bytes equal the oracle's, round trip exact"""
+    bs, n = 4 << 20, (9 << 20) + 777
+    src = O.generate("text", 21, n)
+    blocks, st, (d, off, total) = gpu_blocks(ctx, src, bs, 0, n_states)
+    exp = oracle_blocks(src, bs, 0, n_states)
+    assert not st.any() and all(g == e for g, e in zip(blocks, exp))
+    out, dst_ = ctx.decompress_blocks(d, total, dev(ctx, off), n, bs, 0, n_states)
+    assert not dst_.cpu().numpy().any() and np.array_equal(out.cpu().numpy(), src)
+
+
 def test_more_than_4gib_on_one_gpu(ctx):
     """64-bit indexing end to end: 4.25 GiB of incompressible bytes (input offsets, compressed offsets and the dense
     output all pass 2^32), 128 states, 128 KiB blocks; round trip plus oracle bytes for blocks on both sides of 2^32"""
