@@ -1,9 +1,11 @@
 // fse_encode128.cuh -- 128-state encode: four adjacent states per lane (see fse_kernels128.cuh).
 //
 // Per chunk of 16 rounds (2 048 symbols): pass 1 runs four independent state chains per lane from one
-// 32-bit symbol load per round and stores the quad's two merged pair fields with one 64-bit store; pass 2
-// and the placement are those of the 64-state path (32 merged pair fields per lane, lane order == stream
-// order): lane L serialises the half row (round L>>1, half L&1).
+// 32-bit symbol load per round and stores the quad as ONE field of up to 52 bits (64-bit store, length in the
+// top 6 bits); pass 2 transposes: lane L serialises the half row (round L>>1, half L&1) = 16 quad fields that are
+// consecutive in the stream into a private bit string; warp_place concatenates the 32 strings (lane order ==
+// stream order).  The symbol transforms live in shared memory in one of two forms chosen per block (below).
+// Blocks are split evenly over the CTAs; the warps of a CTA take them from a shared counter.
 #pragma once
 #include "fse_kernels128.cuh"
 
