@@ -222,7 +222,8 @@ __global__ void __launch_bounds__(512, 2) k_decode128c_blocks(DecArgs a)
         uint32_t i0 = 0;
         for (; i0 + 128 <= body; i0 += 128) {
             stage();
-            uint32_t e0 = lds_u16(tab_saddr + s0 * 2), e1 = lds_u16(tab_saddr + s1 * 2);   // fse.rs:363-373, four chains
+            // fse.rs:363-373, four chains.  new_state + bits is an OR: the entry's base is a multiple of 1 << num_bits
+            uint32_t e0 = lds_u16(tab_saddr + s0 * 2), e1 = lds_u16(tab_saddr + s1 * 2);
             uint32_t e2 = lds_u16(tab_saddr + s2 * 2), e3 = lds_u16(tab_saddr + s3 * 2);
             uint32_t y0 = lds_u8(sym_saddr + s0), y1 = lds_u8(sym_saddr + s1), y2 = lds_u8(sym_saddr + s2), y3 = lds_u8(sym_saddr + s3);
             uint32_t n0 = e0 >> 12, n1 = e1 >> 12, n2 = e2 >> 12, n3 = e3 >> 12;
@@ -231,10 +232,10 @@ __global__ void __launch_bounds__(512, 2) k_decode128c_blocks(DecArgs a)
             uint64_t w = ring_bits64(cur - incl);           // state 4l's bits are the uppermost of the lane's window
             uint32_t tot = __shfl_sync(FULL, incl, 31);
             if (tot > cur - floor_bits) { bad = true; break; }
-            s0 = (e0 & 0xfffu) + ((uint32_t)(w >> n123) & ~(0xffffffffu << n0));
-            s1 = (e1 & 0xfffu) + ((uint32_t)(w >> n23) & ~(0xffffffffu << n1));
-            s2 = (e2 & 0xfffu) + ((uint32_t)(w >> n3) & ~(0xffffffffu << n2));
-            s3 = (e3 & 0xfffu) + ((uint32_t)w & ~(0xffffffffu << n3));
+            s0 = (e0 & 0xfffu) | ((uint32_t)(w >> n123) & ~(0xffffffffu << n0));
+            s1 = (e1 & 0xfffu) | ((uint32_t)(w >> n23) & ~(0xffffffffu << n1));
+            s2 = (e2 & 0xfffu) | ((uint32_t)(w >> n3) & ~(0xffffffffu << n2));
+            s3 = (e3 & 0xfffu) | ((uint32_t)w & ~(0xffffffffu << n3));
             uint32_t sy = y0 | (y1 << 8) | (y2 << 16) | (y3 << 24);
             if (out_aligned) *reinterpret_cast<uint32_t *>(out + i0 + 4 * lane) = sy;
             else {
@@ -255,10 +256,10 @@ __global__ void __launch_bounds__(512, 2) k_decode128c_blocks(DecArgs a)
             if (tot > cur - floor_bits) bad = true;
             else {
                 uint64_t w = ring_bits64(cur - incl);
-                if (ia < body) { out[ia] = sym[s0]; s0 = (e0 & 0xfffu) + ((uint32_t)(w >> n123) & ~(0xffffffffu << n0)); }
-                if (ia + 1 < body) { out[ia + 1] = sym[s1]; s1 = (e1 & 0xfffu) + ((uint32_t)(w >> n23) & ~(0xffffffffu << n1)); }
-                if (ia + 2 < body) { out[ia + 2] = sym[s2]; s2 = (e2 & 0xfffu) + ((uint32_t)(w >> n3) & ~(0xffffffffu << n2)); }
-                if (ia + 3 < body) { out[ia + 3] = sym[s3]; s3 = (e3 & 0xfffu) + ((uint32_t)w & ~(0xffffffffu << n3)); }
+                if (ia < body) { out[ia] = sym[s0]; s0 = (e0 & 0xfffu) | ((uint32_t)(w >> n123) & ~(0xffffffffu << n0)); }
+                if (ia + 1 < body) { out[ia + 1] = sym[s1]; s1 = (e1 & 0xfffu) | ((uint32_t)(w >> n23) & ~(0xffffffffu << n1)); }
+                if (ia + 2 < body) { out[ia + 2] = sym[s2]; s2 = (e2 & 0xfffu) | ((uint32_t)(w >> n3) & ~(0xffffffffu << n2)); }
+                if (ia + 3 < body) { out[ia + 3] = sym[s3]; s3 = (e3 & 0xfffu) | ((uint32_t)w & ~(0xffffffffu << n3)); }
                 cur -= tot;
             }
         }
