@@ -1,6 +1,8 @@
 """Hypothesis-driven differential tests, CUDA path (through the C ABI) against the CPU oracle:
 generated alphabets, skews, runs, block sizes, state counts and table_log; every block is either the oracle's bytes
 or one the reference panics on (then it carries an escape), and decode always returns the input."""
+import os
+
 import numpy as np
 import pytest
 from hypothesis import HealthCheck, given, settings, strategies as st
@@ -11,7 +13,8 @@ from test_oracle_properties import byte_strings
 
 pytestmark = pytest.mark.gpu
 
-COMMON = dict(deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large,
+SCALE = int(os.environ.get("FSE_HYP_SCALE", "1"))       # FSE_HYP_SCALE=20 for a long soak
+COMMON = dict(deadline=None, derandomize=SCALE == 1, suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large,
                                                     HealthCheck.function_scoped_fixture])
 
 
@@ -23,7 +26,7 @@ def ctx():
     c.close()
 
 
-@settings(max_examples=120, **COMMON)
+@settings(max_examples=120 * SCALE, **COMMON)
 @given(byte_strings(min_size=1, max_size=40000), st.sampled_from([1, 2, 4, 8, 16, 32, 64, 128]),
        st.sampled_from([130, 257, 1000, 4096, 5000, 20000]), st.sampled_from([0, 0, 5, 9, 11, 12]))
 def test_blocks_equal_the_oracle_and_round_trip(ctx, data, n_states, bs, tl):
@@ -44,7 +47,7 @@ def test_blocks_equal_the_oracle_and_round_trip(ctx, data, n_states, bs, tl):
     assert (dst_.cpu().numpy() >= 0).all() and np.array_equal(out.cpu().numpy(), data)
 
 
-@settings(max_examples=60, **COMMON)
+@settings(max_examples=60 * SCALE, **COMMON)
 @given(byte_strings(min_size=300, max_size=30000), st.sampled_from([32, 64, 128]), st.sampled_from([9, 11, 12]))
 def test_stage_outputs_equal_the_oracle(ctx, data, n_states, tl):
     """histogram -> normalise -> header -> tables through the stage entry points, one table"""

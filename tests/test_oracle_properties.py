@@ -14,7 +14,8 @@ import oracle_lib as O
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
 import pymodel as M  # noqa: E402
 
-COMMON = dict(deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large])
+SCALE = int(os.environ.get("FSE_HYP_SCALE", "1"))       # FSE_HYP_SCALE=20 for a long soak
+COMMON = dict(deadline=None, derandomize=SCALE == 1, suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large])
 
 
 @st.composite
@@ -34,7 +35,7 @@ def byte_strings(draw, min_size=0, max_size=6000):
     return out
 
 
-@settings(max_examples=150, **COMMON)
+@settings(max_examples=150 * SCALE, **COMMON)
 @given(byte_strings(min_size=1), st.sampled_from([0, 5, 7, 9, 11, 12, 13, 15]))
 def test_normalize_sums_to_table_size_and_keeps_zeros(data, tl):
     """histogram.rs:566-577: sum |norm| == 1 << log2; norm[i] == 0 exactly where count[i] == 0"""
@@ -52,7 +53,7 @@ def test_normalize_sums_to_table_size_and_keeps_zeros(data, tl):
     assert n.log2 >= tl and n.table_len == h.table_len
 
 
-@settings(max_examples=150, **COMMON)
+@settings(max_examples=150 * SCALE, **COMMON)
 @given(byte_strings(min_size=2), st.sampled_from([0, 6, 9, 11, 14]), st.binary(max_size=9))
 def test_header_write_read_identity_with_trailing_bytes(data, tl, trailer):
     """histogram.rs:580-586: read(write(n) ++ tail) == (n, tail)"""
@@ -71,7 +72,7 @@ def test_header_write_read_identity_with_trailing_bytes(data, tl, trailer):
     assert list(back.table[:256]) == list(n.table[:256])
 
 
-@settings(max_examples=120, **COMMON)
+@settings(max_examples=120 * SCALE, **COMMON)
 @given(byte_strings(min_size=1, max_size=5000), st.sampled_from([1, 2, 4, 8, 32, 64, 128]), st.sampled_from([0, 0, 9, 11, 12]))
 def test_round_trip_any_state_count(data, n_states, tl):
     """lib.rs:280-302 / fse.rs:479-506 generalised to N states: decode(encode(x)) == x, the stream is consumed exactly"""
@@ -83,7 +84,7 @@ def test_round_trip_any_state_count(data, n_states, tl):
     assert O.decompress_n_len(comp, n_states, data.size) == data.tobytes()
 
 
-@settings(max_examples=60, **COMMON)
+@settings(max_examples=60 * SCALE, **COMMON)
 @given(byte_strings(min_size=2, max_size=700), st.integers(0, 7))
 def test_c_oracle_equals_mechanics_model(data, align):
     """the C restatement and the Python model of the reference's mechanics (accumulator, Vec growth, pointer
@@ -98,7 +99,7 @@ def test_c_oracle_equals_mechanics_model(data, align):
         assert vec.bytes() == comp, n_states
 
 
-@settings(max_examples=60, **COMMON)
+@settings(max_examples=60 * SCALE, **COMMON)
 @given(byte_strings(min_size=2, max_size=3000))
 def test_reference_loop_structure_equals_generic_two_state_codec(data):
     """oracle: the literal lib.rs:146-183 / :215-248 loops (CPU baseline) == the N-state codec at N = 2"""
