@@ -42,6 +42,12 @@ class Context:
         self._L = _capi.lib()
         self.device = torch.device("cuda", device)
         self._h = C.c_void_p()
+        if stream is None:
+            # Run on torch's current stream, so that tensors produced by (asynchronous) torch operations are ordered
+            # before the library's kernels.  torch's default stream is the legacy default stream, whose handle is 0;
+            # the C ABI reads NULL as "create a private stream", so it is passed as cudaStreamLegacy (1).
+            with torch.cuda.device(self.device):
+                stream = torch.cuda.current_stream(self.device).cuda_stream or 1
         s = C.c_void_p(stream) if stream else None
         rc = self._L.fse_b200_create(device, s, C.byref(self._h))
         if rc != 0:
