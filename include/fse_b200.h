@@ -86,7 +86,9 @@ typedef struct { uint16_t new_state; uint8_t symbol; uint8_t num_bits; } fse_b20
 typedef struct fse_b200_ctx fse_b200_ctx;
 
 /* ---- context ------------------------------------------------------------------------------- */
-/* stream: a cudaStream_t (or NULL for a context-owned stream).  The context owns device
+/* stream: a cudaStream_t, or NULL for a context-owned non-blocking stream (then inputs produced on other
+ * streams must be complete, or ordered by an event, before a call; pass cudaStreamLegacy to run on the
+ * legacy default stream).  All work of a context is issued on this stream.  The context owns device
  * workspaces that grow on demand and are reused across calls (the analogue of
  * EncodeTable::update / DecodeTable::update reusing their Vecs, src/fse.rs:101,280). */
 int fse_b200_create(int device, void *stream, fse_b200_ctx **out);
