@@ -79,3 +79,30 @@ def test_stage_outputs_equal_the_oracle(ctx, data, n_states, tl):
     exp_d = np.array([dt.table[i].new_state | (dt.table[i].symbol << 16) | (dt.table[i].num_bits << 24) for i in range(size)],
                      dtype=np.uint32)
     assert np.array_equal(dtab.cpu().numpy().view(np.uint32)[0, :size], exp_d)
+
+
+@settings(max_examples=40 * SCALE, **COMMON)
+@given(byte_strings(min_size=1, max_size=60000), st.sampled_from([1, 2, 32, 64, 128]), st.sampled_from([300, 4096, 20000]),
+       st.sampled_from([0, 9, 11]), st.sampled_from([0, 1]))
+def test_frames_and_host_buffers_round_trip(ctx, data, n_states, bs, tl, mode):
+    """fse_b200_frame_* and fse_b200_compress_host / decompress_host, per-block and global tables: what goes in comes
+    out, and in per-block mode the host path's bytes are the device path's"""
+    if n_states <= 2:
+        data = data[:5000]
+    import entropy_coders_b200 as E
+    if mode == 1 and (O.histogram(data).table_len <= 1 or data.size < 8):
+        return                                               # one global table needs two symbols (histogram.rs:98)
+    try:
+        frame = ctx.frame_compress(data, bs, tl, n_states, mode)
+    except E.FseError as e:
+        assert mode == 1, e                                  # per-block mode never fails: escapes cover every block
+        return
+    info = ctx.frame_info(frame)
+    assert info["n"] == data.size and info["n_states"] == n_states and info["table_mode"] == mode
+    assert np.array_equal(ctx.frame_decompress(frame), data)
+    if mode == 0:
+        dst, off, stat, total = ctx.compress_host(data, bs, tl, n_states)
+        blocks, stat_d, _ = gpu_blocks(ctx, data, bs, tl, n_states)
+        assert dst[:total].tobytes() == b"".join(blocks) and np.array_equal(stat[:len(blocks)], stat_d)
+        out, st2 = ctx.decompress_host(dst, total, off, data.size, bs, tl, n_states)
+        assert (st2[:len(blocks)] >= 0).all() and np.array_equal(out[:data.size], data)
