@@ -106,3 +106,26 @@ def test_frames_and_host_buffers_round_trip(ctx, data, n_states, bs, tl, mode):
         assert dst[:total].tobytes() == b"".join(blocks) and np.array_equal(stat[:len(blocks)], stat_d)
         out, st2 = ctx.decompress_host(dst, total, off, data.size, bs, tl, n_states)
         assert (st2[:len(blocks)] >= 0).all() and np.array_equal(out[:data.size], data)
+
+
+@settings(max_examples=60 * SCALE, **COMMON)
+@given(byte_strings(min_size=2, max_size=3000), st.sampled_from([1, 2]))
+def test_reference_termination_rule(ctx, data, n_states):
+    """fse_decompress / fse_decompress2 (lib.rs:187-248) stop on bit exhaustion: the exhaust-mode kernel yields what the
+    oracle's literal restatement of that loop yields, surplus symbols included"""
+    try:
+        comp = O.compress_n(data, 0, n_states)[0]
+    except ValueError:
+        return
+    cap = 4 * data.size + 64
+    try:
+        exp = O.decompress_n_exhaust(comp, n_states, cap)
+    except ValueError:
+        exp = None
+    off = np.array([0, len(comp)], np.int64)
+    out, out_len, st = ctx.decompress_exhaust(dev(ctx, np.frombuffer(comp, np.uint8).copy()), len(comp), dev(ctx, off), 1, cap, 15, n_states)
+    if exp is None or len(exp) > cap:
+        assert int(st.cpu()[0]) == -2
+    else:
+        assert int(st.cpu()[0]) == 0 and int(out_len.cpu()[0]) == len(exp)
+        assert out.cpu().numpy()[0, :len(exp)].tobytes() == exp and exp[:data.size] == data.tobytes()
