@@ -26,13 +26,26 @@ def ctx():
     c.close()
 
 
+def gpu_blocks_at(ctx, src, block_size, table_log, n_states, shift):
+    """gpu_blocks with the source at byte offset `shift` of its allocation (unaligned vector-load paths)"""
+    import torch
+    buf = torch.empty(src.size + 16, dtype=torch.uint8, device=ctx.device)
+    view = buf[shift:shift + src.size]
+    view.copy_(torch.from_numpy(np.ascontiguousarray(src)))
+    d, off, st, total = ctx.compress_blocks(view, block_size, table_log, n_states)
+    off = off.cpu().numpy().astype(np.int64)
+    raw = d[:total].cpu().numpy().tobytes()
+    assert off[0] == 0 and off[-1] == total
+    return [raw[off[i]:off[i + 1]] for i in range(len(off) - 1)], st.cpu().numpy(), (d, off, total)
+
+
 @settings(max_examples=120 * SCALE, **COMMON)
 @given(byte_strings(min_size=1, max_size=40000), st.sampled_from([1, 2, 4, 8, 16, 32, 64, 128]),
-       st.sampled_from([130, 257, 1000, 4096, 5000, 20000]), st.sampled_from([0, 0, 5, 9, 11, 12]))
-def test_blocks_equal_the_oracle_and_round_trip(ctx, data, n_states, bs, tl):
+       st.sampled_from([130, 257, 1000, 4096, 5000, 20000]), st.sampled_from([0, 0, 5, 9, 11, 12]), st.integers(0, 15))
+def test_blocks_equal_the_oracle_and_round_trip(ctx, data, n_states, bs, tl, shift):
     if n_states <= 2:
         data = data[:6000]                                   # the one-lane paths are for parity, not speed
-    blocks, stat, (d, off, total) = gpu_blocks(ctx, data, bs, tl, n_states)
+    blocks, stat, (d, off, total) = gpu_blocks_at(ctx, data, bs, tl, n_states, shift)
     for b, g in enumerate(blocks):
         blk = data[b * bs:(b + 1) * bs]
         try:
