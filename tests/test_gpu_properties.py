@@ -186,3 +186,31 @@ def test_corrupted_streams_never_fault(ctx, n_states):
                     assert st2[b] == 0 and np.array_equal(outh[b * bs:(b + 1) * bs], src[b * bs:(b + 1) * bs]), (trial, b)
     out, st3 = ctx.decompress_blocks(dev(ctx, good), good.size, dev(ctx, offh), src.size, bs, 0, n_states)
     assert not st3.cpu().numpy().any() and np.array_equal(out.cpu().numpy(), src)
+
+
+def test_corrupted_streams_exhaust_mode_never_fault(ctx):
+    """the same fuzz through the reference-termination decoder (fse_b200_decompress_exhaust): bounded by the capacity"""
+    rng = np.random.default_rng(4242)
+    srcs = [O.generate(k, 5 + i, n).tobytes() for i, (k, n) in enumerate([("text", 3000), ("geo", 2000), ("few", 1500), ("uniform", 1024)])]
+    comps = [O.compress_n(s, 0, 2)[0] for s in srcs]
+    cap = 4 * 3000 + 64
+    for trial in range(120):
+        streams = [bytearray(c) for c in comps]
+        for s in streams:
+            for _ in range(int(rng.integers(0, 4))):
+                s[int(rng.integers(0, len(s)))] ^= 1 << int(rng.integers(0, 8))
+            if trial % 3 == 0:
+                del s[int(rng.integers(1, len(s))):]
+        off = np.zeros(len(streams) + 1, np.int64)
+        off[1:] = np.cumsum([len(s) for s in streams])
+        comp = np.frombuffer(b"".join(bytes(s) for s in streams), np.uint8).copy()
+        out, out_len, st = ctx.decompress_exhaust(dev(ctx, comp), comp.size, dev(ctx, off), len(streams), cap, 15, 2)
+        st, out_len = st.cpu().numpy(), out_len.cpu().numpy()
+        assert ((st <= 0) & (st >= -11)).all() and (out_len <= cap).all(), (trial, st, out_len)
+        for i, s in enumerate(streams):                      # the oracle's literal loop agrees on every damaged stream
+            try:
+                exp = O.decompress_n_exhaust(bytes(s), 2, cap)
+            except ValueError:
+                exp = None
+            if exp is not None and st[i] == 0:
+                assert out_len[i] == len(exp) and out.cpu().numpy()[i, :len(exp)].tobytes() == exp, (trial, i)
