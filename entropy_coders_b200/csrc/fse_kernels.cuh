@@ -358,28 +358,58 @@ __global__ void __launch_bounds__(512) k_encode_blocks(EncArgs a)
     }
 }
 
-// exclusive scan of block sizes -> uint64 offsets[nblocks+1]; single CTA of 1024 threads
+// exclusive scan of block sizes -> uint64 offsets[nblocks+1]; single CTA of 1024 threads, tiles of 8 192 blocks.
+// The sizes of a tile are loaded coalesced into shared memory (padded: one word per 32, so that a thread's eight
+// consecutive entries are conflict free), every thread scans its eight, one block scan gives the bases.  With many
+// small blocks the first version (each thread walking its own slice of global memory) was 15 % of the compress
+// time (65 536 blocks of 4 KiB: 0.19 ms).
+constexpr int SCAN_E = 8, SCAN_TILE = 1024 * SCAN_E;
 __global__ void __launch_bounds__(1024) k_scan_sizes(const uint32_t *__restrict__ hlen, const uint32_t *__restrict__ plen,
                                                       uint32_t nblocks, unsigned long long *offsets)
 {
+    __shared__ uint32_t sz[SCAN_TILE + SCAN_TILE / 32];
     __shared__ unsigned long long wsum[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t per = (nblocks + 1023) / 1024;
-    const uint32_t b0 = tid * per, b1 = min(nblocks, b0 + per);
-    unsigned long long s = 0;
-    for (uint32_t b = b0; b < b1; b++) s += (unsigned long long)hlen[b] + plen[b];
-    unsigned long long incl = warp_incl_add(s, lane);
-    if (lane == 31) wsum[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-        unsigned long long w = wsum[lane];
-        unsigned long long wi = warp_incl_add(w, lane);
-        wsum[lane] = wi - w;
+    unsigned long long carry = 0;
+    for (uint32_t t0 = 0; t0 < nblocks; t0 += SCAN_TILE) {
+#pragma unroll
+        for (int k = 0; k < SCAN_E; k++) {
+            const uint32_t e = k * 1024 + tid, b = t0 + e;
+            sz[e + (e >> 5)] = b < nblocks ? hlen[b] + plen[b] : 0u;
+        }
+        __syncthreads();
+        uint32_t v[SCAN_E];
+        unsigned long long s = 0;
+#pragma unroll
+        for (int k = 0; k < SCAN_E; k++) {
+            const uint32_t e = tid * SCAN_E + k;
+            v[k] = sz[e + (e >> 5)];
+            s += v[k];
+        }
+        unsigned long long incl = warp_incl_add(s, lane);
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long w = wsum[lane];
+            unsigned long long wi = warp_incl_add(w, lane);
+            wsum[lane] = wi - w;
+        }
+        __syncthreads();
+        unsigned long long run = carry + wsum[warp] + incl - s;
+        const uint32_t b0 = t0 + tid * SCAN_E;
+#pragma unroll
+        for (int k = 0; k < SCAN_E; k++) {
+            if (b0 + k < nblocks) offsets[b0 + k] = run;
+            run += v[k];
+        }
+        // the tile total: the last thread's running sum
+        __syncthreads();
+        if (tid == 1023) wsum[0] = run;
+        __syncthreads();
+        carry = wsum[0];
+        __syncthreads();
     }
-    __syncthreads();
-    unsigned long long run = wsum[warp] + incl - s;
-    for (uint32_t b = b0; b < b1; b++) { offsets[b] = run; run += (unsigned long long)hlen[b] + plen[b]; }
-    if (nblocks == 0 ? tid == 0 : (b0 < b1 && b1 == nblocks)) offsets[nblocks] = run;
+    if (tid == 0) offsets[nblocks] = carry;
 }
 
 // byte copy with 4-byte aligned destination stores and funnel-shifted source words
