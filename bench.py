@@ -1,26 +1,29 @@
 #!/usr/bin/env python
 """bench.py -- FSE (tANS) encode/decode throughput on B200, one JSON line.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3few|c3uni|c4|c5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload c4|c5|c2|c3few|c3uni|c1] [--no-configs] [--no-e2e] [--no-cpu]
 
-A "step" is one pass of the hot path over one batch: compress the resident input (histogram +
-normalise + header + table build + encode + offset scan + gather) and decompress it again (header
-parse + table build + decode).  `value` is uncompressed GB per second of that round trip with the
-input resident in HBM; `encode_GBps` / `decode_GBps` give the two directions on their own.
-`e2e` is the same round trip through the host-buffer entry points (fse_b200_compress_host /
-fse_b200_decompress_host) with pinned host buffers, copies inside the timed region.
+Default workload = the configuration BASELINE.json's metric is quoted on: c4, 8 GiB of skewed (geometric 0.2)
+bytes in 128 KiB blocks with per-block tables, STRONG-scaled: rank g of N owns the contiguous block range
+[g*B/N, (g+1)*B/N) of the one logical stream (N = 1 codes all 8 GiB), no collective on the data path.
 
-N > 1 (launched under torchrun): every rank owns a contiguous block range of the logical stream
-(its own 256 MiB slice), no collective on the data path; one all-gather of the per-rank compressed
-totals per step places the output.  Weak scaling.
+A "step" is one pass of the hot path over the resident input: compress (histogram + normalise + header +
+table build + encode + offset scan + dense placement) and decompress it again (header parse + table build +
+decode).  `value` = uncompressed GB per second of that round trip, whole job, device resident, CUDA events,
+max over ranks.  `e2e` = the same round trip through the host-buffer entry points (fse_b200_compress_host /
+fse_b200_decompress_host) with pinned host buffers, host<->device copies inside the timed region.
+`configs` carries short runs of the other BASELINE.json configurations (c2, the c3 table_log sweep, c5).
 
---impl reference times the CPU path: the C restatement of the reference crate's fse_compress2 /
-fse_decompress2 loops (oracle/, "port" -- the crate is Rust and cannot be built in this image),
-multithreaded over blocks on the box's host cores.
+--impl reference times the reference's CPU path on the box's host cores: the C restatement of the crate's
+fse_compress2 / fse_decompress2 loops (oracle/, kind "port": the crate is Rust and no Rust toolchain exists
+in this image), pthreads over blocks, built -O3 -march=native on the box.  Rank 0 alone runs it.
 """
 import argparse
+import ctypes as C
 import json
 import os
+import shutil
 import subprocess
 import sys
 import threading
@@ -29,17 +32,26 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
 
+GIB = 1 << 30
 WORKLOADS = {
-    # name: (generator kind, seed, bytes per GPU, block size, table_log, table_mode, BASELINE.json config)
-    # c1 is the reference's own CPU case (benches/fse_benchmark.rs): one stream, two states; only --impl reference runs it
-    "c1": ("geo", 0xC0FFEE01, 1 << 20, 1 << 20, 11, 0, "1 MiB synthetic skewed bytes (geometric 0.2), one stream, table_log 11, fse_compress2 + fse_decompress2"),
-    "c2": ("text", 0xC0FFEE02, 256 << 20, 65536, 0, 0, "256 MiB synthetic text-like bytes, 64 KiB blocks, per-block tables"),
-    "c3few": ("few", 0xC0FFEE03, 1 << 30, 65536, 11, 0, "1 GiB low-entropy (few-symbol) bytes, 64 KiB blocks"),
-    "c3uni": ("uniform", 0xC0FFEE03, 1 << 30, 65536, 11, 0, "1 GiB near-uniform random bytes, 64 KiB blocks"),
-    "c4": ("geo", 0xC0FFEE04, 1 << 30, 131072, 0, 0, "skewed (geometric 0.2) bytes, 128 KiB blocks, block-range sharded, 1 GiB per GPU"),
-    "c5": ("geo", 0xC0FFEE05, 1 << 30, 131072, 11, 1, "skewed bytes, 128 KiB blocks, one global table via histogram all-reduce, 1 GiB per GPU"),
+    # name: generator kind, seed, bytes (total when strong-scaled, per GPU when weak), block size, table_log,
+    #       table mode, scaling, description (BASELINE.json config)
+    "c1": dict(kind="geo", seed=0xC0FFEE01, nbytes=1 << 20, bs=1 << 20, tlog=11, tmode=0, scaling="weak",
+               desc="1 MiB synthetic skewed bytes (geometric 0.2), one stream, table_log 11, fse_compress2 + fse_decompress2 (CPU only)"),
+    "c2": dict(kind="text", seed=0xC0FFEE02, nbytes=256 << 20, bs=65536, tlog=0, tmode=0, scaling="weak",
+               desc="256 MiB synthetic text-like bytes, 64 KiB blocks, per-block tables"),
+    "c3few": dict(kind="few", seed=0xC0FFEE03, nbytes=GIB, bs=65536, tlog=11, tmode=0, scaling="weak",
+                  desc="1 GiB low-entropy (few-symbol) bytes, 64 KiB blocks, per-block tables"),
+    "c3uni": dict(kind="uniform", seed=0xC0FFEE03, nbytes=GIB, bs=65536, tlog=11, tmode=0, scaling="weak",
+                  desc="1 GiB near-uniform random bytes, 64 KiB blocks, per-block tables"),
+    "c4": dict(kind="geo", seed=0xC0FFEE04, nbytes=8 * GIB, bs=131072, tlog=0, tmode=0, scaling="strong",
+               desc="8 GiB skewed (geometric 0.2) bytes, 128 KiB blocks, per-block tables, block-range sharded"),
+    "c5": dict(kind="geo", seed=0xC0FFEE05, nbytes=8 * GIB, bs=131072, tlog=11, tmode=1, scaling="strong",
+               desc="8 GiB skewed bytes, 128 KiB blocks, one global table via histogram all-reduce, block-range sharded"),
 }
 N_STATES = 128
+KERNEL_NAMES = {"hist": "k_hist_blocks16", "encode": "k_encode128_blocks", "decode": "k_decode128c_blocks",
+                "scan": "k_scan_sizes", "gather": "k_gather"}
 
 
 def peaks():
@@ -48,6 +60,17 @@ def peaks():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def mem_available_gib():
+    try:
+        with open("/proc/meminfo") as f:
+            for line in f:
+                if line.startswith("MemAvailable"):
+                    return int(line.split()[1]) / (1 << 20)
+    except Exception:
+        pass
+    return 0.0
 
 
 class ClockSampler:
@@ -100,79 +123,415 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_port_throughput(kind, seed, block_size, sample_bytes, threads, reps=1):
-    """The reference's CPU path (C restatement, 2 interleaved states, 64-bit accumulator), threads over
-    blocks.  Returns (round-trip GB/s, encode GB/s, decode GB/s, compressed/uncompressed)."""
-    import ctypes as C
+# ---------------------------------------------------------------------------------------------- CPU legs (oracle/)
+
+_native = None
+
+
+def native_oracle():
+    """The timing copy of the CPU port: oracle/fse_oracle.c built -O3 -march=native ON THIS HOST (the portable build
+    that travels with the repo is x86-64-v2).  Falls back to the portable build when gcc is missing."""
+    global _native
+    if _native is not None:
+        return _native
+    import oracle_lib as O
+    L, flags = O.lib(), "-O3 -march=x86-64-v2 (portable build)"
+    out = os.path.join(ROOT, "oracle", "_build", "libfse_oracle_native.so")
+    try:
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        subprocess.check_call(["gcc", "-O3", "-march=native", "-fPIC", "-shared", "-o", out,
+                               os.path.join(ROOT, "oracle", "fse_oracle.c"), "-lpthread"],
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        L = C.CDLL(out)
+        L.fse_or_compress_bound.argtypes = [C.c_size_t]
+        L.fse_or_compress_bound.restype = C.c_size_t
+        L.fse_or_ref_compress2.restype = C.c_long
+        L.fse_or_ref_decompress2.restype = C.c_long
+        flags = "-O3 -march=native (built on this host)"
+    except Exception:
+        pass
+    _native = (L, flags)
+    return _native
+
+
+class CpuPort:
+    """The reference's CPU path over blocks (C restatement: 2 interleaved states, 64-bit accumulator, one flush per
+    symbol pair), pthreads over blocks.  Buffers are allocated and touched once, outside every timed region."""
+
+    def __init__(self, kind, seed, block_size, nbytes, threads):
+        import numpy as np
+        import oracle_lib as O
+        self.L, self.flags = native_oracle()
+        self.np, self.O = np, O
+        self.src = O.generate(kind, seed, nbytes)
+        self.nb = (nbytes + block_size - 1) // block_size
+        self.stride = int(self.L.fse_or_compress_bound(block_size)) + 64
+        self.scratch = np.zeros((self.nb, self.stride), dtype=np.uint8)
+        self.sizes = np.zeros(self.nb, dtype=np.uint64)
+        self.status = np.zeros(self.nb, dtype=np.int32)
+        self.out = np.zeros(nbytes, dtype=np.uint8)
+        self.p = O.BlockParams(block_size, 0, 2, threads, 1)
+        self.nbytes, self.threads = nbytes, threads
+
+    def roundtrip(self, check=False):
+        """-> (encode seconds, decode seconds)"""
+        ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+        L = self.L
+        t0 = time.perf_counter()
+        L.fse_or_compress_blocks(ptr(self.src), C.c_size_t(self.nbytes), C.byref(self.p), ptr(self.scratch),
+                                 C.c_size_t(self.stride), ptr(self.sizes), ptr(self.status))
+        t1 = time.perf_counter()
+        L.fse_or_decompress_blocks(ptr(self.scratch), C.c_size_t(self.stride), ptr(self.sizes), C.c_size_t(self.nb),
+                                   C.byref(self.p), ptr(self.out), C.c_size_t(self.nbytes), ptr(self.status))
+        t2 = time.perf_counter()
+        if check:
+            assert not self.status.any() and self.np.array_equal(self.out, self.src), "CPU port round trip failed"
+        return t1 - t0, t2 - t1
+
+    def ratio(self):
+        return float(self.sizes.sum()) / self.nbytes
+
+
+def cpu_single_stream(kind, seed, nbytes, reps=10, warm=3):
+    """One stream, one thread: fse_compress2 + fse_decompress2 (the shape of benches/fse_benchmark.rs:30-52)."""
     import numpy as np
     import oracle_lib as O
-    L = O.lib()
-    src = O.generate(kind, seed, sample_bytes)
-    nb = (src.size + block_size - 1) // block_size
-    stride = L.fse_or_compress_bound(block_size) + 64
-    scratch = np.zeros((nb, stride), dtype=np.uint8)          # allocated and touched outside the timed region
-    sizes = np.zeros(nb, dtype=np.uint64)
-    status = np.zeros(nb, dtype=np.int32)
-    out = np.zeros(src.size, dtype=np.uint8)
-    p = O.BlockParams(block_size, 0, 2, threads, 1)
+    L, _ = native_oracle()
+    src = O.generate(kind, seed, nbytes)
+    cap = int(L.fse_or_compress_bound(nbytes)) + 64
+    comp = np.zeros(cap, dtype=np.uint8)
+    out = np.zeros(nbytes + 64, dtype=np.uint8)
     ptr = lambda a: a.ctypes.data_as(C.c_void_p)
-    best_e, best_d = 1e9, 1e9
-    for _ in range(reps + 1):                                  # first pass warms caches / page tables
+    be = bd = 1e9
+    for i in range(warm + reps):
         t0 = time.perf_counter()
-        L.fse_or_compress_blocks(ptr(src), src.size, C.byref(p), ptr(scratch), stride, ptr(sizes), ptr(status))
+        ln = L.fse_or_ref_compress2(ptr(src), C.c_size_t(nbytes), ptr(comp), C.c_size_t(cap))
         t1 = time.perf_counter()
-        L.fse_or_decompress_blocks(ptr(scratch), stride, ptr(sizes), nb, C.byref(p), ptr(out), src.size, ptr(status))
+        got = L.fse_or_ref_decompress2(ptr(comp), C.c_size_t(ln), ptr(out), C.c_size_t(nbytes + 64))
         t2 = time.perf_counter()
-        assert not status.any() and np.array_equal(out, src)
-        best_e, best_d = min(best_e, t1 - t0), min(best_d, t2 - t1)
-    ratio = float(sizes.sum()) / src.size
-    return sample_bytes / (best_e + best_d) / 1e9, sample_bytes / best_e / 1e9, sample_bytes / best_d / 1e9, ratio
+        assert got == nbytes and np.array_equal(out[:nbytes], src)
+        if i >= warm:
+            be, bd = min(be, t1 - t0), min(bd, t2 - t1)
+    return {"bytes": nbytes, "threads": 1, "encode_GBps": nbytes / be / 1e9, "decode_GBps": nbytes / bd / 1e9,
+            "roundtrip_GBps": nbytes / (be + bd) / 1e9, "compressed_ratio": ln / nbytes, "best_of": reps, "warmups": warm}
+
+
+def cpu_baseline_leg(w):
+    """cpu_baseline of the main line: a bounded sample of the same workload, all host threads, best of 10 after 3
+    warm-ups, plus the reference bench's own 32 KiB shape and c1, one thread each."""
+    threads = os.cpu_count() or 1
+    sample = min(w["nbytes"], 512 << 20)
+    port = CpuPort(w["kind"], w["seed"], w["bs"], sample, threads)
+    be = bd = 1e9
+    for i in range(13):
+        e, d = port.roundtrip(check=(i == 0))
+        if i >= 3:
+            be, bd = min(be, e), min(bd, d)
+    shapes = {}
+    try:
+        shapes["fse_benchmark_32KiB"] = cpu_single_stream("geo", 0xC0FFEE00, 1 << 15, reps=50, warm=10)
+        shapes["c1_1MiB"] = cpu_single_stream("geo", 0xC0FFEE01, 1 << 20)
+    except Exception as ex:                                        # never lose the main number to an extra
+        shapes["error"] = repr(ex)
+    return {"value": sample / (be + bd) / 1e9, "unit": "GB/s", "cores": threads, "kind": "port",
+            "encode_GBps": sample / be / 1e9, "decode_GBps": sample / bd / 1e9, "compressed_ratio": port.ratio(),
+            "build": port.flags,
+            "sample": "%d MiB of the same workload (%s), %d B blocks, fse_compress2 + fse_decompress2 loop structure (C "
+                      "restatement of the Rust reference: no Rust toolchain in this image), %d threads over blocks, best of 10 "
+                      "after 3 warm-ups" % (sample >> 20, w["kind"], w["bs"], threads),
+            "single_thread_shapes": shapes}
 
 
 def run_reference(args, wl):
-    kind, seed, nbytes, bs, tlog, tmode, desc = WORKLOADS[wl]
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    w = WORKLOADS[wl]
+    if int(os.environ.get("RANK", "0")) != 0:
         return
     threads = os.cpu_count() or 1
-    sample = 64 << 20
-    if wl == "c1":                                            # a single stream is serial: one core, the whole MiB
-        threads, sample = 1, nbytes
-    vals = []
-    for _ in range(args.warmup):
-        cpu_port_throughput(kind, seed, bs, sample, threads)
+    nbytes = w["nbytes"]                                           # the whole job, whatever --gpus says (strong scaling)
+    if w["scaling"] == "weak":
+        nbytes *= max(args.gpus, 1)
+    sample = nbytes
+    # host memory: source + strided scratch + output ~ 3.1 x the sample
+    if mem_available_gib() * GIB < 3.5 * sample:
+        sample = max(64 << 20, min(nbytes, int(mem_available_gib() * GIB / 4) // w["bs"] * w["bs"]))
+    if wl == "c1":                                                 # a single stream is serial: one core
+        threads = 1
+    port = CpuPort(w["kind"], w["seed"], w["bs"], sample, threads)
+    for i in range(max(args.warmup, 1)):
+        port.roundtrip(check=(i == 0))
+    te = td = 0.0
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        vals.append(cpu_port_throughput(kind, seed, bs, sample, threads))
+        e, d = port.roundtrip()
+        te, td = te + e, td + d
     dt = (time.perf_counter() - t0) / max(args.steps, 1)
-    rt = sum(v[0] for v in vals) / len(vals)
+    rt = sample * args.steps / (te + td) / 1e9
+    what = "the whole workload" if sample == nbytes else "%d MiB of the workload (host memory bound)" % (sample >> 20)
     line = {
         "impl": "reference", "metric": "fse_roundtrip_GBps_uncompressed", "value": rt, "unit": "GB/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": wl + ": " + desc, "block_size": bs, "n_states": 2,
-                   "sample": "%d MiB of the workload per step" % (sample >> 20)},
-        "encode_GBps": sum(v[1] for v in vals) / len(vals), "decode_GBps": sum(v[2] for v in vals) / len(vals),
-        "compressed_ratio": vals[-1][3],
-        "cpu_baseline": {"value": rt, "unit": "GB/s", "cores": threads, "kind": "port",
-                         "sample": "%d MiB of %s, %d B blocks, fse_compress2+fse_decompress2 loops (C restatement; the "
-                                   "reference is Rust, no toolchain in this image), %d threads over blocks" % (sample >> 20, kind, bs, threads)},
+        "higher_is_better": True, "scaling": w["scaling"], "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": wl + ": " + w["desc"], "total_bytes": nbytes, "block_size": w["bs"], "n_states": 2,
+                   "sample_bytes_per_step": sample},
+        "encode_GBps": sample * args.steps / te / 1e9, "decode_GBps": sample * args.steps / td / 1e9,
+        "compressed_ratio": port.ratio(),
+        "cpu_baseline": {"value": rt, "unit": "GB/s", "cores": threads, "kind": "port", "build": port.flags,
+                         "sample": "%s per step: %s, %d B blocks, fse_compress2 + fse_decompress2 loops (C restatement; the "
+                                   "reference is Rust, no toolchain in this image), %d threads over blocks"
+                                   % (what, w["kind"], w["bs"], threads)},
         "e2e": {"value": rt, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
 
 
-def run_ours(args, wl):
+# ---------------------------------------------------------------------------------------------- GPU legs
+
+class Job:
+    """One workload resident on this rank's GPU: buffers, the step, and its measurements."""
+
+    def __init__(self, env, wl, tlog=None):
+        import torch
+        from entropy_coders_b200 import sharding as S
+        self.env, self.wl, self.torch, self.S = env, wl, torch, S
+        w = dict(WORKLOADS[wl])
+        if tlog is not None:
+            w["tlog"] = tlog
+        self.w = w
+        ctx, world, rank = env["ctx"], env["world"], env["rank"]
+        bs = w["bs"]
+        if w["scaling"] == "strong":
+            self.total_bytes = w["nbytes"]
+            _, _, first, nbytes = S.shard_blocks(self.total_bytes, bs, rank, world)
+        else:
+            self.total_bytes = w["nbytes"] * world
+            first, nbytes = rank * w["nbytes"], w["nbytes"]
+        self.nbytes, self.first = nbytes, first
+        dev = env["dev"]
+        self.src = ctx.generate(w["kind"], w["seed"], nbytes, first_index=first)
+        self.p = ctx.params(bs, w["tlog"], N_STATES, w["tmode"])
+        self.nb = ctx.num_blocks(nbytes, bs)
+        self.cap = ctx.bound(nbytes, self.p)
+        self.dst = torch.empty(self.cap, dtype=torch.uint8, device=dev)
+        self.offsets = torch.empty(self.nb + 1, dtype=torch.int64, device=dev)
+        self.status = torch.empty(max(self.nb, 1), dtype=torch.int32, device=dev)
+        self.status_d = torch.empty(max(self.nb, 1), dtype=torch.int32, device=dev)
+        self.out = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        self.totals = torch.zeros(world, dtype=torch.int64, device=dev)
+        self.mine = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.ev_c = torch.cuda.Event()
+        self.ev_x = torch.cuda.Event()
+        self.pending_exchange = False
+
+    def global_table(self):
+        ctx = self.env["ctx"]
+        counts = ctx.histogram_global(self.src)
+        self.S.allreduce_histogram(counts)                # NCCL: the only exchange of the global-table mode
+        return ctx.set_global_table(counts, self.w["tlog"])
+
+    def step(self):
+        env, torch = self.env, self.torch
+        ctx, stream, side, world = env["ctx"], env["stream"], env["side"], env["world"]
+        if self.w["tmode"] == 1:
+            self.global_table()
+        ctx.compress_blocks_async(self.src, self.p, self.dst, self.offsets, self.status)
+        if world > 1:
+            # Placement of this rank's output in the logical stream: all-gather of the per-rank totals on a side
+            # stream.  Nothing on the data path consumes it, so the main stream never waits for it inside the
+            # step; it is joined once, after the timed region (finish()).
+            self.ev_c.record(stream)
+            with torch.cuda.stream(side):
+                side.wait_event(self.ev_c)
+                self.mine.copy_(self.offsets[self.nb:self.nb + 1])
+                torch.distributed.all_gather_into_tensor(self.totals, self.mine)
+                self.ev_x.record(side)
+            self.pending_exchange = True
+        ctx.decompress_blocks_async(self.dst, self.cap, self.offsets, self.nb, self.p, self.out, self.nbytes, self.status_d)
+
+    def finish(self):
+        if self.pending_exchange:
+            self.env["stream"].wait_event(self.ev_x)
+            self.pending_exchange = False
+
+    def check(self):
+        torch = self.torch
+        assert not self.status[:self.nb].cpu().numpy().any() and not self.status_d[:self.nb].cpu().numpy().any(), "block failures"
+        assert torch.equal(self.out, self.src), "round trip mismatch"
+        return int(self.offsets[self.nb].item())
+
+    def base_offset(self):
+        return int((torch_cumsum_exclusive(self.totals))[self.env["rank"]].item()) if self.env["world"] > 1 else 0
+
+    def release(self):
+        for k in ("src", "dst", "offsets", "status", "status_d", "out"):
+            setattr(self, k, None)
+        self.torch.cuda.empty_cache()
+
+
+def torch_cumsum_exclusive(t):
+    import torch
+    return torch.cumsum(t, 0) - t
+
+
+def barrier(env):
+    import torch
+    torch.cuda.synchronize()
+    if env["world"] > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+
+
+def measure(env, job, steps, warmup, sample_clocks=False):
+    """warmup untimed steps, then exactly `steps` timed steps between barriers; max over ranks."""
+    import torch
+    ctx, stream, world, rank = env["ctx"], env["stream"], env["world"], env["rank"]
+    for _ in range(max(warmup, 3)):
+        job.step()
+    job.finish()
+    barrier(env)
+    total = job.check()
+    sampler = ClockSampler(env["local"]) if (sample_clocks and rank == 0) else None
+    ctx.set_timing(True)
+    l0 = ctx.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier(env)
+    if sampler:
+        sampler.start()
+    e0.record(stream)
+    for _ in range(steps):
+        job.step()
+    job.finish()
+    e1.record(stream)
+    barrier(env)
+    clocks = sampler.stop() if sampler else None
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launches - l0
+    tm = ctx.get_timing()
+    ctx.set_timing(False)
+    t = torch.tensor([ms, float(total)], dtype=torch.float64, device=env["dev"])
+    tmax = t.clone()
+    if world > 1:
+        torch.distributed.all_reduce(tmax, op=torch.distributed.ReduceOp.MAX)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM)
+    ms_step = float(tmax[0].item()) / steps
+    total_all = float(t[1].item()) if world > 1 else float(total)
+    enc_ms = sum(tm[k][0] for k in ("hist", "encode", "scan", "gather")) / steps
+    dec_ms = tm["decode"][0] / steps
+    peak, peak_src = peaks()
+    dom = max(("hist", "encode", "decode"), key=lambda k: tm[k][0])
+    dom_ms = tm[dom][0] / max(tm[dom][1], 1)
+    alg_bytes = job.nbytes + total if dom != "hist" else job.nbytes
+    achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
+    return {
+        "value": job.total_bytes / (ms_step * 1e-3) / 1e9, "ms_per_step": ms_step, "steps": steps,
+        "encode_GBps": job.nbytes / (enc_ms * 1e-3) / 1e9, "decode_GBps": job.nbytes / (dec_ms * 1e-3) / 1e9,
+        "compressed_ratio": total_all / job.total_bytes, "compressed_bytes_rank0": total,
+        "kernel_ms_per_step": {k: tm[k][0] / steps for k in tm},
+        "roofline": {"bound": "hbm", "kernel": KERNEL_NAMES[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": dom_ms,
+                     "direction_frac": {"encode": (job.nbytes + total) / (enc_ms * 1e-3) / 1e9 / peak,
+                                        "decode": (job.nbytes + total) / (dec_ms * 1e-3) / 1e9 / peak},
+                     "note": "N + C of one rank's launch (uncompressed + compressed bytes; N alone for the histogram) / mean "
+                             "launch time of the kernel with the largest share of the step; direction_frac = the same bytes "
+                             "over ALL kernels of the direction"},
+        "gpu_launches": int(launches), "clocks": clocks, "dominant": dom,
+    }
+
+
+def e2e_leg(env, job, steps):
+    """The round trip through the host-buffer entry points; pinned host buffers, copies inside the timed region."""
+    import torch
+    import entropy_coders_b200 as E
+    w, nbytes, nb = job.w, job.nbytes, job.nb
+    total = int(job.offsets[nb].item())
+    sample = nbytes
+    if mem_available_gib() * GIB < 4.0 * nbytes * max(env["world"], 1):    # pinned: source + compressed + output per rank
+        sample = max(w["bs"], min(nbytes, int(mem_available_gib() * GIB / (5 * env["world"])) // w["bs"] * w["bs"]))
+    hsrc = torch.empty(sample, dtype=torch.uint8, pin_memory=True)
+    hsrc.copy_(job.src[:sample])
+    hdst = torch.empty(int(total * (sample / nbytes) * 1.05) + (1 << 20), dtype=torch.uint8, pin_memory=True)
+    hout = torch.empty(sample, dtype=torch.uint8, pin_memory=True)
+    ctx2 = E.Context(env["local"])
+    if w["tmode"] == 1:
+        hdr, _ = job.global_table()
+        ctx2.set_global_table_from_header(hdr)
+    tot = offs = None
+
+    def e2e_step():
+        _, o, st, t = ctx2.compress_host(hsrc, w["bs"], w["tlog"], N_STATES, w["tmode"], dst=hdst)
+        ctx2.decompress_host(hdst, t, o, sample, w["bs"], w["tlog"], N_STATES, w["tmode"], dst=hout)
+        return t, o
+    for _ in range(2):
+        e2e_step()
+    ksteps = max(1, min(steps, 3 if sample > GIB else 5))
+    barrier(env)
+    t0 = time.perf_counter()
+    for _ in range(ksteps):
+        tot, offs = e2e_step()
+    t1 = time.perf_counter()
+    assert torch.equal(hout, hsrc), "e2e round trip mismatch"
+    te = torch.tensor([t1 - t0], dtype=torch.float64, device=env["dev"])
+    if env["world"] > 1:
+        torch.distributed.all_reduce(te, op=torch.distributed.ReduceOp.MAX)
+    e2e_s = float(te.item()) / ksteps
+    snb = (sample + w["bs"] - 1) // w["bs"]
+    res = {"value": env["world"] * sample / e2e_s / 1e9 if w["scaling"] == "weak" or sample != nbytes
+           else job.total_bytes / e2e_s / 1e9,
+           "unit": "GB/s", "h2d_bytes_per_step": int(sample + tot + (snb + 1) * 8),
+           "d2h_bytes_per_step": int(tot + (snb + 1) * 8 + snb * 4 + sample + snb * 4),
+           "steps": ksteps, "bytes_per_rank": sample,
+           "api": "fse_b200_compress_host + fse_b200_decompress_host, pinned host buffers, rank-local data"}
+    ctx2.close()
+    del hsrc, hdst, hout
+    return res
+
+
+def traffic_probe(wl, tlog, dom_kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, measured now: a child process
+    runs one step of the same workload under `ncu --metrics ...` (N = 1 only).  None when ncu is unavailable."""
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not os.path.exists(ncu):
+        return None, "ncu not found"
+    log = os.path.join(ROOT, "gpurun_out", "traffic_probe.csv")
+    os.makedirs(os.path.dirname(log), exist_ok=True)
+    cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "--csv",
+           "--log-file", log, "-k", "regex:k_(hist|encode|decode)", "-c", "12",
+           sys.executable, os.path.abspath(__file__), "--probe", "--workload", wl]
+    if tlog is not None:
+        cmd += ["--table-log", str(tlog)]
+    try:
+        subprocess.run(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=420, check=True)
+        import csv
+        rd = wr = None
+        with open(log) as f:
+            rows = [r for r in csv.reader(f) if len(r) > 5]
+        hdr = rows[0]
+        ki, mi, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        for r in rows[1:]:
+            if r[ki].startswith(dom_kernel):
+                v = float(r[vi].replace(",", "")) * scale.get(r[ui], 1.0)
+                if r[mi] == "dram__bytes_read.sum":
+                    rd = v                                  # the last launch of the kernel wins (after the warm-up launch)
+                elif r[mi] == "dram__bytes_write.sum":
+                    wr = v
+        if rd is None or wr is None:
+            return None, "kernel not in the ncu log"
+        return rd + wr, "ncu dram__bytes_read.sum + dram__bytes_write.sum, one launch, measured in this run"
+    except Exception as ex:
+        return None, "probe failed: %r" % (ex,)
+
+
+def make_env():
     import torch
     import torch.distributed as dist
     import entropy_coders_b200 as E
-
-    kind, seed, nbytes, bs, tlog, tmode, desc = WORKLOADS[wl]
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
     if world > 1:
         # NCCL prints its version banner on stdout when the first communicator is made: send it to stderr so
         # that stdout carries exactly one JSON line
@@ -180,169 +539,93 @@ def run_ours(args, wl):
         saved = os.dup(1)
         os.dup2(2, 1)
         try:
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-            dist.all_reduce(torch.zeros(1, device=torch.device("cuda", local)))
+            dist.init_process_group("nccl", device_id=dev)
+            dist.all_reduce(torch.zeros(1, device=dev))
             torch.cuda.synchronize()
         finally:
             sys.stdout.flush()
             os.dup2(saved, 1)
             os.close(saved)
-    dev = torch.device("cuda", local)
     stream = torch.cuda.Stream(device=dev)               # kernels, NCCL and the timing events share this stream
     torch.cuda.set_stream(stream)
+    side = torch.cuda.Stream(device=dev)
     ctx = E.Context(local, stream=stream.cuda_stream)
+    return {"world": world, "rank": rank, "local": local, "dev": dev, "stream": stream, "side": side, "ctx": ctx}
 
-    # this rank's contiguous block range of the logical stream
-    src = ctx.generate(kind, seed, nbytes, first_index=rank * nbytes)
-    p = ctx.params(bs, tlog, N_STATES, tmode)
-    nb = ctx.num_blocks(nbytes, bs)
-    cap = ctx.bound(nbytes, p)
-    dst = torch.empty(cap, dtype=torch.uint8, device=dev)
-    offsets = torch.empty(nb + 1, dtype=torch.int64, device=dev)
-    status = torch.empty(nb, dtype=torch.int32, device=dev)
-    status_d = torch.empty(nb, dtype=torch.int32, device=dev)
-    out = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    totals = torch.zeros(world, dtype=torch.int64, device=dev)
 
-    from entropy_coders_b200 import sharding as S
+def run_probe(args, wl):
+    """child of traffic_probe(): one warm-up step and one profiled step, nothing printed"""
+    env = make_env()
+    job = Job(env, wl, args.table_log)
+    job.step()
+    job.step()
+    barrier(env)
+    job.check()
 
-    def global_table():
-        counts = ctx.histogram_global(src)
-        S.allreduce_histogram(counts)                    # NCCL: the only exchange of the global-table mode
-        return ctx.set_global_table(counts, tlog)
 
-    side = torch.cuda.Stream(device=dev)                 # the tiny exchange runs beside the decode kernel
-    ev_c, ev_x = torch.cuda.Event(), torch.cuda.Event()
+def run_ours(args, wl):
+    import torch
+    env = make_env()
+    world, rank = env["world"], env["rank"]
+    job = Job(env, wl, args.table_log)
+    w = job.w
+    m = measure(env, job, args.steps, args.warmup, sample_clocks=True)
+    if rank == 0 and world == 1 and not args.no_traffic:
+        m["roofline"]["traffic"], m["roofline"]["traffic_source"] = traffic_probe(wl, args.table_log, m["roofline"]["kernel"])
 
-    def step():
-        if tmode == 1:
-            global_table()
-        ctx.compress_blocks_async(src, p, dst, offsets, status)
-        if world > 1:                                    # place the output: all-gather of the per-rank totals,
-            ev_c.record(stream)                          # exclusive scan -> this rank's base offset
-            with torch.cuda.stream(side):
-                side.wait_event(ev_c)
-                totals.copy_(S.gather_totals(offsets[nb:nb + 1], dev))
-                S.base_offsets(totals)
-                ev_x.record(side)
-        ctx.decompress_blocks_async(dst, cap, offsets, nb, p, out, nbytes, status_d)
-        if world > 1:
-            stream.wait_event(ev_x)                      # the step is complete when both are
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
-    total = int(offsets[nb].item())
-    assert not status.cpu().numpy().any() and not status_d.cpu().numpy().any(), "block failures"
-    assert torch.equal(out, src), "round trip mismatch"
-
-    sampler = ClockSampler(local)
-    ctx.set_timing(True)
-    l0 = ctx.launches
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    if rank == 0:
-        sampler.start()
-    e0.record(stream)
-    for _ in range(args.steps):
-        step()
-    e1.record(stream)
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    ms = e0.elapsed_time(e1)
-    launches = ctx.launches - l0
-    tm = ctx.get_timing()
-    ctx.set_timing(False)
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    ms_step = ms / args.steps
-    value = world * nbytes / (ms_step * 1e-3) / 1e9
-
-    # per-direction device times (sum of the kernels of each direction, CUDA events on the launching stream)
-    enc_ms = sum(tm[k][0] for k in ("hist", "encode", "scan", "gather")) / args.steps
-    dec_ms = tm["decode"][0] / args.steps
-    peak, peak_src = peaks()
-    # roofline of the dominant kernel: algorithmic bytes (N + C per direction) / its duration
-    dom = max(("encode", "decode"), key=lambda k: tm[k][0])
-    dom_ms = tm[dom][0] / max(tm[dom][1], 1)
-    alg_bytes = nbytes + total
-    achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
-    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this
-    # workload (profiles/r1_ncu_full_c2_n128.txt); only meaningful for the configuration that was profiled
-    traffic = {"encode": 272.98e6 + 143.34e6, "decode": 179.75e6 + 219.48e6}[dom] if (wl == "c2" and N_STATES == 128) else None
-
-    # e2e: host buffers through the host entry points, copies inside the timed region (rank-local data)
     e2e = None
     if not args.no_e2e:
-        hsrc = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
-        hsrc.copy_(src)
-        hdst = torch.empty(total + 4096, dtype=torch.uint8, pin_memory=True)
-        hout = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
-        ctx2 = E.Context(local)
-        if tmode == 1:
-            hdr, _ = global_table()
-            ctx2.set_global_table_from_header(hdr)
-
-        def e2e_step():
-            _, offs, st, tot = ctx2.compress_host(hsrc, bs, tlog, N_STATES, tmode, dst=hdst)
-            o, st2 = ctx2.decompress_host(hdst, tot, offs, nbytes, bs, tlog, N_STATES, tmode, dst=hout)
-            return tot, offs
-        for _ in range(2):
-            e2e_step()
-        ksteps = max(1, min(args.steps, 5))
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(ksteps):
-            tot, offs = e2e_step()
-        t1 = time.perf_counter()
-        assert torch.equal(hout, hsrc), "e2e round trip mismatch"
-        te = torch.tensor([t1 - t0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e_s = float(te.item()) / ksteps
-        e2e = {"value": world * nbytes / e2e_s / 1e9, "unit": "GB/s",
-               "h2d_bytes_per_step": int(nbytes + tot + (nb + 1) * 8),
-               "d2h_bytes_per_step": int(tot + (nb + 1) * 8 + nb * 4 + nbytes + nb * 4),
-               "steps": ksteps, "api": "fse_b200_compress_host + fse_b200_decompress_host, pinned host buffers"}
-        ctx2.close()
+        try:
+            e2e = e2e_leg(env, job, args.steps)
+        except Exception as ex:
+            e2e = {"error": repr(ex)}
+            barrier(env)
+    job.release()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        threads = os.cpu_count() or 1
-        sample = 64 << 20
-        rt, ce, cd, _ = cpu_port_throughput(kind, seed, bs, sample, threads, reps=2)
-        cpu = {"value": rt, "unit": "GB/s", "cores": threads, "kind": "port", "encode_GBps": ce, "decode_GBps": cd,
-               "sample": "%d MiB of the same workload, %d B blocks, fse_compress2+fse_decompress2 loop structure "
-                         "(C restatement of the Rust reference), %d threads over blocks, best of 2" % (sample >> 20, bs, threads)}
+        try:
+            cpu = cpu_baseline_leg(w)
+        except Exception as ex:
+            cpu = {"error": repr(ex)}
+
+    # the other BASELINE.json configurations, short runs (every rank takes part: c5 has a collective)
+    configs = {}
+    if not args.no_configs and wl == "c4":
+        plan = [("c2", None), ("c5", None)] + [(k, t) for k in ("c3few", "c3uni") for t in (9, 11, 12)]
+        for name, tl in plan:
+            key = name if tl is None else "%s_tl%d" % (name, tl)
+            try:
+                j = Job(env, name, tl)
+                r = measure(env, j, 5, 3)
+                configs[key] = {"workload": name + ": " + j.w["desc"], "scaling": j.w["scaling"], "total_bytes": j.total_bytes,
+                                "block_size": j.w["bs"], "table_log": tl if tl is not None else (j.w["tlog"] or "optimal_log2 (11)"),
+                                "n_states": N_STATES, "value": r["value"], "unit": "GB/s", "ms_per_step": r["ms_per_step"],
+                                "encode_GBps_per_gpu": r["encode_GBps"], "decode_GBps_per_gpu": r["decode_GBps"],
+                                "compressed_ratio": r["compressed_ratio"], "kernel_ms_per_step": r["kernel_ms_per_step"],
+                                "roofline_frac": r["roofline"]["frac"], "roofline_kernel": r["roofline"]["kernel"]}
+                j.release()
+            except Exception as ex:
+                configs[key] = {"error": repr(ex)}
+                barrier(env)
 
     if rank == 0:
         line = {
-            "metric": "fse_roundtrip_GBps_uncompressed", "value": value, "unit": "GB/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": wl + ": " + desc, "bytes_per_gpu": nbytes, "block_size": bs, "blocks_per_gpu": nb,
-                       "n_states": N_STATES, "table_log": tlog or "optimal_log2 (11)", "table_mode": "global" if tmode else "per-block",
-                       "l2": "inputs (%d MiB) larger than L2 (126 MB); no flush" % (nbytes >> 20)},
-            "encode_GBps": nbytes / (enc_ms * 1e-3) / 1e9, "decode_GBps": nbytes / (dec_ms * 1e-3) / 1e9,
-            "compressed_ratio": total / nbytes,
-            "kernel_ms_per_step": {k: tm[k][0] / args.steps for k in tm},
-            "roofline": {"bound": "hbm", "kernel": {"encode": "k_encode128_blocks", "decode": "k_decode128c_blocks"}[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes,
-                         "note": "N + C per launch (uncompressed + compressed bytes of one rank) / mean launch time of the dominant kernel"},
-            "e2e": e2e, "cpu_baseline": cpu, "gpu_launches": int(launches), "clocks": clocks,
+            "metric": "fse_roundtrip_GBps_uncompressed", "value": m["value"], "unit": "GB/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": m["ms_per_step"], "higher_is_better": True,
+            "scaling": w["scaling"], "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": wl + ": " + w["desc"], "total_bytes": job.total_bytes, "bytes_per_gpu": job.nbytes,
+                       "block_size": w["bs"], "blocks_per_gpu": job.nb, "n_states": N_STATES,
+                       "table_log": w["tlog"] or "optimal_log2 (11)", "table_mode": "global" if w["tmode"] else "per-block",
+                       "sharding": "rank g owns blocks [g*B/N, (g+1)*B/N) of the one logical stream",
+                       "l2": "inputs (%d MiB per GPU) larger than L2 (126 MB); no flush" % (job.nbytes >> 20)},
+            "encode_GBps": m["encode_GBps"], "decode_GBps": m["decode_GBps"], "compressed_ratio": m["compressed_ratio"],
+            "kernel_ms_per_step": m["kernel_ms_per_step"], "roofline": m["roofline"], "e2e": e2e, "cpu_baseline": cpu,
+            "gpu_launches": m["gpu_launches"], "clocks": m["clocks"], "configs": configs,
         }
         print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        torch.distributed.destroy_process_group()
 
 
 def main():
@@ -351,20 +634,21 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--table-log", type=int, default=None, help="override the workload's table_log (BASELINE config 3 sweeps 9/11/12)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-configs", action="store_true")
+    ap.add_argument("--no-traffic", action="store_true")
+    ap.add_argument("--probe", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
-    if args.table_log is not None:
-        w = list(WORKLOADS[args.workload])
-        w[4] = args.table_log
-        WORKLOADS[args.workload] = tuple(w)
     if args.impl == "reference":
         run_reference(args, args.workload)
     elif args.workload == "c1":
         sys.exit("c1 is the reference's single-stream CPU case: run it with --impl reference (the GPU path codes it "
                  "bit-exactly in tests/test_gpu_parity.py::test_crate_compress_roundtrip, one lane, not a throughput case)")
+    elif args.probe:
+        run_probe(args, args.workload)
     else:
         run_ours(args, args.workload)
 
