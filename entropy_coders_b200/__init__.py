@@ -20,6 +20,7 @@ from ._capi import FseError, Params
 
 TABLE_LOG_MIN, TABLE_LOG_MAX, TABLE_LOG_DEFAULT = 5, 15, 11  # src/lib.rs:9-12
 TABLE_PER_BLOCK, TABLE_GLOBAL = 0, 1
+FLAG_RAW_IF_EXPANDS = 1
 GEN_KINDS = {"geo": 0, "text": 1, "few": 2, "uniform": 3}
 
 
@@ -91,11 +92,15 @@ class Context:
     def _u8(self, n):
         return _torch().empty(max(int(n), 1), dtype=_torch().uint8, device=self.device)
 
-    def params(self, block_size, table_log=0, n_states=32, table_mode=TABLE_PER_BLOCK):
-        return Params(int(block_size), int(table_log), int(n_states), int(table_mode))
+    def params(self, block_size, table_log=0, n_states=32, table_mode=TABLE_PER_BLOCK, segment_size=0, flags=0):
+        return Params(int(block_size), int(table_log), int(n_states), int(table_mode), int(segment_size), int(flags))
 
     def num_blocks(self, n, block_size):
         return int(self._L.fse_b200_num_blocks(n, block_size))
+
+    def num_streams(self, n, p):
+        """entries of the stream index: blocks, or segments when p.segment_size > 0"""
+        return int(self._L.fse_b200_num_streams(n, C.byref(p)))
 
     def bound(self, n, p):
         return int(self._L.fse_b200_compress_blocks_bound(n, C.byref(p)))
@@ -179,12 +184,13 @@ class Context:
         return table, st
 
     # ------------------------------------------------------------------ fused pipelines (device tensors)
-    def compress_blocks(self, src, block_size, table_log=0, n_states=32, table_mode=TABLE_PER_BLOCK, out=None):
-        """-> (dst uint8[cap] (first `total` bytes valid), offsets int64[nb+1], status int32[nb], total)"""
+    def compress_blocks(self, src, block_size, table_log=0, n_states=32, table_mode=TABLE_PER_BLOCK, out=None, segment_size=0, flags=0):
+        """-> (dst uint8[cap] (first `total` bytes valid), offsets int64[nb+1], status int32[nb], total); nb counts
+        segments when segment_size > 0"""
         torch = _torch()
-        p = self.params(block_size, table_log, n_states, table_mode)
+        p = self.params(block_size, table_log, n_states, table_mode, segment_size, flags)
         n = src.numel()
-        nb = self.num_blocks(n, block_size)
+        nb = self.num_streams(n, p)
         cap = self.bound(n, p)
         if out is None:
             dst = self._u8(cap)
@@ -201,11 +207,12 @@ class Context:
         self._ck(self._L.fse_b200_compress_blocks_async(self._h, _ptr(src), src.numel(), C.byref(p), _ptr(dst), dst.numel(),
                                                         _ptr(offsets), _ptr(status)))
 
-    def decompress_blocks(self, comp, total, offsets, n, block_size, table_log=0, n_states=32, table_mode=TABLE_PER_BLOCK, out=None):
+    def decompress_blocks(self, comp, total, offsets, n, block_size, table_log=0, n_states=32, table_mode=TABLE_PER_BLOCK, out=None,
+                          segment_size=0, flags=0):
         """-> (dst uint8[n], status int32[nb])"""
         torch = _torch()
-        p = self.params(block_size, table_log, n_states, table_mode)
-        nb = self.num_blocks(n, block_size)
+        p = self.params(block_size, table_log, n_states, table_mode, segment_size, flags)
+        nb = self.num_streams(n, p)
         if out is None:
             dst = self._u8(n)
             status = torch.empty(max(nb, 1), dtype=torch.int32, device=self.device)
@@ -243,12 +250,13 @@ class Context:
         return int(l2.value)
 
     # ------------------------------------------------------------------ host buffers (numpy / pinned torch)
-    def compress_host(self, src, block_size, table_log=0, n_states=32, table_mode=TABLE_PER_BLOCK, dst=None):
-        """src, dst: host uint8 arrays (numpy or CPU torch).  -> (dst, offsets, status, total)"""
+    def compress_host(self, src, block_size, table_log=0, n_states=32, table_mode=TABLE_PER_BLOCK, dst=None, segment_size=0, flags=0):
+        """src, dst: host uint8 arrays (numpy or CPU torch).  -> (dst, offsets, status, total).  A block that could not
+        be coded does not raise here: its status word is negative (FSE_B200_ERR_BLOCK is reported through `status`)."""
         import numpy as np
-        p = self.params(block_size, table_log, n_states, table_mode)
+        p = self.params(block_size, table_log, n_states, table_mode, segment_size, flags)
         n = int(src.size if hasattr(src, "size") and not callable(src.size) else src.numel())
-        nb = self.num_blocks(n, block_size)
+        nb = self.num_streams(n, p)
         if dst is None:
             dst = np.empty(self.bound(n, p), dtype=np.uint8)
         offsets = np.zeros(nb + 1, dtype=np.uint64)
@@ -260,10 +268,12 @@ class Context:
             self._ck(rc)
         return dst, offsets, status[:nb], int(total.value)
 
-    def decompress_host(self, comp, total, offsets, n, block_size, table_log=0, n_states=32, table_mode=TABLE_PER_BLOCK, dst=None):
+    def decompress_host(self, comp, total, offsets, n, block_size, table_log=0, n_states=32, table_mode=TABLE_PER_BLOCK, dst=None,
+                        segment_size=0, flags=0):
+        """-> (dst, status); a block that failed to decode has a negative status word (no exception: inspect `status`)"""
         import numpy as np
-        p = self.params(block_size, table_log, n_states, table_mode)
-        nb = self.num_blocks(n, block_size)
+        p = self.params(block_size, table_log, n_states, table_mode, segment_size, flags)
+        nb = self.num_streams(n, p)
         if dst is None:
             dst = np.empty(max(n, 1), dtype=np.uint8)
         status = np.zeros(max(nb, 1), dtype=np.int32)
@@ -275,16 +285,18 @@ class Context:
 
 
     # ------------------------------------------------------------------ self-describing frame
-    def frame_compress(self, src, block_size=65536, table_log=0, n_states=128, table_mode=TABLE_PER_BLOCK):
-        """host uint8 array -> numpy uint8 frame (parameters, offsets and payload in one buffer)"""
+    def frame_compress(self, src, block_size=65536, table_log=0, n_states=128, table_mode=TABLE_PER_BLOCK, segment_size=0, flags=0):
+        """host uint8 array -> numpy uint8 frame (parameters, offsets and payload in one buffer).  Raises FseError
+        (ERR_BLOCK) when a block could not be coded: such a frame could never be decoded."""
         import numpy as np
-        p = self.params(block_size, table_log, n_states, table_mode)
+        p = self.params(block_size, table_log, n_states, table_mode, segment_size, flags)
         n = int(src.size if hasattr(src, "size") and not callable(src.size) else src.numel())
         frame = np.empty(int(self._L.fse_b200_frame_bound(n, C.byref(p))), dtype=np.uint8)
         nbytes = C.c_size_t()
         rc = self._L.fse_b200_frame_compress_host(self._h, _host_ptr(src), n, C.byref(p), _host_ptr(frame), frame.size, C.byref(nbytes))
-        if rc not in (0, -11):
-            self._ck(rc)
+        if rc == -11:
+            raise FseError(rc, "frame_compress: at least one block could not be coded")
+        self._ck(rc)
         return frame[: nbytes.value]
 
     def frame_info(self, frame):
@@ -293,7 +305,8 @@ class Context:
         rc = self._L.fse_b200_frame_info(_host_ptr(frame), _host_len(frame), C.byref(p), C.byref(n))
         if rc != 0:
             raise FseError(rc, "bad frame")
-        return {"block_size": p.block_size, "table_log": p.table_log, "n_states": p.n_states, "table_mode": p.table_mode, "n": n.value}
+        return {"block_size": p.block_size, "table_log": p.table_log, "n_states": p.n_states, "table_mode": p.table_mode,
+                "segment_size": p.segment_size, "flags": p.flags, "n": n.value}
 
     def frame_decompress(self, frame):
         import numpy as np
@@ -301,8 +314,9 @@ class Context:
         dst = np.empty(max(n, 1), dtype=np.uint8)
         got = C.c_size_t()
         rc = self._L.fse_b200_frame_decompress_host(self._h, _host_ptr(frame), _host_len(frame), _host_ptr(dst), dst.size, C.byref(got))
-        if rc not in (0, -11):
-            self._ck(rc)
+        if rc == -11:
+            raise FseError(rc, "frame_decompress: at least one block failed to decode (corrupt or truncated frame)")
+        self._ck(rc)
         return dst[: got.value]
 
 

@@ -13,7 +13,7 @@ STATUS = {0: "OK", -1: "ERR_ARG", -2: "ERR_CAPACITY", -3: "ERR_TABLE_LOG", -4: "
 # every symbol include/fse_b200.h declares
 SYMBOLS = [
     "fse_b200_create", "fse_b200_destroy", "fse_b200_last_error", "fse_b200_version", "fse_b200_launch_count",
-    "fse_b200_sync", "fse_b200_set_timing", "fse_b200_get_timing", "fse_b200_compress_bound", "fse_b200_compress_blocks_bound", "fse_b200_num_blocks",
+    "fse_b200_sync", "fse_b200_set_timing", "fse_b200_get_timing", "fse_b200_compress_bound", "fse_b200_compress_blocks_bound", "fse_b200_num_blocks", "fse_b200_num_streams",
     "fse_b200_histogram_blocks", "fse_b200_histogram_global", "fse_b200_normalize", "fse_b200_ncount_write",
     "fse_b200_ncount_read", "fse_b200_build_encode_tables", "fse_b200_build_decode_tables",
     "fse_b200_compress_blocks", "fse_b200_compress_blocks_async", "fse_b200_decompress_blocks",
@@ -25,7 +25,7 @@ SYMBOLS = [
 
 class Params(C.Structure):
     _fields_ = [("block_size", C.c_uint32), ("table_log", C.c_uint32), ("n_states", C.c_uint32),
-                ("table_mode", C.c_uint32)]
+                ("table_mode", C.c_uint32), ("segment_size", C.c_uint32), ("flags", C.c_uint32)]
 
 
 class FseError(RuntimeError):
@@ -65,6 +65,8 @@ def lib():
     L.fse_b200_compress_blocks_bound.restype = sz
     L.fse_b200_num_blocks.argtypes = [sz, u32]
     L.fse_b200_num_blocks.restype = sz
+    L.fse_b200_num_streams.argtypes = [sz, PP]
+    L.fse_b200_num_streams.restype = sz
     L.fse_b200_histogram_blocks.argtypes = [vp, vp, sz, u32, vp, vp]
     L.fse_b200_histogram_global.argtypes = [vp, vp, sz, vp]
     L.fse_b200_normalize.argtypes = [vp, vp, sz, u32, vp, vp, vp, vp]

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SRC = os.path.join(HERE, "csrc", "fse_b200.cu")
-DEPS = [SRC, os.path.join(HERE, "csrc", "fse_decode128c.cuh"), os.path.join(HERE, "csrc", "fse_encode128.cuh"), os.path.join(HERE, "csrc", "fse_kernels128.cuh"), os.path.join(HERE, "csrc", "fse_decode64w.cuh"), os.path.join(HERE, "csrc", "fse_hist16.cuh"), os.path.join(HERE, "csrc", "fse_decode64c.cuh"), os.path.join(HERE, "csrc", "fse_kernels64.cuh"), os.path.join(HERE, "csrc", "fse_kernels.cuh"), os.path.join(HERE, "csrc", "fse_device.cuh"),
+DEPS = [SRC, os.path.join(HERE, "csrc", "fse_shared_enc.cuh"), os.path.join(HERE, "csrc", "fse_shared_dec.cuh"), os.path.join(HERE, "csrc", "fse_decode128c.cuh"), os.path.join(HERE, "csrc", "fse_encode128.cuh"), os.path.join(HERE, "csrc", "fse_kernels128.cuh"), os.path.join(HERE, "csrc", "fse_decode64w.cuh"), os.path.join(HERE, "csrc", "fse_hist16.cuh"), os.path.join(HERE, "csrc", "fse_decode64c.cuh"), os.path.join(HERE, "csrc", "fse_kernels64.cuh"), os.path.join(HERE, "csrc", "fse_kernels.cuh"), os.path.join(HERE, "csrc", "fse_device.cuh"),
         os.path.join(ROOT, "include", "fse_b200.h")]
 OUT = os.path.join(HERE, "libfse_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -29,6 +29,16 @@ def build(force=False, verbose=False):
         cmd.insert(2, "-v")
     subprocess.check_call(cmd)
     return OUT
+
+
+def build_variant(name, defines=()):
+    """development builds (tools/bin/lib<name>.so, selected with FSE_B200_LIB): -DFSE_DEV enables the environment overrides"""
+    out = os.path.join(ROOT, "tools", "bin", "lib%s.so" % name)
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-DFSE_DEV",
+           "-Xcompiler", "-fPIC", "-shared", "-o", out, SRC, "-lcudart"] + ["-D" + d for d in defines]
+    subprocess.check_call(cmd)
+    return out
 
 
 if __name__ == "__main__":

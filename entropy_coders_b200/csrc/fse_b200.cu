@@ -4,6 +4,8 @@
 #include "fse_encode128.cuh"
 #include "fse_decode128c.cuh"
 #include "fse_hist16.cuh"
+#include "fse_shared_enc.cuh"
+#include "fse_shared_dec.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -128,6 +130,17 @@ struct Timed {
 
 bool pow2(uint32_t v) { return v && !(v & (v - 1)); }
 
+// development overrides (variant builds under tools/bin only): the release library ignores the environment
+int dev_opt(const char *name, int dflt)
+{
+#ifdef FSE_DEV
+    if (const char *o = getenv(name)) return atoi(o);
+#else
+    (void)name;
+#endif
+    return dflt;
+}
+
 int check_params(fse_b200_ctx *ctx, const fse_b200_params *p)
 {
     if (!ctx || !p) return FSE_B200_ERR_ARG;
@@ -136,7 +149,23 @@ int check_params(fse_b200_ctx *ctx, const fse_b200_params *p)
     if (p->n_states >= 64 && p->table_log > 13) return fail(ctx, FSE_B200_ERR_UNSUPPORTED, "n_states 64 / 128 need table_log <= 13");
     if (p->table_log != 0 && (p->table_log < 5 || p->table_log > 15)) return fail(ctx, FSE_B200_ERR_ARG, "table_log must be 0 or 5..15");
     if (p->table_mode > 1) return fail(ctx, FSE_B200_ERR_ARG, "table_mode");
+    if (p->segment_size) {
+        if (p->table_mode != FSE_B200_TABLE_PER_BLOCK || p->n_states != 128)
+            return fail(ctx, FSE_B200_ERR_ARG, "segment_size needs per-block tables and n_states 128");
+        if (p->segment_size < 512 || p->block_size % p->segment_size || p->block_size / p->segment_size > 64)
+            return fail(ctx, FSE_B200_ERR_ARG, "segment_size must be >= 512 and divide block_size into at most 64 segments");
+        if (p->table_log > SH_TL_MAX) return fail(ctx, FSE_B200_ERR_UNSUPPORTED, "segment_size needs table_log <= 11");
+    }
+    if (p->flags & ~FSE_B200_FLAG_RAW_IF_EXPANDS) return fail(ctx, FSE_B200_ERR_ARG, "unknown flags");
     return 0;
+}
+
+// entries of the stream index and the bytes one stream covers
+size_t stream_bytes(const fse_b200_params *p) { return p->segment_size ? p->segment_size : p->block_size; }
+size_t num_streams(size_t n, const fse_b200_params *p)
+{
+    const size_t u = stream_bytes(p);
+    return u ? (n + u - 1) / u : 0;
 }
 
 // largest table_log a per-block launch can meet: the request (or optimal_log2 <= 11), raised to
@@ -218,6 +247,12 @@ int fse_b200_create(int device, void *stream, fse_b200_ctx **out)
     cudaFuncSetAttribute(k_decode128c_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 64);   // 16 bytes of static shared memory (block queue)
     cudaFuncSetAttribute(k_encode128_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 64);   // 16 bytes of static shared memory (block queue)
     cudaFuncSetAttribute(k_build_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
+    cudaFuncSetAttribute(k_encode_sh_global<16, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 64);
+    cudaFuncSetAttribute(k_encode_sh_global<16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 64);
+    cudaFuncSetAttribute(k_encode_sh_global<8, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 64);
+    cudaFuncSetAttribute(k_decode_sh_global, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 64);
+    cudaFuncSetAttribute(k_encode_sh_blocks<16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 64);
+    cudaFuncSetAttribute(k_decode_sh_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 64);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { fse_b200_destroy(ctx); return FSE_B200_ERR_CUDA; }
     *out = ctx;
@@ -282,11 +317,11 @@ int fse_b200_sync(fse_b200_ctx *ctx)
 
 size_t fse_b200_compress_bound(size_t size) { return 512 + size + (size >> 7) + 4 + 8; }
 size_t fse_b200_num_blocks(size_t n, uint32_t block_size) { return block_size ? (n + block_size - 1) / block_size : 0; }
+size_t fse_b200_num_streams(size_t n, const fse_b200_params *p) { return p && p->block_size ? num_streams(n, p) : 0; }
 size_t fse_b200_compress_blocks_bound(size_t n, const fse_b200_params *p)
 {
     if (!p || !p->block_size) return 0;
-    size_t nb = fse_b200_num_blocks(n, p->block_size);
-    return nb * scratch_stride(p->block_size, p->n_states ? p->n_states : 32) + 16;
+    return num_streams(n, p) * scratch_stride((uint32_t)stream_bytes(p), p->n_states ? p->n_states : 32) + 16;
 }
 
 // ---------------------------------------------------------------------------------- stages
@@ -512,8 +547,9 @@ int fse_b200_compress_blocks_async(fse_b200_ctx *ctx, const uint8_t *d_src, size
     if (rc) return rc;
     if ((!d_src && n) || !d_dst || !d_offsets || !d_status) return fail(ctx, FSE_B200_ERR_ARG, "compress_blocks: null pointer");
     CK(cudaSetDevice(ctx->device));
-    const size_t nb = fse_b200_num_blocks(n, p->block_size);
-    if (nb > 0x7fffffffull) return fail(ctx, FSE_B200_ERR_ARG, "too many blocks");
+    const size_t nb = fse_b200_num_blocks(n, p->block_size);      // tables (histograms) in per-block mode
+    const size_t ns = num_streams(n, p);                          // entries of the index
+    if (ns > 0x7fffffffull) return fail(ctx, FSE_B200_ERR_ARG, "too many blocks");
     if (dst_cap < fse_b200_compress_blocks_bound(n, p)) return fail(ctx, FSE_B200_ERR_CAPACITY, "dst_cap < fse_b200_compress_blocks_bound");
     const bool global = p->table_mode == FSE_B200_TABLE_GLOBAL;
     if (global && !ctx->g_valid) return fail(ctx, FSE_B200_ERR_ARG, "global table not installed");
@@ -522,10 +558,10 @@ int fse_b200_compress_blocks_async(fse_b200_ctx *ctx, const uint8_t *d_src, size
         return FSE_B200_OK;
     }
     const uint32_t tlmax = global ? ctx->g_log2 : tlmax_for(p);
-    const size_t stride = scratch_stride(p->block_size, p->n_states);
-    CK(ctx->hlen.reserve(nb * 4));
-    CK(ctx->plen.reserve(nb * 4));
-    CK(ctx->scratch.reserve(nb * stride));
+    const size_t stride = scratch_stride((uint32_t)stream_bytes(p), p->n_states);
+    CK(ctx->hlen.reserve(ns * 4));
+    CK(ctx->plen.reserve(ns * 4));
+    CK(ctx->scratch.reserve(ns * stride));
     if (!global) {
         CK(ctx->counts.reserve(nb * 256 * sizeof(uint32_t)));
         Timed t(ctx, FSE_B200_K_HIST);
@@ -536,7 +572,8 @@ int fse_b200_compress_blocks_async(fse_b200_ctx *ctx, const uint8_t *d_src, size
     a.req_log2 = p->table_log; a.n_states = p->n_states; a.tlmax = tlmax;
     a.counts = ctx->counts.as<uint32_t>();
     a.scratch = ctx->scratch.as<uint8_t>(); a.stride = stride;
-    a.pay_cap_words = (uint32_t)(pay_cap_bytes(p->block_size, p->n_states) / 4);
+    a.pay_cap_words = (uint32_t)(pay_cap_bytes((uint32_t)stream_bytes(p), p->n_states) / 4);
+    a.seg_size = p->segment_size; a.segs_per_block = p->segment_size ? p->block_size / p->segment_size : 1;
     a.hlen = ctx->hlen.as<uint32_t>(); a.plen = ctx->plen.as<uint32_t>(); a.status = d_status;
     a.global_mode = global ? 1 : 0;
     a.g.log2 = ctx->g_log2; a.g.table_len = ctx->g_table_len;
@@ -568,7 +605,29 @@ int fse_b200_compress_blocks_async(fse_b200_ctx *ctx, const uint8_t *d_src, size
         CK(cudaGetLastError());
         return FSE_B200_OK;
     }
-    {
+    if (p->segment_size) {
+        // one table per block, its segments coded by the warps of one CTA against bank-replicated tables
+        if (tlmax > SH_TL_MAX) return fail(ctx, FSE_B200_ERR_UNSUPPORTED, "segment_size needs table_log <= 11");
+        const size_t fixed = sh_enc_blocks_layout<16, 16>(tlmax, 0).total, pw = ShEncStage<16>::BYTES;
+        int w = (int)std::min<size_t>(std::min<size_t>(16, a.segs_per_block), (ctx->smem_optin - 64 - fixed) / pw);
+        w = std::max(1, std::min(w, dev_opt("FSE_B200_SH_WARPS", w)));
+        const int g = (int)std::min<size_t>(nb, (size_t)ctx->num_sms);
+        Timed t(ctx, FSE_B200_K_ENCODE);
+        k_encode_sh_blocks<16, 16><<<g, (w + 1) * 32, fixed + w * pw, ctx->stream>>>(a);
+    } else if (global && p->n_states == 128 && tlmax <= SH_TL_MAX) {
+        // one table for the job: CTA-owned, bank-replicated tables (fse_shared_enc.cuh), one CTA per SM
+        const int rounds = dev_opt("FSE_B200_SH_ROUNDS", 16), nsr = dev_opt("FSE_B200_SH_NSR", 16);
+        const size_t fixed = rounds == 8 ? sh_enc_layout<8, 32>(tlmax, 0).total
+                                         : (nsr == 32 ? sh_enc_layout<16, 32>(tlmax, 0).total : sh_enc_layout<16, 16>(tlmax, 0).total);
+        const size_t pw = rounds == 8 ? ShEncStage<8>::BYTES : ShEncStage<16>::BYTES;
+        int w = (int)std::min<size_t>(16, (ctx->smem_optin - 64 - fixed) / pw);
+        w = std::max(1, std::min(w, dev_opt("FSE_B200_SH_WARPS", w)));
+        const int g = (int)std::min<size_t>(nb, (size_t)ctx->num_sms);
+        Timed t(ctx, FSE_B200_K_ENCODE);
+        if (rounds == 8) k_encode_sh_global<8, 32><<<g, w * 32, fixed + w * pw, ctx->stream>>>(a);
+        else if (nsr == 32) k_encode_sh_global<16, 32><<<g, w * 32, fixed + w * pw, ctx->stream>>>(a);
+        else k_encode_sh_global<16, 16><<<g, w * 32, fixed + w * pw, ctx->stream>>>(a);
+    } else {
         Timed t(ctx, FSE_B200_K_ENCODE);
         if (p->n_states == 128) k_encode128_blocks<<<grid, wpc * 32, (size_t)wpc * per_warp, ctx->stream>>>(a);
         else if (wide) k_encode64_blocks<<<grid, wpc * 32, (size_t)wpc * per_warp, ctx->stream>>>(a);
@@ -576,12 +635,12 @@ int fse_b200_compress_blocks_async(fse_b200_ctx *ctx, const uint8_t *d_src, size
     }
     {
         Timed t(ctx, FSE_B200_K_SCAN);
-        k_scan_sizes<<<1, 1024, 0, ctx->stream>>>(a.hlen, a.plen, (uint32_t)nb, reinterpret_cast<unsigned long long *>(d_offsets));
+        k_scan_sizes<<<1, 1024, 0, ctx->stream>>>(a.hlen, a.plen, (uint32_t)ns, reinterpret_cast<unsigned long long *>(d_offsets));
     }
     {
         Timed t(ctx, FSE_B200_K_GATHER);
-        k_gather<<<(int)std::min<size_t>(nb, (size_t)ctx->num_sms * 8), 256, 0, ctx->stream>>>(
-            a.scratch, stride, a.hlen, a.plen, reinterpret_cast<const unsigned long long *>(d_offsets), (uint32_t)nb, d_dst);
+        k_gather<<<(int)std::min<size_t>(ns, (size_t)ctx->num_sms * 8), 256, 0, ctx->stream>>>(
+            a.scratch, stride, a.hlen, a.plen, reinterpret_cast<const unsigned long long *>(d_offsets), (uint32_t)ns, d_dst);
     }
     CK(cudaGetLastError());
     return FSE_B200_OK;
@@ -592,7 +651,7 @@ int fse_b200_compress_blocks(fse_b200_ctx *ctx, const uint8_t *d_src, size_t n, 
 {
     int rc = fse_b200_compress_blocks_async(ctx, d_src, n, p, d_dst, dst_cap, d_offsets, d_status);
     if (rc) return rc;
-    const size_t nb = fse_b200_num_blocks(n, p->block_size);
+    const size_t nb = num_streams(n, p);
     uint64_t total = 0;
     CK(cudaMemcpyAsync(&total, d_offsets + nb, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -606,7 +665,7 @@ int fse_b200_decompress_blocks_async(fse_b200_ctx *ctx, const uint8_t *d_comp, s
     int rc = check_params(ctx, p);
     if (rc) return rc;
     if (!d_comp || !d_offsets || (!d_dst && n) || !d_status) return fail(ctx, FSE_B200_ERR_ARG, "decompress_blocks: null pointer");
-    if (nblocks != fse_b200_num_blocks(n, p->block_size)) return fail(ctx, FSE_B200_ERR_ARG, "nblocks does not match n / block_size");
+    if (nblocks != num_streams(n, p)) return fail(ctx, FSE_B200_ERR_ARG, "nblocks does not match n / block_size (fse_b200_num_streams)");
     if (nblocks > 0x7fffffffull) return fail(ctx, FSE_B200_ERR_ARG, "too many blocks");
     CK(cudaSetDevice(ctx->device));
     if (nblocks == 0) return FSE_B200_OK;
@@ -615,12 +674,43 @@ int fse_b200_decompress_blocks_async(fse_b200_ctx *ctx, const uint8_t *d_comp, s
     const uint32_t tlmax = global ? ctx->g_log2 : tlmax_for(p);
     DecArgs a;
     a.comp = d_comp; a.comp_bytes = comp_bytes; a.offsets = reinterpret_cast<const unsigned long long *>(d_offsets);
-    a.nblocks = (uint32_t)nblocks; a.block_size = p->block_size; a.n = n; a.n_states = p->n_states; a.tlmax = tlmax;
+    a.nblocks = (uint32_t)fse_b200_num_blocks(n, p->block_size); a.block_size = p->block_size; a.n = n; a.n_states = p->n_states; a.tlmax = tlmax;
+    a.seg_size = p->segment_size; a.segs_per_block = p->segment_size ? p->block_size / p->segment_size : 1;
+    a.dec_copies = sh_dec_copies_for(tlmax);
     a.dst = d_dst; a.status = d_status; a.global_mode = global ? 1 : 0;
     a.exhaust = 0; a.out_len = nullptr;
     a.g.log2 = ctx->g_log2; a.g.table_len = ctx->g_table_len;
     a.g.enc_table = ctx->g_enc_table.as<uint16_t>(); a.g.enc_tt = ctx->g_enc_tt.as<uint2>(); a.g.dec_table = ctx->g_dec_table.as<uint32_t>();
     if (p->n_states == 64 && tlmax > 13) return fail(ctx, FSE_B200_ERR_UNSUPPORTED, "n_states 64 needs table_log <= 13");
+    if (p->segment_size) {
+        // one table per block: a CTA per block, its warps decode the block's segments against a bank-replicated table
+        if (tlmax > SH_TL_MAX) return fail(ctx, FSE_B200_ERR_UNSUPPORTED, "segment_size needs table_log <= 11");
+        const int w = (int)std::min<uint32_t>(16, a.segs_per_block);
+        // copies: as many as let two CTAs share an SM (decode needs ~32 warps in flight), at least 8
+        uint32_t R = (uint32_t)dev_opt("FSE_B200_SHD_COPIES", 0);
+        if (!R) {
+            R = 32;
+            while (R > 8 && 2 * (sh_dec_blocks_layout(tlmax, R, w).total + 1024) > ctx->smem_per_sm) R >>= 1;
+        }
+        a.dec_copies = R;
+        const size_t smem = sh_dec_blocks_layout(tlmax, R, w).total;
+        if (smem > ctx->smem_optin - 64) return fail(ctx, FSE_B200_ERR_UNSUPPORTED, "table too large for shared memory");
+        const int ctas = 2 * (smem + 1024) <= ctx->smem_per_sm ? 2 : 1;
+        const int g = (int)std::min<size_t>(a.nblocks, (size_t)ctx->num_sms * ctas);
+        Timed t(ctx, FSE_B200_K_DECODE);
+        k_decode_sh_blocks<<<g, (w + 1) * 32, smem, ctx->stream>>>(a);
+        CK(cudaGetLastError());
+        return FSE_B200_OK;
+    }
+    if (global && p->n_states == 128 && tlmax <= SH_TL_MAX) {
+        // CTA-owned, bank-replicated decode table (fse_shared_dec.cuh), one CTA per SM
+        const int w = std::max(1, std::min(32, dev_opt("FSE_B200_SHD_WARPS", 32)));
+        const int g = (int)std::min<size_t>(nblocks, (size_t)ctx->num_sms);
+        Timed t(ctx, FSE_B200_K_DECODE);
+        k_decode_sh_global<<<g, w * 32, sh_dec_layout(tlmax, a.dec_copies, w).total, ctx->stream>>>(a);
+        CK(cudaGetLastError());
+        return FSE_B200_OK;
+    }
     if (p->n_states == 128) {
         if (tlmax > 13) return fail(ctx, FSE_B200_ERR_UNSUPPORTED, "n_states 128 needs table_log <= 13");
         const size_t half = ctx->smem_per_sm / 2 - 1024;
@@ -682,7 +772,7 @@ int fse_b200_decompress_exhaust(fse_b200_ctx *ctx, const uint8_t *d_comp, size_t
     int rc = check_params(ctx, p);
     if (rc) return rc;
     if (!d_comp || !d_offsets || !d_dst || !d_out_len || !d_status) return fail(ctx, FSE_B200_ERR_ARG, "decompress_exhaust: null pointer");
-    if (p->table_mode != FSE_B200_TABLE_PER_BLOCK) return fail(ctx, FSE_B200_ERR_ARG, "decompress_exhaust: per-block tables only");
+    if (p->table_mode != FSE_B200_TABLE_PER_BLOCK || p->segment_size) return fail(ctx, FSE_B200_ERR_ARG, "decompress_exhaust: per-block tables, no segments");
     if (p->n_states > 32) return fail(ctx, FSE_B200_ERR_ARG, "decompress_exhaust: n_states <= 32");
     if (nblocks > 0x7fffffffull) return fail(ctx, FSE_B200_ERR_ARG, "too many blocks");
     CK(cudaSetDevice(ctx->device));
@@ -693,6 +783,7 @@ int fse_b200_decompress_exhaust(fse_b200_ctx *ctx, const uint8_t *d_comp, size_t
     a.nblocks = (uint32_t)nblocks; a.block_size = p->block_size; a.n = nblocks * (size_t)p->block_size;
     a.n_states = p->n_states; a.tlmax = tlmax;
     a.dst = d_dst; a.status = d_status; a.global_mode = 0; a.exhaust = 1; a.out_len = d_out_len;
+    a.seg_size = 0; a.segs_per_block = 1; a.dec_copies = 0;
     a.g.log2 = 0; a.g.table_len = 0; a.g.enc_table = nullptr; a.g.enc_tt = nullptr; a.g.dec_table = nullptr;
     const DecLayout lay = dec_layout(tlmax);
     int wpc = pick_warps(nblocks, ctx->num_sms, lay.total, ctx->smem_optin, 16);
@@ -706,18 +797,17 @@ int fse_b200_decompress_exhaust(fse_b200_ctx *ctx, const uint8_t *d_comp, size_t
 }
 
 // ---------------------------------------------------------------------------------- host buffers
+// Large host buffers are processed in chunks of whole blocks so that the H2D copy of chunk i+1, the kernels of
+// chunk i and the D2H copy of chunk i-1 overlap (PCIe is full duplex): three streams, events between them.  Every
+// small read-back (per-chunk totals, the index, the status words) lands in the context's pinned buffer, so that no
+// copy inside the loop is a staged synchronous one.  "Streams" below are the entries of the index: blocks, or
+// segments when p->segment_size > 0.
 
 static int worst_status(const int32_t *st, size_t nb)
 {
     for (size_t i = 0; i < nb; i++) if (st[i] < 0) return FSE_B200_ERR_BLOCK;
     return FSE_B200_OK;
 }
-
-
-// ---------------------------------------------------------------------------------- pipelined host paths
-// Large host buffers are processed in chunks of whole blocks so that the H2D copy of chunk i+1, the
-// kernels of chunk i and the D2H copy of chunk i-1 overlap (PCIe is full duplex): three streams, events
-// between them, pinned scalars for the per-chunk totals.
 
 static const size_t PIPE_CHUNK_BYTES = 32u << 20;
 
@@ -733,118 +823,6 @@ static int pipe_setup(fse_b200_ctx *ctx, size_t nchunks)
     return FSE_B200_OK;
 }
 
-static int compress_host_pipelined(fse_b200_ctx *ctx, const uint8_t *h_src, size_t n, const fse_b200_params *p, uint8_t *h_dst,
-                                   size_t dst_cap, uint64_t *h_offsets, int32_t *h_status, uint64_t *h_total)
-{
-    const size_t bs = p->block_size;
-    const size_t cblocks = std::max<size_t>(1, PIPE_CHUNK_BYTES / bs), cbytes = cblocks * bs;
-    const size_t nchunks = (n + cbytes - 1) / cbytes;
-    const size_t nb = fse_b200_num_blocks(n, p->block_size);
-    const size_t cbound = fse_b200_compress_blocks_bound(cbytes, p);
-    int rc = pipe_setup(ctx, nchunks);
-    if (rc) return rc;
-    CK(ctx->stage_in.reserve(n + 16));
-    CK(ctx->stage_out.reserve(nchunks * cbound));
-    CK(ctx->stage_off.reserve(nchunks * (cblocks + 1) * 8));
-    CK(ctx->stage_status.reserve((nb + 1) * 4));
-    CK(ctx->pin.reserve(nchunks * 8));
-    uint64_t *h_tot = reinterpret_cast<uint64_t *>(ctx->pin.p);
-    std::vector<uint64_t> loc((cblocks + 1) * nchunks);
-    std::vector<int32_t> st(nb);
-    // an event orders the copy streams after whatever the caller queued on the compute stream
-    CK(cudaEventRecord(ctx->pipe_ev[2 * nchunks], ctx->stream));
-    CK(cudaStreamWaitEvent(ctx->s_in, ctx->pipe_ev[2 * nchunks], 0));
-    for (size_t c = 0; c < nchunks; c++) {
-        size_t o = c * cbytes, len = std::min(cbytes, n - o);
-        CK(cudaMemcpyAsync(ctx->stage_in.as<uint8_t>() + o, h_src + o, len, cudaMemcpyHostToDevice, ctx->s_in));
-        CK(cudaEventRecord(ctx->pipe_ev[2 * c], ctx->s_in));
-    }
-    for (size_t c = 0; c < nchunks; c++) {
-        size_t o = c * cbytes, len = std::min(cbytes, n - o), cnb = fse_b200_num_blocks(len, p->block_size);
-        uint64_t *d_off = ctx->stage_off.as<uint64_t>() + c * (cblocks + 1);
-        CK(cudaStreamWaitEvent(ctx->stream, ctx->pipe_ev[2 * c], 0));
-        rc = fse_b200_compress_blocks_async(ctx, ctx->stage_in.as<uint8_t>() + o, len, p, ctx->stage_out.as<uint8_t>() + c * cbound,
-                                            cbound, d_off, ctx->stage_status.as<int32_t>() + c * cblocks);
-        if (rc) return rc;
-        CK(cudaMemcpyAsync(h_tot + c, d_off + cnb, 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaEventRecord(ctx->pipe_ev[2 * c + 1], ctx->stream));
-    }
-    uint64_t run = 0;
-    int ret = FSE_B200_OK;
-    for (size_t c = 0; c < nchunks; c++) {
-        size_t o = c * cbytes, len = std::min(cbytes, n - o), cnb = fse_b200_num_blocks(len, p->block_size);
-        CK(cudaEventSynchronize(ctx->pipe_ev[2 * c + 1]));
-        uint64_t tot = h_tot[c];
-        CK(cudaStreamWaitEvent(ctx->s_out, ctx->pipe_ev[2 * c + 1], 0));
-        if (run + tot > dst_cap) ret = FSE_B200_ERR_CAPACITY;
-        else CK(cudaMemcpyAsync(h_dst + run, ctx->stage_out.as<uint8_t>() + c * cbound, tot, cudaMemcpyDeviceToHost, ctx->s_out));
-        CK(cudaMemcpyAsync(loc.data() + c * (cblocks + 1), ctx->stage_off.as<uint64_t>() + c * (cblocks + 1), (cnb + 1) * 8,
-                           cudaMemcpyDeviceToHost, ctx->s_out));
-        run += tot;
-    }
-    if (nb) CK(cudaMemcpyAsync(st.data(), ctx->stage_status.p, nb * 4, cudaMemcpyDeviceToHost, ctx->s_out));
-    CK(cudaStreamSynchronize(ctx->s_out));
-    CK(cudaStreamSynchronize(ctx->stream));
-    *h_total = run;
-    if (ret) return fail(ctx, ret, "compress_host: dst_cap too small");
-    if (h_offsets) {
-        uint64_t base = 0;
-        for (size_t c = 0; c < nchunks; c++) {
-            size_t o = c * cbytes, len = std::min(cbytes, n - o), cnb = fse_b200_num_blocks(len, p->block_size);
-            const uint64_t *l = loc.data() + c * (cblocks + 1);
-            for (size_t b = 0; b < cnb; b++) h_offsets[c * cblocks + b] = base + l[b];
-            base += l[cnb];
-        }
-        h_offsets[nb] = base;
-    }
-    if (h_status && nb) memcpy(h_status, st.data(), nb * 4);
-    return worst_status(st.data(), nb);
-}
-
-static int decompress_host_pipelined(fse_b200_ctx *ctx, const uint8_t *h_comp, size_t comp_bytes, const uint64_t *h_offsets,
-                                     size_t nblocks, const fse_b200_params *p, uint8_t *h_dst, size_t n, int32_t *h_status)
-{
-    const size_t bs = p->block_size;
-    const size_t cblocks = std::max<size_t>(1, PIPE_CHUNK_BYTES / bs), cbytes = cblocks * bs;
-    const size_t nchunks = (nblocks + cblocks - 1) / cblocks;
-    int rc = pipe_setup(ctx, nchunks);
-    if (rc) return rc;
-    if (h_offsets[nblocks] > comp_bytes) return fail(ctx, FSE_B200_ERR_ARG, "decompress_host: offsets exceed comp_bytes");
-    CK(ctx->stage_out.reserve(comp_bytes + 16));
-    CK(ctx->stage_in.reserve(n + 16));
-    CK(ctx->stage_off.reserve((nblocks + 1) * 8));
-    CK(ctx->stage_status.reserve((nblocks + 1) * 4));
-    std::vector<int32_t> st(nblocks);
-    CK(cudaEventRecord(ctx->pipe_ev[2 * nchunks], ctx->stream));
-    CK(cudaStreamWaitEvent(ctx->s_in, ctx->pipe_ev[2 * nchunks], 0));
-    CK(cudaMemcpyAsync(ctx->stage_off.p, h_offsets, (nblocks + 1) * 8, cudaMemcpyHostToDevice, ctx->s_in));
-    for (size_t c = 0; c < nchunks; c++) {
-        size_t b0 = c * cblocks, b1 = std::min(nblocks, b0 + cblocks);
-        for (size_t b = b0; b < b1; b++)
-            if (h_offsets[b + 1] < h_offsets[b]) return fail(ctx, FSE_B200_ERR_ARG, "decompress_host: offsets not monotone");
-        uint64_t o0 = h_offsets[b0], o1 = h_offsets[b1];
-        if (o1 > o0) CK(cudaMemcpyAsync(ctx->stage_out.as<uint8_t>() + o0, h_comp + o0, o1 - o0, cudaMemcpyHostToDevice, ctx->s_in));
-        CK(cudaEventRecord(ctx->pipe_ev[2 * c], ctx->s_in));
-    }
-    for (size_t c = 0; c < nchunks; c++) {
-        size_t b0 = c * cblocks, b1 = std::min(nblocks, b0 + cblocks);
-        size_t o = b0 * bs, len = std::min(cbytes, n - o);
-        CK(cudaStreamWaitEvent(ctx->stream, ctx->pipe_ev[2 * c], 0));
-        rc = fse_b200_decompress_blocks_async(ctx, ctx->stage_out.as<uint8_t>(), comp_bytes, ctx->stage_off.as<uint64_t>() + b0, b1 - b0,
-                                              p, ctx->stage_in.as<uint8_t>() + o, len, ctx->stage_status.as<int32_t>() + b0);
-        if (rc) return rc;
-        CK(cudaEventRecord(ctx->pipe_ev[2 * c + 1], ctx->stream));
-        CK(cudaStreamWaitEvent(ctx->s_out, ctx->pipe_ev[2 * c + 1], 0));
-        CK(cudaMemcpyAsync(h_dst + o, ctx->stage_in.as<uint8_t>() + o, len, cudaMemcpyDeviceToHost, ctx->s_out));
-    }
-    CK(cudaStreamWaitEvent(ctx->s_out, ctx->pipe_ev[2 * (nchunks - 1) + 1], 0));
-    if (nblocks) CK(cudaMemcpyAsync(st.data(), ctx->stage_status.p, nblocks * 4, cudaMemcpyDeviceToHost, ctx->s_out));
-    CK(cudaStreamSynchronize(ctx->s_out));
-    CK(cudaStreamSynchronize(ctx->stream));
-    if (h_status && nblocks) memcpy(h_status, st.data(), nblocks * 4);
-    return worst_status(st.data(), nblocks);
-}
-
 int fse_b200_compress_host(fse_b200_ctx *ctx, const uint8_t *h_src, size_t n, const fse_b200_params *p, uint8_t *h_dst,
                            size_t dst_cap, uint64_t *h_offsets, int32_t *h_status, uint64_t *h_total)
 {
@@ -852,31 +830,74 @@ int fse_b200_compress_host(fse_b200_ctx *ctx, const uint8_t *h_src, size_t n, co
     if (rc) return rc;
     if ((!h_src && n) || !h_dst || !h_total) return fail(ctx, FSE_B200_ERR_ARG, "compress_host: null pointer");
     CK(cudaSetDevice(ctx->device));
-    if (n > 2 * PIPE_CHUNK_BYTES && p->block_size <= PIPE_CHUNK_BYTES)
-        return compress_host_pipelined(ctx, h_src, n, p, h_dst, dst_cap, h_offsets, h_status, h_total);
-    const size_t nb = fse_b200_num_blocks(n, p->block_size);
-    const size_t bound = fse_b200_compress_blocks_bound(n, p);
-    CK(ctx->stage_in.reserve(n + 16));
-    CK(ctx->stage_out.reserve(bound));
-    CK(ctx->stage_off.reserve((nb + 1) * 8));
-    CK(ctx->stage_status.reserve((nb + 1) * 4));
-    CK(cudaMemcpyAsync(ctx->stage_in.p, h_src, n, cudaMemcpyHostToDevice, ctx->stream));
-    rc = fse_b200_compress_blocks_async(ctx, ctx->stage_in.as<uint8_t>(), n, p, ctx->stage_out.as<uint8_t>(), bound,
-                                        ctx->stage_off.as<uint64_t>(), ctx->stage_status.as<int32_t>());
+    const size_t bs = p->block_size, S = bs / stream_bytes(p);
+    const size_t ns = num_streams(n, p);
+    // chunks of whole blocks; small inputs are one chunk
+    const size_t cblocks = (n > 2 * PIPE_CHUNK_BYTES && bs <= PIPE_CHUNK_BYTES) ? std::max<size_t>(1, PIPE_CHUNK_BYTES / bs)
+                                                                                 : std::max<size_t>(1, fse_b200_num_blocks(n, p->block_size));
+    const size_t cbytes = cblocks * bs, cstreams = cblocks * S;
+    const size_t nchunks = std::max<size_t>(1, (n + cbytes - 1) / cbytes);
+    const size_t cbound = fse_b200_compress_blocks_bound(std::min(cbytes, n), p);
+    rc = pipe_setup(ctx, nchunks);
     if (rc) return rc;
-    std::vector<uint64_t> off(nb + 1);
-    std::vector<int32_t> st(nb);
-    CK(cudaMemcpyAsync(off.data(), ctx->stage_off.p, (nb + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    if (nb) CK(cudaMemcpyAsync(st.data(), ctx->stage_status.p, nb * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx->stage_in.reserve(n + 16));
+    CK(ctx->stage_out.reserve(nchunks * cbound));
+    CK(ctx->stage_off.reserve(nchunks * (cstreams + 1) * 8));
+    CK(ctx->stage_status.reserve((ns + 1) * 4));
+    // pinned: totals[nchunks] | loc[nchunks][cstreams + 1] | status[ns]
+    const size_t pin_loc = nchunks * 8, pin_st = pin_loc + nchunks * (cstreams + 1) * 8;
+    CK(ctx->pin.reserve(pin_st + (ns + 1) * 4));
+    uint64_t *h_tot = reinterpret_cast<uint64_t *>(ctx->pin.p);
+    uint64_t *loc = reinterpret_cast<uint64_t *>(static_cast<uint8_t *>(ctx->pin.p) + pin_loc);
+    int32_t *st = reinterpret_cast<int32_t *>(static_cast<uint8_t *>(ctx->pin.p) + pin_st);
+    // an event orders the copy streams after whatever the caller queued on the compute stream
+    CK(cudaEventRecord(ctx->pipe_ev[2 * nchunks], ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->s_in, ctx->pipe_ev[2 * nchunks], 0));
+    for (size_t c = 0; c < nchunks && n; c++) {
+        size_t o = c * cbytes, len = std::min(cbytes, n - o);
+        CK(cudaMemcpyAsync(ctx->stage_in.as<uint8_t>() + o, h_src + o, len, cudaMemcpyHostToDevice, ctx->s_in));
+        CK(cudaEventRecord(ctx->pipe_ev[2 * c], ctx->s_in));
+    }
+    for (size_t c = 0; c < nchunks && n; c++) {
+        size_t o = c * cbytes, len = std::min(cbytes, n - o), cns = num_streams(len, p);
+        uint64_t *d_off = ctx->stage_off.as<uint64_t>() + c * (cstreams + 1);
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->pipe_ev[2 * c], 0));
+        rc = fse_b200_compress_blocks_async(ctx, ctx->stage_in.as<uint8_t>() + o, len, p, ctx->stage_out.as<uint8_t>() + c * cbound,
+                                            cbound, d_off, ctx->stage_status.as<int32_t>() + c * cstreams);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(h_tot + c, d_off + cns, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaEventRecord(ctx->pipe_ev[2 * c + 1], ctx->stream));
+    }
+    uint64_t run = 0;
+    int ret = FSE_B200_OK;
+    for (size_t c = 0; c < nchunks && n; c++) {
+        size_t o = c * cbytes, len = std::min(cbytes, n - o), cns = num_streams(len, p);
+        CK(cudaEventSynchronize(ctx->pipe_ev[2 * c + 1]));
+        const uint64_t tot = h_tot[c];
+        CK(cudaStreamWaitEvent(ctx->s_out, ctx->pipe_ev[2 * c + 1], 0));
+        if (run + tot > dst_cap) ret = FSE_B200_ERR_CAPACITY;
+        else if (tot) CK(cudaMemcpyAsync(h_dst + run, ctx->stage_out.as<uint8_t>() + c * cbound, tot, cudaMemcpyDeviceToHost, ctx->s_out));
+        CK(cudaMemcpyAsync(loc + c * (cstreams + 1), ctx->stage_off.as<uint64_t>() + c * (cstreams + 1), (cns + 1) * 8,
+                           cudaMemcpyDeviceToHost, ctx->s_out));
+        run += tot;
+    }
+    if (ns) CK(cudaMemcpyAsync(st, ctx->stage_status.p, ns * 4, cudaMemcpyDeviceToHost, ctx->s_out));
+    CK(cudaStreamSynchronize(ctx->s_out));
     CK(cudaStreamSynchronize(ctx->stream));
-    uint64_t total = off[nb];
-    *h_total = total;
-    if (h_offsets) memcpy(h_offsets, off.data(), (nb + 1) * 8);
-    if (h_status && nb) memcpy(h_status, st.data(), nb * 4);
-    if (total > dst_cap) return fail(ctx, FSE_B200_ERR_CAPACITY, "compress_host: dst_cap too small");
-    CK(cudaMemcpyAsync(h_dst, ctx->stage_out.p, total, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    return worst_status(st.data(), nb);
+    *h_total = run;
+    if (ret) return fail(ctx, ret, "compress_host: dst_cap too small");
+    if (h_offsets) {
+        uint64_t base = 0;
+        for (size_t c = 0; c < nchunks && n; c++) {
+            size_t o = c * cbytes, len = std::min(cbytes, n - o), cns = num_streams(len, p);
+            const uint64_t *l = loc + c * (cstreams + 1);
+            for (size_t b = 0; b < cns; b++) h_offsets[c * cstreams + b] = base + l[b];
+            base += l[cns];
+        }
+        h_offsets[ns] = base;
+    }
+    if (h_status && ns) memcpy(h_status, st, ns * 4);
+    return worst_status(st, ns);
 }
 
 int fse_b200_decompress_host(fse_b200_ctx *ctx, const uint8_t *h_comp, size_t comp_bytes, const uint64_t *h_offsets,
@@ -886,57 +907,99 @@ int fse_b200_decompress_host(fse_b200_ctx *ctx, const uint8_t *h_comp, size_t co
     if (rc) return rc;
     if (!h_comp || !h_offsets || (!h_dst && n)) return fail(ctx, FSE_B200_ERR_ARG, "decompress_host: null pointer");
     CK(cudaSetDevice(ctx->device));
-    if (nblocks != fse_b200_num_blocks(n, p->block_size)) return fail(ctx, FSE_B200_ERR_ARG, "nblocks does not match n / block_size");
-    if (n > 2 * PIPE_CHUNK_BYTES && p->block_size <= PIPE_CHUNK_BYTES)
-        return decompress_host_pipelined(ctx, h_comp, comp_bytes, h_offsets, nblocks, p, h_dst, n, h_status);
+    const size_t ns = num_streams(n, p);
+    if (nblocks != ns) return fail(ctx, FSE_B200_ERR_ARG, "nblocks does not match n / block_size (fse_b200_num_streams)");
+    if (ns > 0x7fffffffull) return fail(ctx, FSE_B200_ERR_ARG, "too many blocks");
+    if (ns == 0) return FSE_B200_OK;
+    for (size_t b = 0; b < ns; b++)
+        if (h_offsets[b + 1] < h_offsets[b]) return fail(ctx, FSE_B200_ERR_ARG, "decompress_host: offsets not monotone");
+    if (h_offsets[ns] > comp_bytes) return fail(ctx, FSE_B200_ERR_ARG, "decompress_host: offsets exceed comp_bytes");
+    const size_t bs = p->block_size, S = bs / stream_bytes(p);
+    const size_t nb = fse_b200_num_blocks(n, p->block_size);
+    const size_t cblocks = (n > 2 * PIPE_CHUNK_BYTES && bs <= PIPE_CHUNK_BYTES) ? std::max<size_t>(1, PIPE_CHUNK_BYTES / bs) : nb;
+    const size_t cbytes = cblocks * bs, cstreams = cblocks * S;
+    const size_t nchunks = (nb + cblocks - 1) / cblocks;
+    rc = pipe_setup(ctx, nchunks);
+    if (rc) return rc;
     CK(ctx->stage_out.reserve(comp_bytes + 16));
     CK(ctx->stage_in.reserve(n + 16));
-    CK(ctx->stage_off.reserve((nblocks + 1) * 8));
-    CK(ctx->stage_status.reserve((nblocks + 1) * 4));
-    CK(cudaMemcpyAsync(ctx->stage_out.p, h_comp, comp_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->stage_off.p, h_offsets, (nblocks + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-    rc = fse_b200_decompress_blocks_async(ctx, ctx->stage_out.as<uint8_t>(), comp_bytes, ctx->stage_off.as<uint64_t>(), nblocks, p,
-                                          ctx->stage_in.as<uint8_t>(), n, ctx->stage_status.as<int32_t>());
-    if (rc) return rc;
-    std::vector<int32_t> st(nblocks);
-    if (n) CK(cudaMemcpyAsync(h_dst, ctx->stage_in.p, n, cudaMemcpyDeviceToHost, ctx->stream));
-    if (nblocks) CK(cudaMemcpyAsync(st.data(), ctx->stage_status.p, nblocks * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx->stage_off.reserve((ns + 1) * 8));
+    CK(ctx->stage_status.reserve((ns + 1) * 4));
+    CK(ctx->pin.reserve((ns + 1) * 4));
+    int32_t *st = reinterpret_cast<int32_t *>(ctx->pin.p);
+    CK(cudaEventRecord(ctx->pipe_ev[2 * nchunks], ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->s_in, ctx->pipe_ev[2 * nchunks], 0));
+    CK(cudaMemcpyAsync(ctx->stage_off.p, h_offsets, (ns + 1) * 8, cudaMemcpyHostToDevice, ctx->s_in));
+    for (size_t c = 0; c < nchunks; c++) {
+        const size_t s0 = c * cstreams, s1 = std::min(ns, s0 + cstreams);
+        const uint64_t o0 = h_offsets[s0], o1 = h_offsets[s1];
+        if (o1 > o0) CK(cudaMemcpyAsync(ctx->stage_out.as<uint8_t>() + o0, h_comp + o0, o1 - o0, cudaMemcpyHostToDevice, ctx->s_in));
+        CK(cudaEventRecord(ctx->pipe_ev[2 * c], ctx->s_in));
+    }
+    for (size_t c = 0; c < nchunks; c++) {
+        const size_t s0 = c * cstreams, s1 = std::min(ns, s0 + cstreams);
+        const size_t o = c * cbytes, len = std::min(cbytes, n - o);
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->pipe_ev[2 * c], 0));
+        rc = fse_b200_decompress_blocks_async(ctx, ctx->stage_out.as<uint8_t>(), comp_bytes, ctx->stage_off.as<uint64_t>() + s0, s1 - s0,
+                                              p, ctx->stage_in.as<uint8_t>() + o, len, ctx->stage_status.as<int32_t>() + s0);
+        if (rc) return rc;
+        CK(cudaEventRecord(ctx->pipe_ev[2 * c + 1], ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->s_out, ctx->pipe_ev[2 * c + 1], 0));
+        CK(cudaMemcpyAsync(h_dst + o, ctx->stage_in.as<uint8_t>() + o, len, cudaMemcpyDeviceToHost, ctx->s_out));
+    }
+    CK(cudaMemcpyAsync(st, ctx->stage_status.p, ns * 4, cudaMemcpyDeviceToHost, ctx->s_out));
+    CK(cudaStreamSynchronize(ctx->s_out));
     CK(cudaStreamSynchronize(ctx->stream));
-    if (h_status && nblocks) memcpy(h_status, st.data(), nblocks * 4);
-    return worst_status(st.data(), nblocks);
+    if (h_status) memcpy(h_status, st, ns * 4);
+    return worst_status(st, ns);
 }
 
 // ---------------------------------------------------------------------------------- frame (container)
 
 namespace {
-struct FrameHeader {            // 48 bytes, little endian
+struct FrameHeader {            // 56 bytes, little endian
     uint32_t magic;
     uint16_t version, n_states;
     uint32_t block_size, table_log, table_mode, global_header_bytes;
-    uint64_t n, nblocks, payload_bytes;
+    uint64_t n, nstreams, payload_bytes;
+    uint32_t segment_size, flags;
 };
-static_assert(sizeof(FrameHeader) == 48, "frame header layout");
+static_assert(sizeof(FrameHeader) == 56, "frame header layout");
 size_t pad8(size_t v) { return (v + 7) & ~(size_t)7; }
 }  // namespace
 
 size_t fse_b200_frame_bound(size_t n, const fse_b200_params *p)
 {
     if (!p || !p->block_size) return 0;
-    size_t nb = fse_b200_num_blocks(n, p->block_size);
-    return sizeof(FrameHeader) + 512 + (nb + 1) * 8 + fse_b200_compress_blocks_bound(n, p);
+    return sizeof(FrameHeader) + 512 + (num_streams(n, p) + 1) * 8 + fse_b200_compress_blocks_bound(n, p);
 }
 
+// Everything in a frame header is untrusted: each term is checked against what is left of the frame before it is
+// used, so that no sum can wrap, and the parameters must be ones the library could have written.
 int fse_b200_frame_info(const uint8_t *h_frame, size_t frame_bytes, fse_b200_params *p_out, size_t *n_out)
 {
     if (!h_frame || frame_bytes < sizeof(FrameHeader)) return FSE_B200_ERR_ARG;
     FrameHeader h;
     memcpy(&h, h_frame, sizeof(h));
-    if (h.magic != FSE_B200_FRAME_MAGIC || h.version != 1) return FSE_B200_ERR_ARG;
-    if (h.block_size == 0 || h.nblocks != fse_b200_num_blocks(h.n, h.block_size) || h.global_header_bytes > 512) return FSE_B200_ERR_ARG;
-    size_t need = sizeof(FrameHeader) + pad8(h.global_header_bytes) + (h.nblocks + 1) * 8 + h.payload_bytes;
-    if (need > frame_bytes) return FSE_B200_ERR_CAPACITY;
-    if (p_out) { p_out->block_size = h.block_size; p_out->table_log = h.table_log; p_out->n_states = h.n_states; p_out->table_mode = h.table_mode; }
-    if (n_out) *n_out = h.n;
+    if (h.magic != FSE_B200_FRAME_MAGIC || h.version != 2) return FSE_B200_ERR_ARG;
+    fse_b200_params p;
+    p.block_size = h.block_size; p.table_log = h.table_log; p.n_states = h.n_states; p.table_mode = h.table_mode;
+    p.segment_size = h.segment_size; p.flags = h.flags;
+    fse_b200_ctx scratch_ctx;                               // only its error string is touched
+    if (check_params(&scratch_ctx, &p)) return FSE_B200_ERR_ARG;
+    if (h.global_header_bytes > 512 || (p.table_mode == FSE_B200_TABLE_GLOBAL) != (h.global_header_bytes != 0)) return FSE_B200_ERR_ARG;
+    if (h.n > ((uint64_t)1 << 62)) return FSE_B200_ERR_ARG;
+    if (h.nstreams != num_streams((size_t)h.n, &p) || h.nstreams > 0x7fffffffull) return FSE_B200_ERR_ARG;
+    size_t left = frame_bytes - sizeof(FrameHeader);
+    const size_t gh = pad8(h.global_header_bytes);
+    if (gh > left) return FSE_B200_ERR_CAPACITY;
+    left -= gh;
+    const size_t idx = ((size_t)h.nstreams + 1) * 8;        // nstreams < 2^31: cannot wrap
+    if (idx > left) return FSE_B200_ERR_CAPACITY;
+    left -= idx;
+    if (h.payload_bytes > left) return FSE_B200_ERR_CAPACITY;
+    if (p_out) *p_out = p;
+    if (n_out) *n_out = (size_t)h.n;
     return FSE_B200_OK;
 }
 
@@ -947,12 +1010,13 @@ int fse_b200_frame_compress_host(fse_b200_ctx *ctx, const uint8_t *h_src, size_t
     if (rc) return rc;
     if ((!h_src && n) || !h_frame || !h_frame_bytes) return fail(ctx, FSE_B200_ERR_ARG, "frame_compress_host: null pointer");
     CK(cudaSetDevice(ctx->device));
-    const size_t nb = fse_b200_num_blocks(n, p->block_size);
+    const size_t ns = num_streams(n, p);
     FrameHeader h;
     memset(&h, 0, sizeof(h));
-    h.magic = FSE_B200_FRAME_MAGIC; h.version = 1; h.n_states = (uint16_t)p->n_states;
+    h.magic = FSE_B200_FRAME_MAGIC; h.version = 2; h.n_states = (uint16_t)p->n_states;
     h.block_size = p->block_size; h.table_log = p->table_log; h.table_mode = p->table_mode;
-    h.n = n; h.nblocks = nb;
+    h.segment_size = p->segment_size; h.flags = p->flags;
+    h.n = n; h.nstreams = ns;
     uint8_t ghdr[512];
     size_t gbytes = 0;
     if (p->table_mode == FSE_B200_TABLE_GLOBAL) {
@@ -970,18 +1034,18 @@ int fse_b200_frame_compress_host(fse_b200_ctx *ctx, const uint8_t *h_src, size_t
         h.global_header_bytes = (uint32_t)gbytes;
     }
     const size_t off_pos = sizeof(FrameHeader) + pad8(gbytes);
-    const size_t pay_pos = off_pos + (nb + 1) * 8;
+    const size_t pay_pos = off_pos + (ns + 1) * 8;
     if (frame_cap < pay_pos) return fail(ctx, FSE_B200_ERR_CAPACITY, "frame_compress_host: frame_cap too small");
-    std::vector<uint64_t> off(nb + 1);
+    std::vector<uint64_t> off(ns + 1);
     uint64_t total = 0;
     rc = fse_b200_compress_host(ctx, h_src, n, p, h_frame + pay_pos, frame_cap - pay_pos, off.data(), nullptr, &total);
     if (rc != FSE_B200_OK && rc != FSE_B200_ERR_BLOCK) return rc;
     h.payload_bytes = total;
     memcpy(h_frame, &h, sizeof(h));
     if (gbytes) { memset(h_frame + sizeof(FrameHeader), 0, pad8(gbytes)); memcpy(h_frame + sizeof(FrameHeader), ghdr, gbytes); }
-    memcpy(h_frame + off_pos, off.data(), (nb + 1) * 8);
+    memcpy(h_frame + off_pos, off.data(), (ns + 1) * 8);
     *h_frame_bytes = pay_pos + total;
-    return rc;
+    return rc;                                              // FSE_B200_ERR_BLOCK: a block could not be coded, the frame cannot be decoded
 }
 
 int fse_b200_frame_decompress_host(fse_b200_ctx *ctx, const uint8_t *h_frame, size_t frame_bytes, uint8_t *h_dst,
@@ -1003,11 +1067,12 @@ int fse_b200_frame_decompress_host(fse_b200_ctx *ctx, const uint8_t *h_frame, si
         if (rc) return rc;
     }
     const size_t off_pos = sizeof(FrameHeader) + pad8(h.global_header_bytes);
-    std::vector<uint64_t> off(h.nblocks + 1);
-    memcpy(off.data(), h_frame + off_pos, (h.nblocks + 1) * 8);     // the frame may be unaligned
-    if (off[h.nblocks] != h.payload_bytes) return fail(ctx, FSE_B200_ERR_ARG, "frame_decompress_host: offsets do not match payload size");
+    std::vector<uint64_t> off((size_t)h.nstreams + 1);      // bounded by the frame size (fse_b200_frame_info)
+    memcpy(off.data(), h_frame + off_pos, ((size_t)h.nstreams + 1) * 8);     // the frame may be unaligned
+    if (off[h.nstreams] != h.payload_bytes) return fail(ctx, FSE_B200_ERR_ARG, "frame_decompress_host: offsets do not match payload size");
     *h_n = n;
-    return fse_b200_decompress_host(ctx, h_frame + off_pos + (h.nblocks + 1) * 8, h.payload_bytes, off.data(), h.nblocks, &p, h_dst, n, nullptr);
+    return fse_b200_decompress_host(ctx, h_frame + off_pos + ((size_t)h.nstreams + 1) * 8, (size_t)h.payload_bytes, off.data(),
+                                    (size_t)h.nstreams, &p, h_dst, n, nullptr);
 }
 
 // ---------------------------------------------------------------------------------- generators

@@ -167,6 +167,9 @@ struct EncArgs {
     int32_t *status;
     GlobalTable g;
     int global_mode;
+    // segmented per-block mode (fse_shared_enc.cuh): a block = segs_per_block streams of seg_size bytes sharing the block's
+    // table; scratch slots, hlen, plen and status are per stream
+    uint32_t seg_size, segs_per_block;
     // fused placement (128-state kernel): blocks are handed out by a ticket counter in index order, each warp
     // publishes its block's size, obtains the sum of all earlier sizes by decoupled look-back and copies its
     // own (L2-hot) stream to its final position: no separate scan + gather pass
@@ -462,6 +465,8 @@ struct DecArgs {
     int32_t *status;
     GlobalTable g;
     int global_mode;
+    uint32_t seg_size, segs_per_block;   // segmented per-block mode: offsets / status are per stream (fse_shared_dec.cuh)
+    uint32_t dec_copies;                 // copies of the CTA-owned decode table (32 / 16 / 8)
     // exhaust mode (the reference's own termination rule, src/lib.rs:198,228: decode until the bit
     // stack cannot supply num_bits): block b may produce up to block_size bytes, out_len[b] = produced
     int exhaust;

@@ -222,7 +222,7 @@ namespace detail {
 inline size_t compress_one(const std::vector<uint8_t> &src, std::vector<uint8_t> &dst, uint32_t n_states, size_t *header_bytes)
 {
     if (src.size() < n_states || src.empty()) throw Panic("called `Option::unwrap()` on a `None` value");   // lib.rs:121,154,156
-    fse_b200_params p{(uint32_t)src.size(), 0, n_states, FSE_B200_TABLE_PER_BLOCK};
+    fse_b200_params p{(uint32_t)src.size(), 0, n_states, FSE_B200_TABLE_PER_BLOCK, 0, 0};
     size_t cap = fse_b200_compress_blocks_bound(src.size(), &p);
     size_t start = dst.size();
     dst.resize(start + cap);
@@ -246,7 +246,7 @@ inline std::optional<size_t> decompress_one(const std::vector<uint8_t> &src, std
     Dev<uint64_t> doff(off, 2);
     Dev<uint32_t> out_len(1);
     Dev<int32_t> st(1);
-    fse_b200_params p{(uint32_t)cap, 15, n_states, FSE_B200_TABLE_PER_BLOCK};
+    fse_b200_params p{(uint32_t)cap, 15, n_states, FSE_B200_TABLE_PER_BLOCK, 0, 0};
     ck(fse_b200_decompress_exhaust(ctx(), comp.p, src.size(), doff.p, 1, &p, out.p, out_len.p, st.p), "decompress_exhaust");
     int32_t rc = st.at(0);
     if (rc == FSE_B200_ERR_TABLE_LOG || rc == FSE_B200_ERR_TOO_MANY || rc == FSE_B200_ERR_IO || rc == FSE_B200_ERR_NO_MARKER)

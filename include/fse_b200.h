@@ -76,7 +76,23 @@ typedef struct {
                              value handed to Histogram::normalize (src/histogram.rs:95), 5..15 */
     uint32_t n_states;    /* interleaved states per block: 1, 2, 4, 8, 16, 32, 64 or 128 (64 / 128: table_log <= 13) */
     uint32_t table_mode;  /* FSE_B200_TABLE_PER_BLOCK or FSE_B200_TABLE_GLOBAL */
+    uint32_t segment_size; /* 0: a block is one stream (above).  > 0 (per-block tables, n_states 128, table_log <= 11,
+                             a divisor of block_size, >= 512): the block keeps ONE table and ONE header, and its bytes
+                             are coded as block_size / segment_size independent streams ("segments") against that table,
+                             each the header-less payload the crate tests at src/fse.rs:394-421 for its slice.  One
+                             CTA codes a block: its warps share one bank-replicated copy of the table in shared memory.
+                             The index then has one entry per SEGMENT (fse_b200_num_streams): stream s = block * (block_size /
+                             segment_size) + k; the first stream of a block starts with the block's header (or its
+                             escape byte, then the other streams of the block are empty); a tail segment shorter
+                             than 128 bytes is stored raw (status 1).  Wherever an entry point says "nblocks",
+                             "offsets[nblocks + 1]" or "status[nblocks]", read fse_b200_num_streams(n, p). */
+    uint32_t flags;       /* FSE_B200_FLAG_* */
 } fse_b200_params;
+
+/* A block (or segment) whose coded form would be larger than 1 + its length is stored as 0x0F + raw bytes instead
+ * (status 1).  Off by default: the reference has no such fallback (src/fse.rs:191-193 only bounds the expansion),
+ * so the default output stays byte-identical to it. */
+#define FSE_B200_FLAG_RAW_IF_EXPANDS 1u
 
 /* src/fse.rs:80-84 SymbolTransform */
 typedef struct { uint32_t bits; int32_t find_state; } fse_b200_symbol_transform;
@@ -117,6 +133,8 @@ size_t fse_b200_compress_bound(size_t size);
 /* worst-case bytes of the dense output of fse_b200_compress_blocks for n input bytes */
 size_t fse_b200_compress_blocks_bound(size_t n, const fse_b200_params *p);
 size_t fse_b200_num_blocks(size_t n, uint32_t block_size);
+/* entries of the stream index: blocks, or segments when p->segment_size > 0 */
+size_t fse_b200_num_streams(size_t n, const fse_b200_params *p);
 
 /* ---- stage entry points (device pointers) --------------------------------------------------- */
 /* Histogram::new per block, src/histogram.rs:18-66.
@@ -215,9 +233,9 @@ int fse_b200_decompress_host(fse_b200_ctx *ctx, const uint8_t *h_comp, size_t co
                              uint8_t *h_dst, size_t n, int32_t *h_status);
 
 /* ---- self-describing frame (the container the reference does not have) ------- */
-/* Layout (little endian):  "FSEB" | u16 version = 1 | u16 n_states | u32 block_size | u32 table_log |
- * u32 table_mode | u32 global_header_bytes | u64 n | u64 nblocks | u64 payload_bytes |
- * global NCount header (table_mode 1 only, padded to 8 bytes) | u64 offsets[nblocks + 1] | payload.
+/* Layout (little endian):  "FSEB" | u16 version = 2 | u16 n_states | u32 block_size | u32 table_log |
+ * u32 table_mode | u32 global_header_bytes | u64 n | u64 nstreams | u64 payload_bytes | u32 segment_size | u32 flags |
+ * global NCount header (table_mode 1 only, padded to 8 bytes) | u64 offsets[nstreams + 1] | payload.
  * Everything a decoder needs travels with the data; the payload is the dense block streams above. */
 #define FSE_B200_FRAME_MAGIC 0x42455346u /* "FSEB" */
 size_t fse_b200_frame_bound(size_t n, const fse_b200_params *p);

@@ -31,7 +31,7 @@ def test_sizing_helpers(L):
     assert L.fse_b200_compress_bound(65536) == 66572          # fse.rs:191-193
     assert L.fse_b200_num_blocks(256 << 20, 65536) == 4096
     assert L.fse_b200_num_blocks(65537, 65536) == 2
-    p = _capi.Params(65536, 0, 32, 0)
+    p = _capi.Params(65536, 0, 32, 0, 0, 0)
     assert L.fse_b200_compress_blocks_bound(1 << 20, C.byref(p)) >= 16 * 66572
     assert b"sm_100a" in L.fse_b200_version()
 

@@ -673,7 +673,7 @@ def test_frame_container(ctx):
         src = O.generate(kind, 55, n)
         frame = ctx.frame_compress(src, bs, tl, 128, mode)
         info = ctx.frame_info(frame)
-        assert info == {"block_size": bs, "table_log": tl, "n_states": 128, "table_mode": mode, "n": n}
+        assert info == {"block_size": bs, "table_log": tl, "n_states": 128, "table_mode": mode, "segment_size": 0, "flags": 0, "n": n}
         fresh = E.Context(0)                                  # nothing but the frame is needed to decode
         assert np.array_equal(fresh.frame_decompress(frame), src)
         fresh.close()
@@ -687,3 +687,157 @@ def test_frame_container(ctx):
         ctx.frame_info(bad)
     with pytest.raises(E.FseError):
         ctx.frame_info(frame[:40])
+
+
+# ------------------------------------------------------------------------------------ segmented per-block mode
+
+def oracle_segments(src, block_size, seg, table_log):
+    """Expected stream list of the segmented mode: per block ONE header (NormHistogram::new + write of the whole
+    block, src/histogram.rs:299-303,376-431) and, per segment, the header-less 128-state payload of that slice coded
+    with the block's table (the composition the crate tests at src/fse.rs:394-421).  -> (streams, statuses)"""
+    streams, status = [], []
+    for o in range(0, len(src), block_size):
+        blk = src[o:o + block_size]
+        nseg = (len(blk) + seg - 1) // seg
+        h = O.histogram(blk)
+        esc = None
+        if h.table_len <= 1:
+            esc = (bytes([0x0E, 0x00]), 2)
+        elif len(blk) <= 4 and table_log == 0:
+            esc = (bytes([0x0F]) + blk.tobytes(), 1)
+        elif len(blk) < 128:
+            esc = (bytes([0x0F]) + blk.tobytes(), 1)
+        if esc is None:
+            tl = table_log
+            if tl == 0:
+                rc, tl = O.optimal_log2(h)
+                assert rc >= 0
+            rc, nh = O.normalize(h, tl)
+            assert rc >= 0
+            header = O.ncount_write(nh)[0]
+            et = O.enc_table(nh)
+        for k in range(nseg):
+            if esc is not None:
+                streams.append(esc[0] if k == 0 else b"")
+                status.append(esc[1])
+                continue
+            sl = blk[k * seg:(k + 1) * seg]
+            if len(sl) < 128:
+                body, st = sl.tobytes(), 1
+            else:
+                body, st = O.encode_payload(et, sl, 128)[0], 0
+            streams.append((header if k == 0 else b"") + body)
+            status.append(st)
+    return streams, status
+
+
+@pytest.mark.parametrize("kind,bs,seg,tl,n", [
+    ("geo", 131072, 8192, 0, 5 * 131072),              # BASELINE config 4's shape
+    ("text", 65536, 8192, 0, 3 * 65536 + 20000),        # config 2's shape, ragged last block (3 segments, one short)
+    ("few", 65536, 4096, 11, 2 * 65536 + 4096 + 100),    # a 100-byte tail segment is stored raw
+    ("uniform", 32768, 2048, 9, 4 * 32768 + 2048 * 3 + 777),
+    ("geo", 16384, 512, 10, 16384 * 3 + 512 * 5 + 129),
+    ("text", 8192, 1024, 0, 8192 * 37 + 1),              # more blocks than SMs hold at once; a 1-byte last block (escape)
+])
+def test_segmented_blocks_bit_exact(ctx, kind, bs, seg, tl, n):
+    """segment_size > 0: one table and one header per block, its segments coded as independent 128-state streams by the
+    warps of one CTA against bank-replicated tables.  Every stream equals the oracle's composition, byte for byte."""
+    src = O.generate(kind, 0xC0FFEE04, n)
+    d, off, st, total = ctx.compress_blocks(dev(ctx, src), bs, tl, 128, segment_size=seg)
+    offh = off.cpu().numpy().astype(np.int64)
+    buf = d[:total].cpu().numpy().tobytes()
+    exp, est = oracle_segments(src, bs, seg, tl)
+    assert len(offh) - 1 == len(exp) == ctx.num_streams(n, ctx.params(bs, tl, 128, 0, seg))
+    sth = st.cpu().numpy()
+    for s_, e in enumerate(exp):
+        assert buf[offh[s_]:offh[s_ + 1]] == e, (s_, len(e), offh[s_ + 1] - offh[s_])
+        assert sth[s_] == est[s_], (s_, sth[s_], est[s_])
+    out, dst_ = ctx.decompress_blocks(d, total, off, n, bs, tl, 128, segment_size=seg)
+    assert (dst_.cpu().numpy() == np.array(est)).all()
+    assert np.array_equal(out.cpu().numpy(), src)
+
+
+def test_segmented_degenerate_blocks(ctx):
+    """blocks the reference panics on (all zero, tiny) inside a segmented stream: block-level escapes in the first stream"""
+    bs, seg = 16384, 2048
+    src = O.generate("text", 5, 6 * bs + 3)
+    src[bs:2 * bs] = 0                                      # all-zero block -> 0x0E
+    src[3 * bs:4 * bs] = 65                                 # one symbol: stays FSE (length-driven decode)
+    d, off, st, total = ctx.compress_blocks(dev(ctx, src), bs, 0, 128, segment_size=seg)
+    offh = off.cpu().numpy().astype(np.int64)
+    buf = d[:total].cpu().numpy().tobytes()
+    exp, est = oracle_segments(src, bs, seg, 0)
+    for s_, e in enumerate(exp):
+        assert buf[offh[s_]:offh[s_ + 1]] == e, s_
+    assert list(st.cpu().numpy()) == est
+    out, dst_ = ctx.decompress_blocks(d, total, off, src.size, bs, 0, 128, segment_size=seg)
+    assert (dst_.cpu().numpy() >= 0).all() and np.array_equal(out.cpu().numpy(), src)
+
+
+def test_segmented_decode_errors(ctx):
+    """corrupt segmented streams give a negative status for the streams concerned, never a crash"""
+    bs, seg = 65536, 8192
+    src = O.generate("geo", 9, 4 * bs)
+    d, off, st, total = ctx.compress_blocks(dev(ctx, src), bs, 0, 128, segment_size=seg)
+    offh = off.cpu().numpy().astype(np.int64)
+    bad = d.clone()
+    bad[int(offh[8])] = 0x3B                                # block 1 header: table_log nibble 11 + 5 > 15
+    out, dst_ = ctx.decompress_blocks(bad, total, off, src.size, bs, 0, 128, segment_size=seg)
+    s = dst_.cpu().numpy()
+    assert (s[8:16] < 0).all() and (s[:8] == 0).all() and (s[16:] == 0).all()
+    o = out.cpu().numpy()
+    assert np.array_equal(o[:bs], src[:bs]) and np.array_equal(o[2 * bs:], src[2 * bs:])
+    bad = d.clone()
+    bad[int(offh[20]) - 1] = 0                              # stream 19 loses its marker byte
+    out, dst_ = ctx.decompress_blocks(bad, total, off, src.size, bs, 0, 128, segment_size=seg)
+    s = dst_.cpu().numpy()
+    assert s[19] < 0 and (np.delete(s, 19) == 0).all()
+
+
+def test_segmented_host_and_frame(ctx):
+    """the host-buffer entry points and the frame carry segment_size"""
+    import entropy_coders_b200 as E
+    bs, seg = 131072, 8192
+    src = O.generate("geo", 77, 70 * bs + 12345)            # > 64 MiB? no: 9 MiB, one chunk; the pipelined path is in test_full_size
+    dst, off, st, total = ctx.compress_host(src, bs, 0, 128, segment_size=seg)
+    exp, est = oracle_segments(src, bs, seg, 0)
+    assert total == sum(len(e) for e in exp) and dst[:total].tobytes() == b"".join(exp)
+    out, st2 = ctx.decompress_host(dst, total, off, src.size, bs, 0, 128, segment_size=seg)
+    assert np.array_equal(out, src) and (st2 >= 0).all()
+    frame = ctx.frame_compress(src, bs, 0, 128, segment_size=seg)
+    assert ctx.frame_info(frame)["segment_size"] == seg
+    fresh = E.Context(0)
+    assert np.array_equal(fresh.frame_decompress(frame), src)
+    fresh.close()
+
+
+def test_frame_forged_headers(ctx):
+    """every size in a frame header is untrusted; forged values must be rejected, not wrapped"""
+    import struct
+    import entropy_coders_b200 as E
+    src = O.generate("text", 3, 200000)
+    frame = ctx.frame_compress(src, 65536, 0, 128)
+    hdr = bytearray(frame[:56].tobytes())
+    def forged(**kw):
+        f = list(struct.unpack("<IHHIIIIQQQII", bytes(hdr)))
+        names = ["magic", "version", "n_states", "block_size", "table_log", "table_mode", "ghb", "n", "nstreams", "payload", "seg", "flags"]
+        for k, v in kw.items():
+            f[names.index(k)] = v
+        out = frame.copy()
+        out[:56] = np.frombuffer(struct.pack("<IHHIIIIQQQII", *f), dtype=np.uint8)
+        return out
+    for kw in (dict(payload=2 ** 64 - 8), dict(payload=2 ** 63), dict(block_size=1, n=2 ** 61, nstreams=2 ** 61),
+               dict(nstreams=2 ** 61 - 1), dict(n_states=3), dict(n_states=256), dict(table_log=16), dict(table_mode=7),
+               dict(ghb=400), dict(seg=100), dict(flags=0x80), dict(n=2 ** 63), dict(version=1)):
+        with pytest.raises(E.FseError):
+            ctx.frame_info(forged(**kw))
+        with pytest.raises(E.FseError):
+            ctx.frame_decompress(forged(**kw))
+    # a flipped payload byte: the frame parses, a block fails, and that is an exception, not silent garbage
+    bad = frame.copy()
+    pay0 = len(frame) - int(struct.unpack("<Q", bytes(hdr[40:48]))[0])
+    bad[pay0] = 0x3F
+    with pytest.raises(E.FseError):
+        ctx.frame_decompress(bad)
+    with pytest.raises(E.FseError):
+        ctx.frame_decompress(frame[:len(frame) - 1000])      # truncated
