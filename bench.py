@@ -50,8 +50,18 @@ WORKLOADS = {
                desc="8 GiB skewed bytes, 128 KiB blocks, one global table via histogram all-reduce, block-range sharded"),
 }
 N_STATES = 128
-KERNEL_NAMES = {"hist": "k_hist_blocks16", "encode": "k_encode128_blocks", "decode": "k_decode128c_blocks",
-                "scan": "k_scan_sizes", "gather": "k_gather"}
+SEGMENT_SIZE = 0          # > 0: code every block as block_size / SEGMENT_SIZE independent 128-state streams (fse_shared_enc.cuh); measured slower
+
+
+def kernel_names(tmode, seg):
+    """the kernels behind the timed spans (fse_b200.cu dispatch at n_states 128, table_log <= 11)"""
+    if tmode == 1:
+        enc, dec = "k_encode_sh_global", "k_decode_sh_global"          # CTA-owned bank-replicated tables
+    elif seg:
+        enc, dec = "k_encode_sh_blocks", "k_decode_sh_blocks"
+    else:
+        enc, dec = "k_encode128_blocks", "k_decode128c_blocks"         # one private table set per warp
+    return {"hist": "k_hist_blocks16", "encode": enc, "decode": dec, "scan": "k_scan_sizes", "gather": "k_gather"}
 
 
 def peaks():
@@ -309,8 +319,11 @@ class Job:
         self.nbytes, self.first = nbytes, first
         dev = env["dev"]
         self.src = ctx.generate(w["kind"], w["seed"], nbytes, first_index=first)
-        self.p = ctx.params(bs, w["tlog"], N_STATES, w["tmode"])
-        self.nb = ctx.num_blocks(nbytes, bs)
+        self.seg = int(env.get("segment_size", 0)) if w["tmode"] == 0 else 0
+        if self.seg and bs % self.seg:
+            self.seg = 0
+        self.p = ctx.params(bs, w["tlog"], N_STATES, w["tmode"], self.seg)
+        self.nb = ctx.num_streams(nbytes, self.p)
         self.cap = ctx.bound(nbytes, self.p)
         self.dst = torch.empty(self.cap, dtype=torch.uint8, device=dev)
         self.offsets = torch.empty(self.nb + 1, dtype=torch.int64, device=dev)
@@ -427,7 +440,7 @@ def measure(env, job, steps, warmup, sample_clocks=False):
         "encode_GBps": job.nbytes / (enc_ms * 1e-3) / 1e9, "decode_GBps": job.nbytes / (dec_ms * 1e-3) / 1e9,
         "compressed_ratio": total_all / job.total_bytes, "compressed_bytes_rank0": total,
         "kernel_ms_per_step": {k: tm[k][0] / steps for k in tm},
-        "roofline": {"bound": "hbm", "kernel": KERNEL_NAMES[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": kernel_names(job.w["tmode"], job.seg)[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": dom_ms,
                      "direction_frac": {"encode": (job.nbytes + total) / (enc_ms * 1e-3) / 1e9 / peak,
@@ -459,8 +472,8 @@ def e2e_leg(env, job, steps):
     tot = offs = None
 
     def e2e_step():
-        _, o, st, t = ctx2.compress_host(hsrc, w["bs"], w["tlog"], N_STATES, w["tmode"], dst=hdst)
-        ctx2.decompress_host(hdst, t, o, sample, w["bs"], w["tlog"], N_STATES, w["tmode"], dst=hout)
+        _, o, st, t = ctx2.compress_host(hsrc, w["bs"], w["tlog"], N_STATES, w["tmode"], dst=hdst, segment_size=job.seg)
+        ctx2.decompress_host(hdst, t, o, sample, w["bs"], w["tlog"], N_STATES, w["tmode"], dst=hout, segment_size=job.seg)
         return t, o
     for _ in range(2):
         e2e_step()
@@ -475,7 +488,7 @@ def e2e_leg(env, job, steps):
     if env["world"] > 1:
         torch.distributed.all_reduce(te, op=torch.distributed.ReduceOp.MAX)
     e2e_s = float(te.item()) / ksteps
-    snb = (sample + w["bs"] - 1) // w["bs"]
+    snb = (sample + (job.seg or w["bs"]) - 1) // (job.seg or w["bs"])
     res = {"value": env["world"] * sample / e2e_s / 1e9 if w["scaling"] == "weak" or sample != nbytes
            else job.total_bytes / e2e_s / 1e9,
            "unit": "GB/s", "h2d_bytes_per_step": int(sample + tot + (snb + 1) * 8),
@@ -500,6 +513,7 @@ def traffic_probe(wl, tlog, dom_kernel):
            sys.executable, os.path.abspath(__file__), "--probe", "--workload", wl]
     if tlog is not None:
         cmd += ["--table-log", str(tlog)]
+    cmd += ["--segment-size", str(SEGMENT_SIZE)]
     try:
         subprocess.run(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=420, check=True)
         import csv
@@ -550,7 +564,7 @@ def make_env():
     torch.cuda.set_stream(stream)
     side = torch.cuda.Stream(device=dev)
     ctx = E.Context(local, stream=stream.cuda_stream)
-    return {"world": world, "rank": rank, "local": local, "dev": dev, "stream": stream, "side": side, "ctx": ctx}
+    return {"segment_size": SEGMENT_SIZE, "world": world, "rank": rank, "local": local, "dev": dev, "stream": stream, "side": side, "ctx": ctx}
 
 
 def run_probe(args, wl):
@@ -615,7 +629,7 @@ def run_ours(args, wl):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": m["ms_per_step"], "higher_is_better": True,
             "scaling": w["scaling"], "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": wl + ": " + w["desc"], "total_bytes": job.total_bytes, "bytes_per_gpu": job.nbytes,
-                       "block_size": w["bs"], "blocks_per_gpu": job.nb, "n_states": N_STATES,
+                       "block_size": w["bs"], "blocks_per_gpu": job.nb, "n_states": N_STATES, "segment_size": job.seg,
                        "table_log": w["tlog"] or "optimal_log2 (11)", "table_mode": "global" if w["tmode"] else "per-block",
                        "sharding": "rank g owns blocks [g*B/N, (g+1)*B/N) of the one logical stream",
                        "l2": "inputs (%d MiB per GPU) larger than L2 (126 MB); no flush" % (job.nbytes >> 20)},
@@ -641,7 +655,12 @@ def main():
     ap.add_argument("--no-configs", action="store_true")
     ap.add_argument("--no-traffic", action="store_true")
     ap.add_argument("--probe", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--segment-size", type=int, default=None,
+                    help="bytes per independently coded segment of a block (per-block tables); 0 = one stream per block")
     args = ap.parse_args()
+    global SEGMENT_SIZE
+    if args.segment_size is not None:
+        SEGMENT_SIZE = args.segment_size
     if args.impl == "reference":
         run_reference(args, args.workload)
     elif args.workload == "c1":

@@ -393,6 +393,9 @@ __device__ __forceinline__ void sh_build_enc_block(const EncArgs &a, uint32_t b,
         if (lane == 0) bs[0] = 0x0F;
         hl = 1 + bn; kind = 1;
     } else if (log2 > a.tlmax || log2 > SH_TL_MAX) kind = ST_UNSUPPORTED;
+#if defined(FSE_DIAG_SKIPBUILD)                               /* timing experiment: tables of the CTA's first block for all its blocks */
+    if (b != (uint32_t)(((unsigned long long)a.nblocks * blockIdx.x) / gridDim.x)) { if (lane == 0) { meta->hl = 27; meta->kind = 0; } __syncwarp(); return; }
+#endif
     if (rc >= 0 && kind == 0) {
         const uint32_t hbits = warp_ncount_write(norm, log2, table_len, rows, reinterpret_cast<uint32_t *>(bs), lane);
         hl = (hbits + 7) >> 3;
