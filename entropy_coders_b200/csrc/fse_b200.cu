@@ -157,6 +157,8 @@ int check_params(fse_b200_ctx *ctx, const fse_b200_params *p)
         if (p->table_log > SH_TL_MAX) return fail(ctx, FSE_B200_ERR_UNSUPPORTED, "segment_size needs table_log <= 11");
     }
     if (p->flags & ~FSE_B200_FLAG_RAW_IF_EXPANDS) return fail(ctx, FSE_B200_ERR_ARG, "unknown flags");
+    if (p->flags && (p->segment_size || p->table_mode != FSE_B200_TABLE_PER_BLOCK))
+        return fail(ctx, FSE_B200_ERR_ARG, "FSE_B200_FLAG_RAW_IF_EXPANDS needs per-block tables and one stream per block");
     return 0;
 }
 
@@ -574,6 +576,7 @@ int fse_b200_compress_blocks_async(fse_b200_ctx *ctx, const uint8_t *d_src, size
     a.scratch = ctx->scratch.as<uint8_t>(); a.stride = stride;
     a.pay_cap_words = (uint32_t)(pay_cap_bytes((uint32_t)stream_bytes(p), p->n_states) / 4);
     a.seg_size = p->segment_size; a.segs_per_block = p->segment_size ? p->block_size / p->segment_size : 1;
+    a.flags = p->flags;
     a.hlen = ctx->hlen.as<uint32_t>(); a.plen = ctx->plen.as<uint32_t>(); a.status = d_status;
     a.global_mode = global ? 1 : 0;
     a.g.log2 = ctx->g_log2; a.g.table_len = ctx->g_table_len;
@@ -584,27 +587,9 @@ int fse_b200_compress_blocks_async(fse_b200_ctx *ctx, const uint8_t *d_src, size
     int wpc = pick_warps(nb, ctx->num_sms, per_warp, ctx->smem_optin, 16);
     if (p->n_states == 128) wpc = (int)std::min<size_t>(16, (ctx->smem_optin - 64) / per_warp);   // balanced CTA queues: no wave quantisation
     if (wpc < 1) return fail(ctx, FSE_B200_ERR_UNSUPPORTED, "table_log too large for shared memory");
-    if (const char *o = getenv("FSE_B200_ENC_WPC")) wpc = std::max(1, std::min(wpc, atoi(o)));   // development override
+    wpc = std::max(1, std::min(wpc, dev_opt("FSE_B200_ENC_WPC", wpc)));
     int grid = (int)std::min<size_t>((nb + wpc - 1) / wpc, (size_t)ctx->num_sms);
     if (p->n_states == 128) grid = (int)std::min<size_t>(nb, (size_t)ctx->num_sms);
-    a.fused = 0; a.desc = nullptr; a.ticket = nullptr; a.dst = d_dst;
-    a.offsets = reinterpret_cast<unsigned long long *>(d_offsets);
-    const char *fz = getenv("FSE_B200_FUSED");               // development switch, default off
-    if (p->n_states == 128 && fz && fz[0] == '1') {
-        // fused placement: ticketed blocks + decoupled look-back inside the encode kernel; a block only ever
-        // waits for blocks that were handed out before it.  Measured SLOWER than scan + gather (c2: 0.86 ms
-        // against 0.51 + 0.12 ms): every block has to wait for all earlier blocks of its wave, so the copies
-        // are not hidden behind encoding.  Kept as an experiment, off by default.
-        CK(ctx->misc.reserve(nb * 8 + 16));
-        CK(cudaMemsetAsync(ctx->misc.p, 0, nb * 8 + 16, ctx->stream));
-        a.fused = 1;
-        a.desc = ctx->misc.as<unsigned long long>() + 2;
-        a.ticket = ctx->misc.as<unsigned int>();
-        Timed t(ctx, FSE_B200_K_ENCODE);
-        k_encode128_blocks<<<grid, wpc * 32, (size_t)wpc * per_warp, ctx->stream>>>(a);
-        CK(cudaGetLastError());
-        return FSE_B200_OK;
-    }
     if (p->segment_size) {
         // one table per block, its segments coded by the warps of one CTA against bank-replicated tables
         if (tlmax > SH_TL_MAX) return fail(ctx, FSE_B200_ERR_UNSUPPORTED, "segment_size needs table_log <= 11");
@@ -714,15 +699,14 @@ int fse_b200_decompress_blocks_async(fse_b200_ctx *ctx, const uint8_t *d_comp, s
     if (p->n_states == 128) {
         if (tlmax > 13) return fail(ctx, FSE_B200_ERR_UNSUPPORTED, "n_states 128 needs table_log <= 13");
         const size_t half = ctx->smem_per_sm / 2 - 1024;
-        const char *dv = getenv("FSE_B200_DECODE128");          // development switch: "c" compact tables, "w" wide entries
-        const bool compact = tlmax <= 12 && !(dv && dv[0] == 'w');
+        const bool compact = tlmax <= 12 && !dev_opt("FSE_B200_DECODE128_WIDE", 0);
         const size_t per_warp = compact ? dec64c_layout(tlmax).total : dec64w_layout(tlmax).total;
         // balanced CTA queues (every CTA gets nblocks / grid blocks): take every warp that fits, two CTAs per SM
         int wpc = (int)std::min<size_t>(16, (std::min(half, ctx->smem_optin) - 64) / per_warp);
         int ctas = 2;
         if (wpc < 1) { wpc = (int)std::min<size_t>(16, (ctx->smem_optin - 64) / per_warp); ctas = 1; }
         if (wpc < 1) return fail(ctx, FSE_B200_ERR_UNSUPPORTED, "table_log too large for shared memory");
-        if (const char *o = getenv("FSE_B200_WPC")) wpc = std::max(1, std::min(wpc, atoi(o)));   // development override
+        wpc = std::max(1, std::min(wpc, dev_opt("FSE_B200_WPC", wpc)));
         int grid = (int)std::min<size_t>(nblocks, (size_t)ctx->num_sms * ctas);
         Timed t(ctx, FSE_B200_K_DECODE);
         if (compact) k_decode128c_blocks<<<grid, wpc * 32, (size_t)wpc * per_warp, ctx->stream>>>(a);
@@ -730,8 +714,7 @@ int fse_b200_decompress_blocks_async(fse_b200_ctx *ctx, const uint8_t *d_comp, s
         CK(cudaGetLastError());
         return FSE_B200_OK;
     }
-    const char *variant = getenv("FSE_B200_DECODE64");      // development switch: "c" compact, "w" wide entries
-    const bool use_wide = variant ? variant[0] == 'w' : false;   // measured: compact 0.49 ms vs wide 0.70 ms on c2
+    const bool use_wide = dev_opt("FSE_B200_DECODE64_WIDE", 0) != 0;   // measured: compact 0.49 ms vs wide 0.70 ms on c2
     if (p->n_states == 64 && (tlmax <= 12 || use_wide)) {
         // two CTAs per SM, each with half of the SM's shared memory
         const size_t half = ctx->smem_per_sm / 2 - 1024;            // 1 KiB per CTA is reserved by the runtime

@@ -271,63 +271,6 @@ __device__ void encode128_payload_warp(const uint8_t *__restrict__ bsrc, uint32_
     bits_out = wdone * 32 + cb;
 }
 
-// warp-level byte copy with 4-byte aligned destination stores (src is 4-byte aligned)
-__device__ __forceinline__ void warp_copy_bytes(uint8_t *dst, const uint8_t *src, uint32_t len, int lane)
-{
-    uint32_t head = (uint32_t)((4 - ((uintptr_t)dst & 3)) & 3);
-    if (head > len) head = len;
-    if ((uint32_t)lane < head) dst[lane] = src[lane];
-    const uint32_t nwords = (len - head) >> 2;
-    const uint32_t *sw = reinterpret_cast<const uint32_t *>(src);
-    uint32_t *dw = reinterpret_cast<uint32_t *>(dst + head);
-    const uint32_t sh = head * 8;
-    for (uint32_t k = lane; k < nwords; k += 32) {
-        uint32_t w0 = sw[k], w1 = sh ? sw[k + 1] : 0u;
-        dw[k] = __funnelshift_r(w0, w1, sh);
-    }
-    const uint32_t t0 = head + (nwords << 2);
-    if (t0 + lane < len) dst[t0 + lane] = src[t0 + lane];
-}
-
-__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p)
-{
-    unsigned long long v;
-    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ void st_volatile_u64(unsigned long long *p, unsigned long long v)
-{
-    asm volatile("st.volatile.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
-}
-
-// Sum of the sizes of all blocks before b (decoupled look-back over the descriptor array).  Every earlier
-// block was handed out before b (ticket order), so its owner is running and will publish.
-__device__ __forceinline__ unsigned long long lookback_exclusive(unsigned long long *desc, uint32_t b, int lane, unsigned int *err)
-{
-    unsigned long long excl = 0;
-    long long j = (long long)b - 1;
-    uint32_t polls = 0;
-    while (j >= 0) {
-        const long long idx = j - lane;
-        unsigned long long d;
-        for (;;) {
-            d = idx >= 0 ? ld_volatile_u64(desc + idx) : 2ull;           // before block 0: prefix 0
-            if (!__any_sync(FULL, (d & 3) == 0)) break;
-            if (++polls > (1u << 22)) { if (lane == 0) atomicExch(err, 1u); return excl; }   // never hang the GPU
-            __nanosleep(64);
-        }
-        const uint32_t pm = __ballot_sync(FULL, (d & 3) == 2);
-        const int upto = pm ? (__ffs((int)pm) - 1) : 31;
-        unsigned long long v = lane <= upto ? (d >> 2) : 0ull;
-#pragma unroll
-        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-        excl += v;
-        if (pm) break;
-        j -= 32;
-    }
-    return excl;
-}
-
 __global__ void __launch_bounds__(512) k_encode128_blocks(EncArgs a)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -362,13 +305,12 @@ __global__ void __launch_bounds__(512) k_encode128_blocks(EncArgs a)
     // the warps take the next block from a shared counter
     __shared__ uint32_t cta_next;
     const uint32_t cta_first = (uint32_t)(((unsigned long long)a.nblocks * blockIdx.x) / gridDim.x);
-    const uint32_t cta_last = a.fused ? a.nblocks : (uint32_t)(((unsigned long long)a.nblocks * (blockIdx.x + 1)) / gridDim.x);
+    const uint32_t cta_last = (uint32_t)(((unsigned long long)a.nblocks * (blockIdx.x + 1)) / gridDim.x);
     if (threadIdx.x == 0) cta_next = cta_first;
     __syncthreads();
     for (;;) {
         uint32_t b = 0;
-        if (lane == 0) b = a.fused ? atomicAdd(a.ticket, 1u)     // fused placement: global index order
-                                   : atomicAdd(&cta_next, 1u);
+        if (lane == 0) b = atomicAdd(&cta_next, 1u);
         b = __shfl_sync(FULL, b, 0);
         if (b >= cta_last) break;
         const size_t off = (size_t)b * a.block_size;
@@ -450,25 +392,14 @@ __global__ void __launch_bounds__(512) k_encode128_blocks(EncArgs a)
                 encode128_payload_warp<0>(bsrc, bn, log2, et, fld, rows, pay, a.pay_cap_words, lane, pbits, ovf);
             }
             if (ovf) { st = ST_CAPACITY; hl = 0; pl = 0; }
-            else pl = (pbits + 7) >> 3;
+            else {
+                pl = (pbits + 7) >> 3;
+                if (!a.global_mode && warp_raw_if_expands(a.flags, hl, pl, bs, bsrc, bn, lane)) { hl = 1; pl = bn; st = 1; }
+            }
         } while (0);
         __syncwarp();
         if (lane == 0) a.status[b] = st;
-        if (!a.fused) {
-            if (lane == 0) { a.hlen[b] = hl; a.plen[b] = pl; }
-            continue;
-        }
-        const unsigned long long size = (unsigned long long)hl + pl;
-        if (lane == 0) st_volatile_u64(a.desc + b, (size << 2) | 1ull);
-        const unsigned long long excl = lookback_exclusive(a.desc, b, lane, a.ticket + 1);
-        if (lane == 0) {
-            st_volatile_u64(a.desc + b, ((excl + size) << 2) | 2ull);
-            a.offsets[b] = excl;
-            if (b == a.nblocks - 1) a.offsets[a.nblocks] = excl + size;
-        }
-        __syncwarp();
-        warp_copy_bytes(a.dst + excl, bs, hl, lane);
-        warp_copy_bytes(a.dst + excl + hl, bs + HDR_RESERVE, pl, lane);
+        if (lane == 0) { a.hlen[b] = hl; a.plen[b] = pl; }
     }
 }
 

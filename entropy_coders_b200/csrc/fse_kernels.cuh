@@ -170,15 +170,20 @@ struct EncArgs {
     // segmented per-block mode (fse_shared_enc.cuh): a block = segs_per_block streams of seg_size bytes sharing the block's
     // table; scratch slots, hlen, plen and status are per stream
     uint32_t seg_size, segs_per_block;
-    // fused placement (128-state kernel): blocks are handed out by a ticket counter in index order, each warp
-    // publishes its block's size, obtains the sum of all earlier sizes by decoupled look-back and copies its
-    // own (L2-hot) stream to its final position: no separate scan + gather pass
-    int fused;
-    unsigned long long *desc;     // [nblocks], zeroed: value << 2 | status (1 = own size, 2 = inclusive prefix)
-    unsigned int *ticket;         // zeroed; ticket[1] is an error flag (look-back gave up)
-    uint8_t *dst;
-    unsigned long long *offsets;  // [nblocks + 1]
+    uint32_t flags;          // FSE_B200_FLAG_* (per-block tables, one stream per block)
 };
+
+// FSE_B200_FLAG_RAW_IF_EXPANDS: a block whose header + payload would not be smaller than 1 + its length is stored as
+// 0x0F + raw bytes.  The reference has no such fallback (fse.rs:191-193 only bounds the expansion), so
+// this only runs when the caller asks for it.  Returns true when the block was replaced (hl = 1, pl = bn, status 1).
+__device__ __forceinline__ bool warp_raw_if_expands(uint32_t flags, uint32_t hl, uint32_t pl, uint8_t *bs, const uint8_t *__restrict__ bsrc,
+                                                    uint32_t bn, int lane)
+{
+    if (!(flags & 1u) || hl + pl < 1 + bn) return false;
+    for (uint32_t i = lane; i < bn; i += 32) bs[512 + i] = bsrc[i];      // the payload area starts at HDR_RESERVE
+    if (lane == 0) bs[0] = 0x0F;
+    return true;
+}
 
 // fse.rs:210-218
 __device__ __forceinline__ uint32_t enc_first(const uint16_t *tab, const uint2 *tt, uint32_t sym)
@@ -353,9 +358,11 @@ __global__ void __launch_bounds__(512) k_encode_blocks(EncArgs a)
         bool ovf;
         encode_payload_warp(bsrc, bn, N, log2, tab, tt, fld, rows, pay, a.pay_cap_words, lane, pbits, ovf);
         if (ovf) st = ST_CAPACITY;
+        uint32_t hl = ovf ? 0 : hbytes, pl = ovf ? 0 : (pbits + 7) >> 3;
+        if (!ovf && !a.global_mode && warp_raw_if_expands(a.flags, hl, pl, bs, bsrc, bn, lane)) { hl = 1; pl = bn; st = 1; }
         if (lane == 0) {
-            a.hlen[b] = ovf ? 0 : hbytes;
-            a.plen[b] = ovf ? 0 : (pbits + 7) >> 3;
+            a.hlen[b] = hl;
+            a.plen[b] = pl;
             a.status[b] = st;
         }
     }

@@ -266,9 +266,11 @@ __global__ void __launch_bounds__(512) k_encode64_blocks(EncArgs a)
         bool ovf;
         encode64_payload_warp(bsrc, bn, log2, tab_saddr, tt_saddr, fld, rows, pay, a.pay_cap_words, lane, pbits, ovf);
         if (ovf) st = ST_CAPACITY;
+        uint32_t hl = ovf ? 0 : hbytes, pl = ovf ? 0 : (pbits + 7) >> 3;
+        if (!ovf && !a.global_mode && warp_raw_if_expands(a.flags, hl, pl, bs, bsrc, bn, lane)) { hl = 1; pl = bn; st = 1; }
         if (lane == 0) {
-            a.hlen[b] = ovf ? 0 : hbytes;
-            a.plen[b] = ovf ? 0 : (pbits + 7) >> 3;
+            a.hlen[b] = hl;
+            a.plen[b] = pl;
             a.status[b] = st;
         }
     }

@@ -841,3 +841,119 @@ def test_frame_forged_headers(ctx):
         ctx.frame_decompress(bad)
     with pytest.raises(E.FseError):
         ctx.frame_decompress(frame[:len(frame) - 1000])      # truncated
+
+
+# ------------------------------------------------------------------------------------ full-size runs at the bench's parameters
+
+def _full_size(ctx, kind, seed, n, bs, tl, mode, sample_blocks, ratio_range, segment_size=0):
+    """BASELINE.json shapes at the state count bench.py uses (128): round trip, index consistency, a checksum of the
+    decoded bytes against the generator, and a sample of blocks byte-exact against the oracle"""
+    import torch
+    src = ctx.generate(kind, seed, n)
+    header = None
+    if mode == 1:
+        header, log2 = ctx.set_global_table(ctx.histogram_global(src), tl)
+        nh = O.ncount_read(header)[1]
+        et = O.enc_table(nh)
+    d, off, st, total = ctx.compress_blocks(src, bs, tl, 128, table_mode=mode, segment_size=segment_size)
+    assert not st.cpu().numpy().any()
+    offh = off.cpu().numpy()
+    assert offh[0] == 0 and offh[-1] == total and (np.diff(offh) > 0).all()
+    assert ratio_range[0] < total / n < ratio_range[1], total / n
+    out, dst_ = ctx.decompress_blocks(d, total, off, n, bs, tl, 128, table_mode=mode, segment_size=segment_size)
+    assert not dst_.cpu().numpy().any()
+    assert torch.equal(out, src)
+    for b in sample_blocks:
+        blk = src[b * bs:(b + 1) * bs].cpu().numpy()
+        assert np.array_equal(blk, O.generate(kind, seed, bs, first_index=b * bs))       # device generator == oracle generator
+        got = d[offh[b]:offh[b + 1]].cpu().numpy().tobytes() if not segment_size else None
+        if mode == 1:
+            assert got == O.encode_payload(et, blk, 128)[0], b
+        elif not segment_size:
+            assert got == O.compress_n(blk, tl, 128)[0], b
+    del src, d, out
+    torch.cuda.empty_cache()
+
+
+def test_full_size_c2_n128(ctx):
+    """config 2: 256 MiB text-like, 64 KiB blocks (4 096), optimal_log2, 128 states"""
+    _full_size(ctx, "text", 0xC0FFEE02, 256 << 20, 65536, 0, 0, (0, 1, 777, 2047, 4095), (0.60, 0.72))
+
+
+@pytest.mark.parametrize("kind,tl,rng", [("few", 9, (0.05, 0.12)), ("few", 11, (0.05, 0.12)), ("few", 12, (0.05, 0.12)),
+                                         ("uniform", 9, (1.0, 1.02)), ("uniform", 11, (1.0, 1.02)), ("uniform", 12, (1.0, 1.02))])
+def test_full_size_c3_n128(ctx, kind, tl, rng):
+    """config 3: 1 GiB few-symbol / uniform, 64 KiB blocks (16 384), table_log 9 / 11 / 12, 128 states"""
+    _full_size(ctx, kind, 0xC0FFEE03, 1 << 30, 65536, tl, 0, (0, 5, 8191, 16383), rng)
+
+
+def test_full_size_c4_n128(ctx):
+    """config 4's shape: geometric bytes, 128 KiB blocks, 16 384 of them (2 GiB), 128 states"""
+    _full_size(ctx, "geo", 0xC0FFEE04, 2 << 30, 131072, 0, 0, (0, 3, 9999, 16383), (0.44, 0.47))
+
+
+def test_full_size_c5_global_n128(ctx):
+    """config 5's shape on one GPU: one table from the whole-buffer histogram, 16 384 header-less 128 KiB blocks"""
+    _full_size(ctx, "geo", 0xC0FFEE05, 2 << 30, 131072, 11, 1, (0, 4, 8000, 16383), (0.44, 0.47))
+
+
+def test_full_size_c4_segmented(ctx):
+    """the segmented per-block mode at config 4's shape (8 KiB segments, 16 per block)"""
+    _full_size(ctx, "geo", 0xC0FFEE04, 1 << 30, 131072, 0, 0, (0, 8191), (0.45, 0.49), segment_size=8192)
+
+
+@pytest.mark.parametrize("kind,tl,bs", [("text", 9, 30000), ("uniform", 10, 16384), ("few", 5, 4096), ("geo", 11, 131072), ("text", 0, 65536)])
+def test_global_table_sweep(ctx, kind, tl, bs):
+    """CTA-owned bank-replicated tables (global mode): table_log 5..11 (32 copies up to 10, 16 at 11), ragged blocks,
+    every block byte-exact against the oracle's header-less 128-state stream"""
+    n = 23 * bs + 1000
+    src = O.generate(kind, 0xC0FFEE05, n)
+    dsrc = dev(ctx, src)
+    header, log2 = ctx.set_global_table(ctx.histogram_global(dsrc), tl)
+    h = O.histogram(src)
+    if tl == 0:
+        rc, tl_eff = O.optimal_log2(h)
+        assert rc >= 0
+    else:
+        tl_eff = tl
+    rc, nh = O.normalize(h, tl_eff)
+    assert rc >= 0 and log2 == nh.log2 and header == O.ncount_write(nh)[0]
+    d, off, st, total = ctx.compress_blocks(dsrc, bs, tl, 128, table_mode=1)
+    offh = off.cpu().numpy()
+    buf = d[:total].cpu().numpy().tobytes()
+    et = O.enc_table(nh)
+    for b in range(len(offh) - 1):
+        blk = src[b * bs:(b + 1) * bs]
+        exp = blk.tobytes() if len(blk) < 128 else O.encode_payload(et, blk, 128)[0]
+        assert buf[offh[b]:offh[b + 1]] == exp, b
+    out, dst_ = ctx.decompress_blocks(d, total, off, n, bs, tl, 128, table_mode=1)
+    assert (dst_.cpu().numpy() >= 0).all() and np.array_equal(out.cpu().numpy(), src)
+    # unaligned source and destination
+    d2, off2, st2, total2 = ctx.compress_blocks(dsrc[3:], bs, tl, 128, table_mode=1)
+    out2, dst2 = ctx.decompress_blocks(d2, total2, off2, n - 3, bs, tl, 128, table_mode=1)
+    assert (dst2.cpu().numpy() >= 0).all() and np.array_equal(out2.cpu().numpy(), src[3:])
+
+
+@pytest.mark.parametrize("n_states", [2, 32, 64, 128])
+def test_raw_if_expands(ctx, n_states):
+    """SURVEY 8f (f2), opt-in: a block whose coded form is not smaller than 1 + its length is stored 0x0F + raw.  Without
+    the flag the output stays the reference's (expanding) stream; compressible data is unaffected by the flag."""
+    import entropy_coders_b200 as E
+    bs = 65536
+    uni = O.generate("uniform", 1, 6 * bs + 1000)
+    d0, off0, st0, tot0 = ctx.compress_blocks(dev(ctx, uni), bs, 0, n_states)
+    d1, off1, st1, tot1 = ctx.compress_blocks(dev(ctx, uni), bs, 0, n_states, flags=E.FLAG_RAW_IF_EXPANDS)
+    assert tot0 > uni.size and not st0.cpu().numpy().any()           # the reference expands uniform bytes
+    o1 = off1.cpu().numpy()
+    assert (st1.cpu().numpy() == 1).all() and tot1 == uni.size + len(o1) - 1
+    buf = d1[:tot1].cpu().numpy().tobytes()
+    for b in range(len(o1) - 1):
+        assert buf[o1[b]:o1[b + 1]] == bytes([0x0F]) + uni[b * bs:(b + 1) * bs].tobytes()
+    out, dst_ = ctx.decompress_blocks(d1, tot1, off1, uni.size, bs, 0, n_states, flags=E.FLAG_RAW_IF_EXPANDS)
+    assert np.array_equal(out.cpu().numpy(), uni)
+    out, dst_ = ctx.decompress_blocks(d1, tot1, off1, uni.size, bs, 0, n_states)    # the decoder needs no flag
+    assert np.array_equal(out.cpu().numpy(), uni)
+    txt = O.generate("text", 2, 3 * bs)
+    a = ctx.compress_blocks(dev(ctx, txt), bs, 0, n_states)
+    b_ = ctx.compress_blocks(dev(ctx, txt), bs, 0, n_states, flags=E.FLAG_RAW_IF_EXPANDS)
+    assert a[3] == b_[3] and a[0][:a[3]].cpu().numpy().tobytes() == b_[0][:b_[3]].cpu().numpy().tobytes()
