@@ -183,6 +183,36 @@ class Context:
         self._ck(self._L.fse_b200_build_decode_tables(self._h, _ptr(norm), _ptr(log2), _ptr(tlen), nt, max_table_log, _ptr(table), _ptr(st)))
         return table, st
 
+    # ------------------------------------------------------------------ bit I/O primitives (src/bitstream)
+    def bitstack_write(self, vals, bits, mark=True):
+        """BitStackWriter: fields (vals[i] masked to bits[i] <= 16 bits) LSB first in index order (+ marker) -> (bytes, bit count)"""
+        torch = _torch()
+        n = int(vals.numel())
+        cap = (int(bits.sum().item()) + 64) // 8 + 8 if n else 16
+        cap = (cap + 3) & ~3
+        out = torch.zeros(cap, dtype=torch.uint8, device=self.device)
+        nbits = C.c_uint64()
+        self._ck(self._L.fse_b200_bitstack_write(self._h, _ptr(vals), _ptr(bits), n, 1 if mark else 0, _ptr(out), cap, C.byref(nbits)))
+        return out[: (nbits.value + 7) // 8], int(nbits.value)
+
+    def bitstack_read(self, data, bits):
+        """BitStackReader: the fields back in index order (read from the end) -> (vals, status)"""
+        torch = _torch()
+        n = int(bits.numel())
+        vals = torch.zeros(max(n, 1), dtype=torch.int32, device=self.device)
+        st = C.c_int32()
+        self._ck(self._L.fse_b200_bitstack_read(self._h, _ptr(data), int(data.numel()), _ptr(bits), n, _ptr(vals), C.byref(st)))
+        return vals[:n], int(st.value)
+
+    def bitstream_read(self, data, total_bits, bits):
+        """BitStreamReader: forward reads under a total_bits bound -> (vals, status: bits left or a negative code)"""
+        torch = _torch()
+        n = int(bits.numel())
+        vals = torch.zeros(max(n, 1), dtype=torch.int32, device=self.device)
+        st = C.c_int32()
+        self._ck(self._L.fse_b200_bitstream_read(self._h, _ptr(data), int(data.numel()), int(total_bits), _ptr(bits), n, _ptr(vals), C.byref(st)))
+        return vals[:n], int(st.value)
+
     # ------------------------------------------------------------------ fused pipelines (device tensors)
     def compress_blocks(self, src, block_size, table_log=0, n_states=32, table_mode=TABLE_PER_BLOCK, out=None, segment_size=0, flags=0):
         """-> (dst uint8[cap] (first `total` bytes valid), offsets int64[nb+1], status int32[nb], total); nb counts

@@ -19,6 +19,7 @@ SYMBOLS = [
     "fse_b200_compress_blocks", "fse_b200_compress_blocks_async", "fse_b200_decompress_blocks",
     "fse_b200_decompress_blocks_async", "fse_b200_decompress_exhaust", "fse_b200_set_global_table", "fse_b200_set_global_table_from_header",
     "fse_b200_compress_host", "fse_b200_decompress_host", "fse_b200_generate",
+    "fse_b200_bitstack_write", "fse_b200_bitstack_read", "fse_b200_bitstream_read",
     "fse_b200_frame_bound", "fse_b200_frame_compress_host", "fse_b200_frame_info", "fse_b200_frame_decompress_host",
 ]
 
@@ -84,6 +85,9 @@ def lib():
     L.fse_b200_compress_host.argtypes = [vp, vp, sz, PP, vp, sz, vp, vp, C.POINTER(u64)]
     L.fse_b200_decompress_host.argtypes = [vp, vp, sz, vp, sz, PP, vp, sz, vp]
     L.fse_b200_generate.argtypes = [vp, i32, u64, u64, vp, sz]
+    L.fse_b200_bitstack_write.argtypes = [vp, vp, vp, sz, i32, vp, sz, C.POINTER(u64)]
+    L.fse_b200_bitstack_read.argtypes = [vp, vp, sz, vp, sz, vp, C.POINTER(C.c_int32)]
+    L.fse_b200_bitstream_read.argtypes = [vp, vp, sz, u64, vp, sz, vp, C.POINTER(C.c_int32)]
     L.fse_b200_frame_bound.argtypes = [sz, PP]
     L.fse_b200_frame_bound.restype = sz
     L.fse_b200_frame_compress_host.argtypes = [vp, vp, sz, PP, vp, sz, C.POINTER(sz)]

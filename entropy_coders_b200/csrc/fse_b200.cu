@@ -6,6 +6,7 @@
 #include "fse_hist16.cuh"
 #include "fse_shared_enc.cuh"
 #include "fse_shared_dec.cuh"
+#include "fse_bitio.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -453,6 +454,58 @@ int fse_b200_build_decode_tables(fse_b200_ctx *ctx, const int32_t *d_norm, const
         return fail(ctx, FSE_B200_ERR_ARG, "build_decode_tables: bad argument");
     return build_tables(ctx, d_norm, d_log2, d_table_len, ntables, max_table_log, 1, nullptr, nullptr, nullptr,
                         reinterpret_cast<uint32_t *>(d_table), d_status, true);
+}
+
+// ---------------------------------------------------------------------------------- bit I/O primitives
+
+int fse_b200_bitstack_write(fse_b200_ctx *ctx, const uint32_t *d_vals, const uint8_t *d_bits, size_t n, int mark,
+                            uint8_t *d_out, size_t out_cap, uint64_t *h_nbits)
+{
+    if (!ctx || (!d_vals && n) || (!d_bits && n) || !d_out || !h_nbits || n > 0x7fffffffull) return fail(ctx, FSE_B200_ERR_ARG, "bitstack_write: bad argument");
+    if (((uintptr_t)d_out & 3) != 0) return fail(ctx, FSE_B200_ERR_ARG, "bitstack_write: d_out must be 4-byte aligned");
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->misc.reserve(64));
+    unsigned long long *d_n = ctx->misc.as<unsigned long long>();
+    int *d_st = reinterpret_cast<int *>(d_n + 1);
+    k_bitstack_write<<<1, 32, 0, ctx->stream>>>(d_vals, d_bits, (uint32_t)n, mark, reinterpret_cast<uint32_t *>(d_out), (uint32_t)(out_cap / 4), d_n, d_st);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    struct { unsigned long long nbits; int st; } r;
+    CK(cudaMemcpyAsync(&r, d_n, 12, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *h_nbits = r.nbits;
+    return r.st < 0 ? fail(ctx, r.st, "bitstack_write: out_cap too small") : FSE_B200_OK;
+}
+
+int fse_b200_bitstack_read(fse_b200_ctx *ctx, const uint8_t *d_in, size_t nbytes, const uint8_t *d_bits, size_t n, uint32_t *d_vals,
+                           int32_t *h_status)
+{
+    if (!ctx || (!d_in && nbytes) || (!d_bits && n) || (!d_vals && n) || !h_status || n > 0x7fffffffull) return fail(ctx, FSE_B200_ERR_ARG, "bitstack_read: bad argument");
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->misc.reserve(64));
+    int *d_st = ctx->misc.as<int>();
+    k_bitstack_read<<<1, 32, 0, ctx->stream>>>(d_in, nbytes, d_bits, (uint32_t)n, d_vals, d_st);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h_status, d_st, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return FSE_B200_OK;
+}
+
+int fse_b200_bitstream_read(fse_b200_ctx *ctx, const uint8_t *d_in, size_t nbytes, uint64_t total_bits, const uint8_t *d_bits, size_t n,
+                            uint32_t *d_vals, int32_t *h_status)
+{
+    if (!ctx || (!d_in && nbytes) || (!d_bits && n) || (!d_vals && n) || !h_status || n > 0x7fffffffull || nbytes > 0x1fffffffull)
+        return fail(ctx, FSE_B200_ERR_ARG, "bitstream_read: bad argument");
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->misc.reserve(64));
+    int *d_st = ctx->misc.as<int>();
+    k_bitstream_read<<<1, 32, 0, ctx->stream>>>(d_in, nbytes, total_bits, d_bits, (uint32_t)n, d_vals, d_st);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h_status, d_st, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return FSE_B200_OK;
 }
 
 // ---------------------------------------------------------------------------------- global table

@@ -167,6 +167,116 @@ inline NormHistogram Histogram::normalize(uint32_t log2) const
 }
 inline NormHistogram Histogram::normalize_optimal() const { return normalize(optimal_log2()); }
 
+
+// ------------------------------------------------------------------------------------------------
+// bitstream: the crate's bit I/O objects (src/bitstream/mod.rs:8-15) as plain host C++.  They are the
+// host-side per-call objects of the API; the block pipelines run the same arithmetic per lane on the GPU
+// (BitRowS / warp_place, the payload ring) and are checked against these through the oracle.  Byte-level
+// behaviour follows the reference: bit k of a stream is bit (k mod 8) of byte (start + k div 8), fields are
+// laid down LSB first in call order, the last byte is zero padded (writer.rs:163-180, :201-222).
+// ------------------------------------------------------------------------------------------------
+namespace bitstream {
+
+struct UnexpectedEof : std::runtime_error { UnexpectedEof() : std::runtime_error("failed to fill whole buffer") {} };   // io::ErrorKind::UnexpectedEof
+
+class BitStackWriter {                                     // src/bitstream/writer.rs:5-223
+    std::vector<uint8_t> &out_;
+    size_t start_;                                         // a writer starts at the vector's length: on a byte boundary (:18-20)
+    uint64_t acc_ = 0;                                     // bits not yet in the vector, LSB first
+    unsigned held_ = 0;
+    size_t total_ = 0;
+public:
+    explicit BitStackWriter(std::vector<uint8_t> &writer) : out_(writer), start_(writer.size()) {}
+    // whole bytes leave the accumulator (writer.rs:43-110 does it in aligned 32-bit stores; the bytes are the same)
+    void flush()
+    {
+        while (held_ >= 8) { out_.push_back((uint8_t)acc_); acc_ >>= 8; held_ -= 8; }
+    }
+    // val must have no bits above `bits` (debug-asserted in the reference, :170-175); bits <= 16 (:142-146)
+    void write_bits(size_t val, size_t bits)
+    {
+        if (bits > 16) throw Panic("write_bits: at most 16 bits per call");
+        if (bits < 64 && (val >> bits) != 0) throw Panic("write_bits: value has bits above the field");
+        acc_ |= (uint64_t)val << held_;
+        held_ += (unsigned)bits;
+        total_ += bits;
+        flush();
+    }
+    void write_bits_unmasked(size_t val, size_t bits) { write_bits(val & (((size_t)1 << bits) - 1), bits); }   // :195-198
+    // bits written since new (the reference's comment says bytes; it returns bits: :220-221, bitstream/mod.rs:38-47)
+    size_t finish()
+    {
+        flush();
+        if (held_) { out_.push_back((uint8_t)acc_); acc_ = 0; held_ = 0; }
+        out_.resize(start_ + (total_ + 7) / 8);
+        return total_;
+    }
+};
+
+class BitStackReader {                                     // src/bitstream/stack_reader.rs:5-227
+    const uint8_t *p_;
+    size_t bits_;                                          // unread bits below the marker
+    BitStackReader(const uint8_t *p, size_t bits) : p_(p), bits_(bits) {}
+public:
+    // None on an empty slice or when the last byte is zero: its highest set bit is the marker (:18-20, :77-83)
+    static std::optional<BitStackReader> create(const uint8_t *data, size_t len)
+    {
+        if (len == 0 || data[len - 1] == 0) return std::nullopt;
+        return BitStackReader(data, (len - 1) * 8 + (31 - __builtin_clz((unsigned)data[len - 1])));
+    }
+    // the n most recently written unread bits with their original significance (:176-184); None when fewer are left
+    std::optional<size_t> peek(size_t n) const
+    {
+        if (n > 16) throw Panic("peek: at most 16 bits per call");
+        if (n > bits_) return std::nullopt;
+        size_t lo = bits_ - n, v = 0;
+        for (size_t k = 0; k < n; k++) v |= (size_t)((p_[(lo + k) >> 3] >> ((lo + k) & 7)) & 1) << k;
+        return v;
+    }
+    std::optional<size_t> read(size_t n)                   // :211-215
+    {
+        auto v = peek(n);
+        if (v) bits_ -= n;
+        return v;
+    }
+    void reload() {}                                       // the refill of the 64-bit window (:97-172) has no observable effect here
+    size_t available() const { return bits_; }             // unread bits (the reference reports those in its window; both are 0 at the end)
+    bool finish() const { return bits_ == 0; }             // :224-226
+};
+
+class BitStreamReader {                                    // src/bitstream/stream_reader.rs:5-136
+    const uint8_t *p_;
+    size_t len_, total_bits_, read_ = 0;
+public:
+    BitStreamReader(const uint8_t *data, size_t len, size_t total_bits) : p_(data), len_(len), total_bits_(total_bits)
+    {
+        if (len == 0) throw Panic("No bytes provided to read from");                      // :17
+        if ((total_bits + 7) / 8 != len) throw Panic("Total number of bytes should be exactly enough to contain the total number of bits");   // :18-21
+    }
+    size_t peek(size_t n) const                            // :82-114
+    {
+        if (n > 32) throw Panic("peek: at most 32 bits per call");
+        if (read_ + n > total_bits_) throw UnexpectedEof();
+        size_t v = 0;
+        for (size_t k = 0; k < n; k++) v |= (size_t)((p_[(read_ + k) >> 3] >> ((read_ + k) & 7)) & 1) << k;
+        return v;
+    }
+    void advance_by(size_t n)                              // :67-75
+    {
+        if (read_ + n > total_bits_) throw UnexpectedEof();
+        read_ += n;
+    }
+    size_t read(size_t n) { size_t v = peek(n); advance_by(n); return v; }   // :56-60
+    size_t available() const { return total_bits_ - read_; }                 // :117-119
+    // (remaining bytes, bits left, bit offset into the first of them) (:123-128)
+    struct Rest { const uint8_t *data; size_t len, bits_left, bit_offset; };
+    Rest finish() const { return {p_ + read_ / 8, len_ - read_ / 8, total_bits_ - read_, read_ % 8}; }
+    // complete the current byte and return what is left (:132-135)
+    std::pair<const uint8_t *, size_t> finish_byte() const { size_t b = (read_ + 7) / 8; return {p_ + b, len_ - b}; }
+};
+
+}  // namespace bitstream
+
 namespace fse {
 struct SymbolTransform { uint32_t bits; int32_t find_state; };          // src/fse.rs:80-84
 struct DecodeTransform { uint16_t new_state; uint8_t symbol; uint8_t num_bits; };   // src/fse.rs:260-265
@@ -215,6 +325,59 @@ public:
         table.resize(size);
         for (size_t i = 0; i < size; i++) table[i] = {h[i].new_state, h[i].symbol, h[i].num_bits};
     }
+};
+
+// fse::Encoder / fse::Decoder (src/fse.rs:196-251, :341-386): the per-symbol state machines over tables built on the
+// GPU (EncodeTable / DecodeTable above).  Host objects for callers that drive a stream symbol by symbol; "Encoders can
+// be interleaved ... each one only mutably borrows the BitStackWriter when encoding a symbol" (src/fse.rs:16-17).
+class Encoder {
+    uint32_t value_ = 0;
+    const EncodeTable *table_;
+public:
+    explicit Encoder(const EncodeTable &table) : table_(&table) {}                        // :203-205
+    // the first symbol to encode (the last to be read) starts from the smallest state and costs no bits (:210-218)
+    static Encoder new_first_symbol(const EncodeTable &table, uint8_t first_symbol)
+    {
+        Encoder e(table);
+        const SymbolTransform &tt = table.symbol_tt[first_symbol];
+        const uint32_t bits_out = (tt.bits + (1u << 15)) >> 16;
+        const uint32_t v = (bits_out << 16) - tt.bits;
+        e.value_ = table.table[(size_t)((int32_t)(v >> bits_out) + tt.find_state)];
+        return e;
+    }
+    void encode(bitstream::BitStackWriter &writer, uint8_t sym)                            // :227-245
+    {
+        const SymbolTransform &tt = table_->symbol_tt[sym];
+        const uint32_t bits_out = (tt.bits + value_) >> 16;
+        writer.write_bits_unmasked(value_, bits_out);
+        value_ = table_->table[(size_t)((int32_t)(value_ >> bits_out) + tt.find_state)];
+    }
+    void finish(bitstream::BitStackWriter &writer) const { writer.write_bits_unmasked(value_, table_->table_log); }   // :248-250
+    uint32_t state() const { return value_; }
+};
+
+class Decoder {
+    uint16_t state_;
+    const DecodeTable *table_;
+    Decoder(uint16_t s, const DecodeTable &t) : state_(s), table_(&t) {}
+public:
+    // None when the reader holds fewer than table_log bits (:349-352)
+    static std::optional<Decoder> create(const DecodeTable &table, bitstream::BitStackReader &reader)
+    {
+        auto s = reader.read(table.table_log);
+        if (!s) return std::nullopt;
+        return Decoder((uint16_t)*s, table);
+    }
+    // None when the reader cannot supply num_bits: the end of the stream (:363-380)
+    std::optional<uint8_t> decode_symbol(bitstream::BitStackReader &reader)
+    {
+        const DecodeTransform &e = table_->table[state_];
+        auto low = reader.read(e.num_bits);
+        if (!low) return std::nullopt;
+        state_ = (uint16_t)(e.new_state + *low);
+        return e.symbol;
+    }
+    uint8_t finish() const { return table_->table[state_].symbol; }                       // :383-385
 };
 }  // namespace fse
 

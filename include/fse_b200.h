@@ -175,6 +175,24 @@ int fse_b200_build_decode_tables(fse_b200_ctx *ctx, const int32_t *d_norm, const
                                  const uint32_t *d_table_len, size_t ntables, uint32_t max_table_log,
                                  fse_b200_decode_transform *d_table, int32_t *d_status);
 
+/* ---- bit I/O primitives (device pointers; one warp each: the packing / reading code of the coders on its own) ---- */
+/* BitStackWriter, src/bitstream/writer.rs:140-222: the n fields (d_vals[i] masked to d_bits[i] <= 16 bits, as
+ * write_bits_unmasked :195-198) are appended LSB first in index order, then a marker bit when `mark` (src/lib.rs:141,181).
+ * d_out: 4-byte aligned, out_cap bytes; *h_nbits = bits written (finish(), :220-221); the stream occupies
+ * ceil(bits / 8) bytes, zero padded. */
+int fse_b200_bitstack_write(fse_b200_ctx *ctx, const uint32_t *d_vals, const uint8_t *d_bits, size_t n, int mark,
+                            uint8_t *d_out, size_t out_cap, uint64_t *h_nbits);
+/* BitStackReader, src/bitstream/stack_reader.rs:17-226: finds the marker (highest set bit of the last byte) and reads
+ * the fields from the END (field n-1 first; d_vals[i] receives field i).  *h_status: FSE_B200_OK when every field was
+ * supplied and nothing is left (finish() == true), FSE_B200_ERR_NO_MARKER (new -> None), FSE_B200_ERR_LENGTH (read -> None
+ * or bits left over). */
+int fse_b200_bitstack_read(fse_b200_ctx *ctx, const uint8_t *d_in, size_t nbytes, const uint8_t *d_bits, size_t n,
+                           uint32_t *d_vals, int32_t *h_status);
+/* BitStreamReader, src/bitstream/stream_reader.rs:16-135: forward reads under a total_bits bound.  *h_status: bits left
+ * (finish(), >= 0), FSE_B200_ERR_IO on UnexpectedEof, FSE_B200_ERR_PANIC when the reference's constructor asserts (:17-21). */
+int fse_b200_bitstream_read(fse_b200_ctx *ctx, const uint8_t *d_in, size_t nbytes, uint64_t total_bits, const uint8_t *d_bits,
+                            size_t n, uint32_t *d_vals, int32_t *h_status);
+
 /* ---- fused pipelines (device pointers) ------------------------------------------------------ */
 /* fse_compress / fse_compress2 per block, src/lib.rs:112-183 (histogram + normalise + header +
  * encode table + encode), then an exclusive scan of the block sizes and a gather into d_dst.
