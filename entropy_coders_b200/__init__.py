@@ -140,6 +140,20 @@ class Context:
         self._ck(self._L.fse_b200_normalize(self._h, _ptr(counts64), nt, table_log, _ptr(norm), _ptr(log2), _ptr(tlen), _ptr(st)))
         return norm, log2, tlen, st
 
+    def normalize_zstd(self, counts64, table_log=0, use_low_prob_count=True):
+        """libzstd's FSE_normalizeCount (not the crate's normalize): counts64 int64[nt,256] ->
+        (norm int32[nt,256], log2[nt], table_len[nt], status[nt])"""
+        torch = _torch()
+        counts64 = counts64.reshape(-1, 256).contiguous()
+        nt = counts64.shape[0]
+        norm = torch.empty((nt, 256), dtype=torch.int32, device=self.device)
+        log2 = torch.empty(nt, dtype=torch.int32, device=self.device)
+        tlen = torch.empty(nt, dtype=torch.int32, device=self.device)
+        st = torch.empty(nt, dtype=torch.int32, device=self.device)
+        self._ck(self._L.fse_b200_normalize_zstd(self._h, _ptr(counts64), nt, table_log, 1 if use_low_prob_count else 0,
+                                                 _ptr(norm), _ptr(log2), _ptr(tlen), _ptr(st)))
+        return norm, log2, tlen, st
+
     def ncount_write(self, norm, log2, tlen):
         """NormHistogram::write, src/histogram.rs:376-431 -> (rows uint8[nt,512], bytes[nt], bits[nt])"""
         torch = _torch()

@@ -14,7 +14,7 @@ STATUS = {0: "OK", -1: "ERR_ARG", -2: "ERR_CAPACITY", -3: "ERR_TABLE_LOG", -4: "
 SYMBOLS = [
     "fse_b200_create", "fse_b200_destroy", "fse_b200_last_error", "fse_b200_version", "fse_b200_launch_count",
     "fse_b200_sync", "fse_b200_set_timing", "fse_b200_get_timing", "fse_b200_compress_bound", "fse_b200_compress_blocks_bound", "fse_b200_num_blocks", "fse_b200_num_streams",
-    "fse_b200_histogram_blocks", "fse_b200_histogram_global", "fse_b200_normalize", "fse_b200_ncount_write",
+    "fse_b200_histogram_blocks", "fse_b200_histogram_global", "fse_b200_normalize", "fse_b200_normalize_zstd", "fse_b200_ncount_write",
     "fse_b200_ncount_read", "fse_b200_build_encode_tables", "fse_b200_build_decode_tables",
     "fse_b200_compress_blocks", "fse_b200_compress_blocks_async", "fse_b200_decompress_blocks",
     "fse_b200_decompress_blocks_async", "fse_b200_decompress_exhaust", "fse_b200_set_global_table", "fse_b200_set_global_table_from_header",
@@ -71,6 +71,7 @@ def lib():
     L.fse_b200_histogram_blocks.argtypes = [vp, vp, sz, u32, vp, vp]
     L.fse_b200_histogram_global.argtypes = [vp, vp, sz, vp]
     L.fse_b200_normalize.argtypes = [vp, vp, sz, u32, vp, vp, vp, vp]
+    L.fse_b200_normalize_zstd.argtypes = [vp, vp, sz, u32, i32, vp, vp, vp, vp]
     L.fse_b200_ncount_write.argtypes = [vp, vp, vp, vp, sz, vp, sz, vp, vp]
     L.fse_b200_ncount_read.argtypes = [vp, vp, sz, vp, sz, vp, vp, vp, vp, vp]
     L.fse_b200_build_encode_tables.argtypes = [vp, vp, vp, vp, sz, u32, vp, vp, vp, vp]

@@ -7,6 +7,7 @@
 #include "fse_shared_enc.cuh"
 #include "fse_shared_dec.cuh"
 #include "fse_bitio.cuh"
+#include "fse_zstd_norm.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -384,6 +385,21 @@ int fse_b200_normalize(fse_b200_ctx *ctx, const uint64_t *d_counts64, size_t nta
     int grid = (int)std::min<size_t>(ntables, (size_t)ctx->num_sms * 16);
     k_normalize<<<grid, 32, 0, ctx->stream>>>(reinterpret_cast<const unsigned long long *>(d_counts64), (uint32_t)ntables,
                                               table_log, d_norm, d_log2, d_table_len, d_status);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    return FSE_B200_OK;
+}
+
+int fse_b200_normalize_zstd(fse_b200_ctx *ctx, const uint64_t *d_counts64, size_t ntables, uint32_t table_log, int use_low_prob_count,
+                            int32_t *d_norm, uint32_t *d_log2, uint32_t *d_table_len, int32_t *d_status)
+{
+    if (!ctx || !d_counts64 || !d_norm || !d_log2 || !d_table_len || !d_status) return fail(ctx, FSE_B200_ERR_ARG, "normalize_zstd: bad argument");
+    if (table_log > 15) return fail(ctx, FSE_B200_ERR_ARG, "table_log must be 0..15 (values the algorithm rejects are reported per table)");
+    CK(cudaSetDevice(ctx->device));
+    if (ntables == 0) return FSE_B200_OK;
+    k_normalize_zstd<<<(unsigned)((ntables + 63) / 64), 64, 0, ctx->stream>>>(reinterpret_cast<const unsigned long long *>(d_counts64), (uint32_t)ntables,
+                                                                              table_log, use_low_prob_count, d_norm, d_log2, d_table_len, d_status);
     ctx->launches++;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(ctx->stream));

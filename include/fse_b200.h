@@ -152,6 +152,17 @@ int fse_b200_histogram_global(fse_b200_ctx *ctx, const uint8_t *d_src, size_t n,
 int fse_b200_normalize(fse_b200_ctx *ctx, const uint64_t *d_counts64, size_t ntables, uint32_t table_log,
                        int32_t *d_norm, uint32_t *d_log2, uint32_t *d_table_len, int32_t *d_status);
 
+/* A second normaliser: libzstd's FSE_normalizeCount + FSE_normalizeM2 (zstd 1.5.x
+ * lib/compress/fse_compress.c), for tables that must equal the ones libzstd's entropy stage builds from the same counts.
+ * The crate shares zstd's NCount header format (src/histogram.rs:342) but not every normalisation detail (the
+ * `to_distribute != 0` guard at :144; low-probability symbols are always -1 there, here only with use_low_prob_count;
+ * table_log 5..12, >= FSE_minTableLog, 0 = 11).  d_status: 0; 3 = one symbol holds every count (zstd's RLE case,
+ * d_norm all zero); FSE_B200_ERR_TABLE_LOG (> 12); FSE_B200_ERR_PANIC (zstd's ERROR(GENERIC)).  Not part of the
+ * reference's path; the outputs feed fse_b200_ncount_write / build_*_tables like those of fse_b200_normalize. */
+int fse_b200_normalize_zstd(fse_b200_ctx *ctx, const uint64_t *d_counts64, size_t ntables, uint32_t table_log,
+                            int use_low_prob_count, int32_t *d_norm, uint32_t *d_log2, uint32_t *d_table_len,
+                            int32_t *d_status);
+
 /* NormHistogram::write, src/histogram.rs:376-431.  d_out: ntables rows of `stride` bytes;
  * d_bytes / d_bits: uint32[ntables] (bytes appended / header bits, the latter is write()'s return). */
 int fse_b200_ncount_write(fse_b200_ctx *ctx, const int32_t *d_norm, const uint32_t *d_log2,

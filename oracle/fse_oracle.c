@@ -194,6 +194,113 @@ int fse_or_norm_new(const uint8_t *data, size_t n, fse_or_norm *out)
     return fse_or_normalize(&h, log2, out);
 }
 
+
+/* ---------------------------------------------------------------- zstd-interoperable normalisation
+ * NOT the reference crate's arithmetic: this restates libzstd's published FSE_normalizeCount / FSE_normalizeM2
+ * (lib/compress/fse_compress.c, zstd 1.5.x), whose NCount header format the crate shares (histogram.rs:342).  The crate's
+ * normalize differs from it in three places: the `to_distribute != 0 &&` guard (histogram.rs:144), low-probability symbols
+ * are always -1 (zstd: -1 only with useLowProbCount), and the table_log range (zstd: 5..12 and >= FSE_minTableLog).
+ * PARITY UNPINNED: no libzstd build in this image exports FSE_normalizeCount; pinned only by the hand-derived vectors in
+ * tests/test_zstd_normalize.py.  Returns 0, 3 (one symbol holds every count: zstd's "rle special case", norm untouched = 0)
+ * or a negative status. */
+static int zstd_normalize_m2(int32_t *norm, uint32_t table_log, const uint64_t *count, uint64_t total, uint32_t max_symbol,
+                             int32_t low_prob_count)
+{
+    const int32_t NOT_YET_ASSIGNED = -2;
+    uint32_t s, distributed = 0, to_distribute;
+    const uint64_t low_threshold = total >> table_log;
+    uint64_t low_one = (total * 3) >> (table_log + 1);
+    for (s = 0; s <= max_symbol; s++) {
+        if (count[s] == 0) { norm[s] = 0; continue; }
+        if (count[s] <= low_threshold) { norm[s] = low_prob_count; distributed++; total -= count[s]; continue; }
+        if (count[s] <= low_one) { norm[s] = 1; distributed++; total -= count[s]; continue; }
+        norm[s] = NOT_YET_ASSIGNED;
+    }
+    to_distribute = (1u << table_log) - distributed;
+    if (to_distribute == 0) return 0;
+    if ((total / to_distribute) > low_one) {
+        low_one = (total * 3) / ((uint64_t)to_distribute * 2);
+        for (s = 0; s <= max_symbol; s++)
+            if (norm[s] == NOT_YET_ASSIGNED && count[s] <= low_one) { norm[s] = 1; distributed++; total -= count[s]; }
+        to_distribute = (1u << table_log) - distributed;
+    }
+    if (distributed == max_symbol + 1) {
+        uint32_t max_v = 0;
+        uint64_t max_c = 0;
+        for (s = 0; s <= max_symbol; s++)
+            if (count[s] > max_c) { max_v = s; max_c = count[s]; }
+        norm[max_v] += (int32_t)to_distribute;
+        return 0;
+    }
+    if (total == 0) {
+        for (s = 0; to_distribute > 0; s = (s + 1) % (max_symbol + 1))
+            if (norm[s] > 0) { to_distribute--; norm[s]++; }
+        return 0;
+    }
+    {
+        const uint64_t v_step_log = 62 - (uint64_t)table_log;
+        const uint64_t mid = (1ull << (v_step_log - 1)) - 1;
+        const uint64_t r_step = (((1ull << v_step_log) * to_distribute) + mid) / total;
+        uint64_t tmp_total = mid;
+        for (s = 0; s <= max_symbol; s++) {
+            if (norm[s] == NOT_YET_ASSIGNED) {
+                const uint64_t end = tmp_total + count[s] * r_step;
+                const uint32_t weight = (uint32_t)(end >> v_step_log) - (uint32_t)(tmp_total >> v_step_log);
+                if (weight < 1) return FSE_OR_ERR_PANIC;
+                norm[s] = (int32_t)weight;
+                tmp_total = end;
+            }
+        }
+    }
+    return 0;
+}
+
+int fse_or_normalize_zstd(const fse_or_hist *h, uint32_t table_log, int use_low_prob_count, fse_or_norm *out)
+{
+    static const uint32_t RTB[8] = {0, 473195, 504333, 520860, 550000, 700000, 750000, 830000};
+    memset(out, 0, sizeof(*out));
+    if (h->size == 0 || h->table_len == 0) return FSE_OR_ERR_PANIC;
+    const uint32_t max_symbol = h->table_len - 1;
+    if (table_log == 0) table_log = 11;                                          /* FSE_DEFAULT_TABLELOG */
+    if (table_log < 5) return FSE_OR_ERR_PANIC;                                  /* FSE_MIN_TABLELOG: ERROR(GENERIC) */
+    if (table_log > 12) return FSE_OR_ERR_TABLE_LOG;                             /* FSE_MAX_TABLELOG: ERROR(tableLog_tooLarge) */
+    {
+        uint32_t min_src = ilog2_u64(h->size) + 1, min_sym = (max_symbol ? ilog2_u32(max_symbol) : 0) + 2;
+        if (table_log < (min_src < min_sym ? min_src : min_sym)) return FSE_OR_ERR_PANIC;   /* FSE_minTableLog */
+    }
+    out->log2 = table_log;
+    out->table_len = h->table_len;
+    const int32_t low_prob_count = use_low_prob_count ? -1 : 1;
+    const uint64_t scale = 62 - (uint64_t)table_log;
+    const uint64_t step = (1ull << 62) / h->size;
+    const uint64_t v_step = 1ull << (scale - 20);
+    int64_t still = 1ll << table_log;
+    uint32_t largest = 0;
+    int32_t largest_p = 0;
+    const uint64_t low_threshold = h->size >> table_log;
+    for (uint32_t s = 0; s <= max_symbol; s++) {
+        const uint64_t c = h->table[s];
+        if (c == h->size) return 3;                                              /* rle special case */
+        if (c == 0) { out->table[s] = 0; continue; }
+        if (c <= low_threshold) { out->table[s] = low_prob_count; still--; }
+        else {
+            int32_t proba = (int32_t)((c * step) >> scale);
+            if (proba < 8) {
+                const uint64_t rest_to_beat = v_step * RTB[proba];
+                proba += (c * step) - ((uint64_t)proba << scale) > rest_to_beat;
+            }
+            if (proba > largest_p) { largest_p = proba; largest = s; }
+            out->table[s] = proba;
+            still -= proba;
+        }
+    }
+    if (-still >= (out->table[largest] >> 1)) {
+        int rc = zstd_normalize_m2(out->table, table_log, h->table, h->size, max_symbol, low_prob_count);
+        if (rc < 0) return rc;
+    } else out->table[largest] += (int32_t)still;
+    return 0;
+}
+
 /* histogram.rs:330-337 */
 size_t fse_or_write_bound(const fse_or_norm *nh)
 {

@@ -62,6 +62,7 @@ def lib():
         L.fse_or_histogram.restype = None
         L.fse_or_optimal_log2.argtypes = [C.POINTER(Hist), C.POINTER(C.c_uint32)]
         L.fse_or_normalize.argtypes = [C.POINTER(Hist), C.c_uint32, C.POINTER(Norm)]
+        L.fse_or_normalize_zstd.argtypes = [C.POINTER(Hist), C.c_uint32, C.c_int, C.POINTER(Norm)]
         L.fse_or_norm_new.argtypes = [u8p, sz, C.POINTER(Norm)]
         L.fse_or_write_bound.argtypes = [C.POINTER(Norm)]
         L.fse_or_write_bound.restype = sz
@@ -130,6 +131,22 @@ def normalize(h, log2):
     n = Norm()
     rc = lib().fse_or_normalize(C.byref(h), log2, C.byref(n))
     return rc, n
+
+
+def normalize_zstd(h, log2, use_low_prob_count=True):
+    n = Norm()
+    rc = lib().fse_or_normalize_zstd(C.byref(h), log2, 1 if use_low_prob_count else 0, C.byref(n))
+    return rc, n
+
+
+def hist_from_counts(counts):
+    h = Hist()
+    nz = [i for i, c in enumerate(counts) if c]
+    for i, c in enumerate(counts):
+        h.table[i] = int(c)
+    h.size = int(sum(counts))
+    h.table_len = (nz[-1] + 1) if nz else 1
+    return h
 
 
 def optimal_log2(h):
