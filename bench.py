@@ -489,11 +489,36 @@ def e2e_leg(env, job, steps):
         torch.distributed.all_reduce(te, op=torch.distributed.ReduceOp.MAX)
     e2e_s = float(te.item()) / ksteps
     snb = (sample + (job.seg or w["bs"]) - 1) // (job.seg or w["bs"])
+    # the raw link: the same pinned buffers copied each way on every rank at once (what bounds the e2e figure)
+    link = None
+    try:
+        lb = min(sample, 1 << 30)
+        dtmp = torch.empty(lb, dtype=torch.uint8, device=env["dev"])
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        barrier(env)
+        ev[0].record()
+        dtmp.copy_(hsrc[:lb], non_blocking=True)
+        ev[1].record()
+        hout[:lb].copy_(dtmp, non_blocking=True)
+        ev[2].record()
+        torch.cuda.synchronize()
+        bw = torch.tensor([lb / ev[0].elapsed_time(ev[1]) / 1e6, lb / ev[1].elapsed_time(ev[2]) / 1e6], dtype=torch.float64, device=env["dev"])
+        if env["world"] > 1:
+            torch.distributed.all_reduce(bw, op=torch.distributed.ReduceOp.MIN)
+        h2d, d2h = float(bw[0].item()), float(bw[1].item())
+        moved = float(sample + tot)                          # per direction and rank: N + C each way over a round trip
+        link = {"h2d_GBps_min_rank": h2d, "d2h_GBps_min_rank": d2h,
+                "round_trip_bound_GBps": env["world"] * sample / (moved / (min(h2d, d2h) * 1e9)) / 1e9,
+                "note": "pinned copies of 1 GiB each way on all ranks at once; bound = N / ((N + C) / slower direction), full duplex"}
+        del dtmp
+    except Exception as ex:
+        link = {"error": repr(ex)}
     res = {"value": env["world"] * sample / e2e_s / 1e9 if w["scaling"] == "weak" or sample != nbytes
            else job.total_bytes / e2e_s / 1e9,
            "unit": "GB/s", "h2d_bytes_per_step": int(sample + tot + (snb + 1) * 8),
            "d2h_bytes_per_step": int(tot + (snb + 1) * 8 + snb * 4 + sample + snb * 4),
            "steps": ksteps, "bytes_per_rank": sample,
+           "pcie": link, "numa_node": env.get("numa"),
            "api": "fse_b200_compress_host + fse_b200_decompress_host, pinned host buffers, rank-local data"}
     ctx2.close()
     del hsrc, hdst, hout
@@ -537,6 +562,26 @@ def traffic_probe(wl, tlog, dom_kernel):
         return None, "probe failed: %r" % (ex,)
 
 
+def bind_to_gpu_numa(local):
+    """Pin this process to the CPUs that are local to its GPU (sysfs local_cpulist of the PCI device), so that the pinned
+    host buffers of the e2e leg are first-touched on the GPU's own NUMA node.  Returns the node number or None."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        base = "/sys/bus/pci/devices/" + bdf
+        cpus = set()
+        for part in open(base + "/local_cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return int(open(base + "/numa_node").read().strip())
+    except Exception:
+        return None
+
+
 def make_env():
     import torch
     import torch.distributed as dist
@@ -545,6 +590,7 @@ def make_env():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa(local) if world > 1 else None
     dev = torch.device("cuda", local)
     if world > 1:
         # NCCL prints its version banner on stdout when the first communicator is made: send it to stderr so
@@ -564,7 +610,7 @@ def make_env():
     torch.cuda.set_stream(stream)
     side = torch.cuda.Stream(device=dev)
     ctx = E.Context(local, stream=stream.cuda_stream)
-    return {"segment_size": SEGMENT_SIZE, "world": world, "rank": rank, "local": local, "dev": dev, "stream": stream, "side": side, "ctx": ctx}
+    return {"segment_size": SEGMENT_SIZE, "numa": numa, "world": world, "rank": rank, "local": local, "dev": dev, "stream": stream, "side": side, "ctx": ctx}
 
 
 def run_probe(args, wl):

@@ -264,17 +264,28 @@ def fse_compress2(src, dst):
     return _payload_bits(out, len(out) - len(rest))
 
 
+EXHAUST_LIMIT = 1 << 30     # hard limit of the exhaust-mode output when the caller gives no max_len
+
+
 def _decompress(src, dst, n_states, max_len):
     import torch
     src = bytes(src)
     if len(src) == 0:
         raise Panic("No bytes provided to read from")        # stream_reader.rs:17 via lib.rs:191,219
     ctx = _ctx()
+    # No length is stored (lib.rs:198,228): the capacity grows geometrically until the stream fits (skewed data can expand
+    # far beyond 64 x: p = 0.995 gives ~175 x).  Only the stream that never terminates (every state needs 0 bits, SURVEY.md
+    # Q1: the reference loops until out of memory) ends in a Panic, at EXHAUST_LIMIT or the caller's max_len.
     cap = max_len if max_len is not None else max(4096, 64 * len(src))
     comp = _dev_u8(src)
     off = torch.tensor([0, len(src)], dtype=torch.int64, device=ctx.device)
-    out, out_len, st = ctx.decompress_exhaust(comp, len(src), off, 1, cap, 15, n_states)
-    code = int(st[0].item())
+    while True:
+        out, out_len, st = ctx.decompress_exhaust(comp, len(src), off, 1, cap, 15, n_states)
+        code = int(st[0].item())
+        if code == -2 and max_len is None and cap < EXHAUST_LIMIT:
+            cap = min(cap * 8, EXHAUST_LIMIT)
+            continue
+        break
     if code in (-3, -4, -5, -6):
         return None                                           # .ok()? / BitStackReader::new -> None
     if code == -7:

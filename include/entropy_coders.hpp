@@ -14,6 +14,7 @@
 
 #include <array>
 #include <cstdint>
+#include <memory>
 #include <optional>
 #include <stdexcept>
 #include <string>
@@ -403,15 +404,26 @@ inline size_t compress_one(const std::vector<uint8_t> &src, std::vector<uint8_t>
 inline std::optional<size_t> decompress_one(const std::vector<uint8_t> &src, std::vector<uint8_t> &dst, uint32_t n_states, size_t cap)
 {
     if (src.empty()) throw Panic("No bytes provided to read from");           // stream_reader.rs:17 via lib.rs:191,219
+    // No length is stored: unless the caller bounds it, the capacity grows geometrically until the stream fits (skewed
+    // data expands far beyond 64 x); only the never-terminating stream of quirk Q1 reaches the 1 GiB limit and panics.
+    const bool grow = cap == 0;
     if (cap == 0) cap = std::max<size_t>(4096, 64 * src.size());
-    Dev<uint8_t> comp(src.data(), src.size()), out(cap);
+    Dev<uint8_t> comp(src.data(), src.size());
     uint64_t off[2] = {0, src.size()};
     Dev<uint64_t> doff(off, 2);
     Dev<uint32_t> out_len(1);
     Dev<int32_t> st(1);
-    fse_b200_params p{(uint32_t)cap, 15, n_states, FSE_B200_TABLE_PER_BLOCK, 0, 0};
-    ck(fse_b200_decompress_exhaust(ctx(), comp.p, src.size(), doff.p, 1, &p, out.p, out_len.p, st.p), "decompress_exhaust");
-    int32_t rc = st.at(0);
+    std::unique_ptr<Dev<uint8_t>> outp;
+    int32_t rc;
+    for (;;) {
+        outp.reset(new Dev<uint8_t>(cap));
+        fse_b200_params p{(uint32_t)cap, 15, n_states, FSE_B200_TABLE_PER_BLOCK, 0, 0};
+        ck(fse_b200_decompress_exhaust(ctx(), comp.p, src.size(), doff.p, 1, &p, outp->p, out_len.p, st.p), "decompress_exhaust");
+        rc = st.at(0);
+        if (rc == FSE_B200_ERR_CAPACITY && grow && cap < ((size_t)1 << 30)) { cap = std::min<size_t>(cap * 8, (size_t)1 << 30); continue; }
+        break;
+    }
+    Dev<uint8_t> &out = *outp;
     if (rc == FSE_B200_ERR_TABLE_LOG || rc == FSE_B200_ERR_TOO_MANY || rc == FSE_B200_ERR_IO || rc == FSE_B200_ERR_NO_MARKER)
         return std::nullopt;                                                   // .ok()? / BitStackReader::new -> None
     if (rc == FSE_B200_ERR_LENGTH) throw Panic("called `Option::unwrap()` on a `None` value");   // lib.rs:197,224-225

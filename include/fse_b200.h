@@ -246,6 +246,9 @@ int fse_b200_decompress_exhaust(fse_b200_ctx *ctx, const uint8_t *d_comp, size_t
  * *h_header_bytes in: capacity, out: bytes. */
 int fse_b200_set_global_table(fse_b200_ctx *ctx, const uint64_t *d_counts64, uint32_t table_log,
                               uint8_t *h_header, size_t *h_header_bytes, uint32_t *h_log2);
+/* The table must give every byte value that occurs in the data a non-zero count (build it from the histogram of the
+ * data, as fse_b200_frame_compress_host does): like the crate's Encoder, the encode kernels do not look for symbols the
+ * table does not know, and a block that contains one is reported with status 0 but cannot be decoded. */
 /* Same, from a stored header (decode side). */
 int fse_b200_set_global_table_from_header(fse_b200_ctx *ctx, const uint8_t *h_header, size_t header_bytes,
                                           uint32_t *h_log2);

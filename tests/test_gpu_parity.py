@@ -957,3 +957,19 @@ def test_raw_if_expands(ctx, n_states):
     a = ctx.compress_blocks(dev(ctx, txt), bs, 0, n_states)
     b_ = ctx.compress_blocks(dev(ctx, txt), bs, 0, n_states, flags=E.FLAG_RAW_IF_EXPANDS)
     assert a[3] == b_[3] and a[0][:a[3]].cpu().numpy().tobytes() == b_[0][:b_[3]].cpu().numpy().tobytes()
+
+
+def test_crate_decompress_of_highly_skewed_data():
+    """a valid reference stream can expand more than 64 x (p ~ 0.997); the crate mirror grows its capacity
+    instead of reporting 'does not terminate'"""
+    import entropy_coders_b200 as E
+    rng = np.random.default_rng(5)
+    src = np.where(rng.random(400000) < 0.003, 1, 0).astype(np.uint8)
+    src[-1] = 1
+    comp = bytearray()
+    E.fse_compress2(src.tobytes(), comp)
+    assert len(src) > 64 * len(comp)
+    out = bytearray()
+    n = E.fse_decompress2(bytes(comp), out)
+    assert n == len(src) and bytes(out) == src.tobytes()
+    assert bytes(comp) == O.ref_compress2(src)
