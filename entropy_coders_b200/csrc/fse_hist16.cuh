@@ -6,6 +6,10 @@
 // (later stores win, and they carry the larger count).  Measured 1.37 TB/s on 256 MiB against
 // 0.64-0.97 TB/s for 32-bit columns (6 warps per SM) and 0.16-0.7 TB/s for match.any aggregation
 // (tools/hist_bench.cu).  A lane sees block_size/32 + 30 bytes, so blocks up to 1 MiB cannot overflow.
+// Lanes 2k and 2k+1 share a bank in this layout (two wavefronts per access: ncu 1.89 / 2.00).  Round 2 measured the
+// conflict-free alternative (bins 2j / 2j+1 as the halves of the lane's own word at j * 128 + lane * 4: one wavefront
+// per access, two more address instructions per byte): SLOWER, 4.94 vs 4.39 ms on 8 GiB geometric and 0.646 vs 0.519 ms
+// on 1 GiB few-symbol: the kernel is bound by instruction issue and latency before shared-memory wavefronts.
 #pragma once
 #include "fse_device.cuh"
 
