@@ -92,13 +92,17 @@ __device__ __forceinline__ int sh_decode_payload_warp(const uint8_t *pay, uint32
         hi = __funnelshift_r(w1, w2, s);
     };
     bool pending = false, tma_ok = true;
+    // The ring holds words [lowq, lowq + 256).  One test per round covers both stages of the refill: nothing to do while
+    // the cursor is in the upper half.  Below it, one lane starts a 512-byte bulk copy (TMA) of the next lower 128 words
+    // into the dead upper half, and the warp waits on the mbarrier only when a round could reach below lowq.
     auto stage = [&]() {
-        if (!pending && lowq && (cur >> 5) + 3 < lowq + 128) {
+        if ((cur >> 5) + 3 >= lowq + 128 || !lowq) return;
+        if (!pending) {
             __syncwarp();
             if (lane == 0) bulk_g2s(ring_saddr + (((lowq - 128) & 255) << 2), origin + (lowq - 128), 512, wk.bar);
             pending = true;
         }
-        if (pending && (cur >> 5) < lowq + 56) {               // a round takes at most 52 words
+        if ((cur >> 5) < lowq + 56) {                          // a round takes at most 52 words
             tma_ok = tma_ok && mbar_wait(wk.bar, wk.par);
             wk.par ^= 1;
             lowq -= 128;
@@ -132,30 +136,37 @@ __device__ __forceinline__ int sh_decode_payload_warp(const uint8_t *pay, uint32
 #define SHD_NEXT(e, win, n) (((e & SHD_ADDR_MASK) | lanepart) + ((win) & ~(0xffffffffu << (n))) * (1u << SH))
 #define SHD_NB(e) ((e) >> 28)                               /* (IMAD.HI runs at a quarter of the ALU rate: tools/pipe_bench.cu) */
 #define SHD_SYM(e) ((e) >> 20)                              /* symbol in the low byte */
-    for (; i0 + 128 <= body; i0 += 128) {
-        stage();
-        const uint32_t e0 = lds_u32(a0), e1 = lds_u32(a1), e2 = lds_u32(a2), e3 = lds_u32(a3);   // fse.rs:363-373, four chains
-        const uint32_t n0 = SHD_NB(e0), n1 = SHD_NB(e1), n2 = SHD_NB(e2), n3 = SHD_NB(e3);
-        const uint32_t n23 = n2 + n3, n123 = n1 + n23, nbs = n0 + n123;
-        const uint32_t incl = warp_incl_add_pred(nbs);
-        uint32_t lo, hi;
-        ring_bits64(cur - incl, lo, hi);                    // state 4l's bits are the uppermost of the lane's window
-        const uint32_t tot = __shfl_sync(FULL, incl, 31);
-        if (tot > cur - floor_bits) { bad = true; break; }
-        const uint32_t w2 = __funnelshift_r(lo, hi, n3), w1 = __funnelshift_r(lo, hi, n23);      // n23 <= 22
-        const uint32_t w0 = __funnelshift_r(w1, hi >> n23, n1);
-        a3 = SHD_NEXT(e3, lo, n3);
-        a2 = SHD_NEXT(e2, w2, n2);
-        a1 = SHD_NEXT(e1, w1, n1);
-        a0 = SHD_NEXT(e0, w0, n0);
-        const uint32_t sy = __byte_perm(__byte_perm(SHD_SYM(e0), SHD_SYM(e1), 0x0040), __byte_perm(SHD_SYM(e2), SHD_SYM(e3), 0x0040), 0x5410);
-        if (out_aligned) *reinterpret_cast<uint32_t *>(out + i0 + 4 * lane) = sy;
-        else {
-            out[i0 + 4 * lane] = (uint8_t)sy; out[i0 + 4 * lane + 1] = (uint8_t)(sy >> 8);
-            out[i0 + 4 * lane + 2] = (uint8_t)(sy >> 16); out[i0 + 4 * lane + 3] = (uint8_t)(sy >> 24);
-        }
-        cur -= tot;
+    // one full round: fse.rs:363-373 on four chains per lane; STORE writes the lane's four symbols
+#define SHD_ROUND(STORE)                                                                                              \
+    {                                                                                                                 \
+        stage();                                                                                                      \
+        const uint32_t e0 = lds_u32(a0), e1 = lds_u32(a1), e2 = lds_u32(a2), e3 = lds_u32(a3);                         \
+        const uint32_t n0 = SHD_NB(e0), n1 = SHD_NB(e1), n2 = SHD_NB(e2), n3 = SHD_NB(e3);                              \
+        const uint32_t n23 = n2 + n3, n123 = n1 + n23, nbs = n0 + n123;                                                 \
+        const uint32_t incl = warp_incl_add_pred(nbs);                                                                  \
+        uint32_t lo, hi;                                                                                                \
+        ring_bits64(cur - incl, lo, hi);        /* state 4l's bits are the uppermost of the lane's window */            \
+        const uint32_t tot = __shfl_sync(FULL, incl, 31);                                                               \
+        if (tot > cur - floor_bits) { bad = true; break; }                                                              \
+        const uint32_t w2 = __funnelshift_r(lo, hi, n3), w1 = __funnelshift_r(lo, hi, n23);   /* n23 <= 22 */           \
+        const uint32_t w0 = __funnelshift_r(w1, hi >> n23, n1);                                                         \
+        a3 = SHD_NEXT(e3, lo, n3);                                                                                      \
+        a2 = SHD_NEXT(e2, w2, n2);                                                                                      \
+        a1 = SHD_NEXT(e1, w1, n1);                                                                                      \
+        a0 = SHD_NEXT(e0, w0, n0);                                                                                      \
+        const uint32_t sy = __byte_perm(__byte_perm(SHD_SYM(e0), SHD_SYM(e1), 0x0040), __byte_perm(SHD_SYM(e2), SHD_SYM(e3), 0x0040), 0x5410); \
+        STORE;                                                                                                          \
+        cur -= tot;                                                                                                     \
     }
+    if (out_aligned) {
+        uint32_t *ow = reinterpret_cast<uint32_t *>(out) + lane;
+        for (; i0 + 128 <= body; i0 += 128, ow += 32) SHD_ROUND(*ow = sy)
+    } else {
+        uint8_t *ob = out + 4 * lane;
+        for (; i0 + 128 <= body; i0 += 128, ob += 128)
+            SHD_ROUND(ob[0] = (uint8_t)sy; ob[1] = (uint8_t)(sy >> 8); ob[2] = (uint8_t)(sy >> 16); ob[3] = (uint8_t)(sy >> 24))
+    }
+#undef SHD_ROUND
     if (!bad && i0 < body) {                                // last partial round
         stage();
         const uint32_t ia = i0 + 4 * lane;
