@@ -52,32 +52,16 @@ __global__ void __launch_bounds__(512, 2) k_decode64w_blocks(DecArgs a)
         const size_t off = (size_t)b * a.block_size;
         const uint32_t bn = (uint32_t)min((size_t)a.block_size, a.n - off);
         uint8_t *out = a.dst + off;
-        const unsigned long long o0 = a.offsets[b], o1 = a.offsets[b + 1];
         int st = ST_OK;
-        if (o1 < o0 || o1 > a.comp_bytes || o1 - o0 > 0xffffffffull) {
-            if (lane == 0) a.status[b] = ST_LENGTH;
+        const uint8_t *cs;
+        uint32_t clen;
+        if (dec_block_prologue(a, b, bn, N, out, lane, cs, clen, st)) {      // bad offsets, raw tail, escape blocks
+            if (lane == 0) { a.status[b] = st; if (a.exhaust) a.out_len[b] = 0; }
             continue;
         }
-        const uint8_t *cs = a.comp + o0;
-        const uint32_t clen = (uint32_t)(o1 - o0);
         uint32_t log2 = glog2, consumed = 0;
         __syncwarp();
         if (!a.global_mode) {
-            if (clen == 0) { if (lane == 0) a.status[b] = ST_PANIC; continue; }
-            uint32_t first = cs[0];
-            if ((first & 0x0f) == 0x0f) {
-                if (clen != 1 + bn) { if (lane == 0) a.status[b] = ST_LENGTH; continue; }
-                for (uint32_t i = lane; i < bn; i += 32) out[i] = cs[1 + i];
-                if (lane == 0) a.status[b] = 1;
-                continue;
-            }
-            if ((first & 0x0f) == 0x0e) {
-                if (clen != 2) { if (lane == 0) a.status[b] = ST_LENGTH; continue; }
-                uint8_t v = cs[1];
-                for (uint32_t i = lane; i < bn; i += 32) out[i] = v;
-                if (lane == 0) a.status[b] = 2;
-                continue;
-            }
 #pragma unroll
             for (int k = 0; k < 8; k++) norm[k * 32 + lane] = 0;
             __syncwarp();
@@ -93,11 +77,6 @@ __global__ void __launch_bounds__(512, 2) k_decode64w_blocks(DecArgs a)
             if (log2 > a.tlmax || log2 > 13) { if (lane == 0) a.status[b] = ST_UNSUPPORTED; continue; }
             warp_spread(norm, log2, table_len, sym, ctr, reinterpret_cast<uint16_t *>(tab), lane);   // posmap: first half of tab
             warp_build_decode(norm, log2, table_len, sym, ctr, tab, lane);   // entry c overwrites spread cells <= c only
-        } else if (bn < N) {
-            if (clen != bn) { if (lane == 0) a.status[b] = ST_LENGTH; continue; }
-            for (uint32_t i = lane; i < bn; i += 32) out[i] = cs[i];
-            if (lane == 0) a.status[b] = 1;
-            continue;
         }
         if (bn < N) { if (lane == 0) a.status[b] = ST_LENGTH; continue; }
         const uint8_t *pay = cs + consumed;

@@ -480,6 +480,42 @@ struct DecArgs {
     uint32_t *out_len;
 };
 
+// What every block decoder does before it looks at a header: the offset checks, the short raw tail of the global-table
+// mode and the escape blocks (include/fse_b200.h: 0x0F raw, 0x0E run; no valid header starts with them, histogram.rs:439-441).
+// Returns true when the block is finished (st = its status word); otherwise cs / clen are the stream to parse.  All lanes call.
+__device__ __forceinline__ bool dec_block_prologue(const DecArgs &a, uint32_t b, uint32_t bn, uint32_t N, uint8_t *out, int lane,
+                                                   const uint8_t *&cs, uint32_t &clen, int &st)
+{
+    const unsigned long long o0 = a.offsets[b], o1 = a.offsets[b + 1];
+    if (o1 < o0 || o1 > a.comp_bytes || o1 - o0 > 0xffffffffull) { st = ST_LENGTH; return true; }
+    cs = a.comp + o0;
+    clen = (uint32_t)(o1 - o0);
+    if (a.global_mode) {
+        if (bn >= N) return false;
+        if (clen != bn) { st = ST_LENGTH; return true; }     // a short tail is stored raw, no escape
+        for (uint32_t i = lane; i < bn; i += 32) out[i] = cs[i];
+        st = 1;
+        return true;
+    }
+    if (clen == 0) { st = ST_PANIC; return true; }           // stream_reader.rs:17
+    const uint32_t first = cs[0];
+    if (a.exhaust && (first & 0x0f) > 10) { st = ST_TABLE_LOG; return true; }   // TableLogTooLarge -> None, histogram.rs:439-441, lib.rs:191,219
+    if ((first & 0x0f) == 0x0f) {                            // raw escape
+        if (clen != 1 + bn) { st = ST_LENGTH; return true; }
+        for (uint32_t i = lane; i < bn; i += 32) out[i] = cs[1 + i];
+        st = 1;
+        return true;
+    }
+    if ((first & 0x0f) == 0x0e) {                            // run escape
+        if (clen != 2) { st = ST_LENGTH; return true; }
+        const uint8_t v = cs[1];
+        for (uint32_t i = lane; i < bn; i += 32) out[i] = v;
+        st = 2;
+        return true;
+    }
+    return false;
+}
+
 __global__ void __launch_bounds__(512) k_decode_blocks(DecArgs a)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -504,36 +540,16 @@ __global__ void __launch_bounds__(512) k_decode_blocks(DecArgs a)
         const size_t off = (size_t)b * a.block_size;
         const uint32_t bn = (uint32_t)min((size_t)a.block_size, a.n - off);
         uint8_t *out = a.dst + off;
-        const unsigned long long o0 = a.offsets[b], o1 = a.offsets[b + 1];
         int st = ST_OK;
-        if (o1 < o0 || o1 > a.comp_bytes || o1 - o0 > 0xffffffffull) {
-            if (lane == 0) a.status[b] = ST_LENGTH;
+        const uint8_t *cs;
+        uint32_t clen;
+        if (dec_block_prologue(a, b, bn, N, out, lane, cs, clen, st)) {      // bad offsets, raw tail, escape blocks
+            if (lane == 0) { a.status[b] = st; if (a.exhaust) a.out_len[b] = 0; }
             continue;
         }
-        const uint8_t *cs = a.comp + o0;
-        const uint32_t clen = (uint32_t)(o1 - o0);
         uint32_t log2 = glog2, consumed = 0;
         __syncwarp();
         if (!a.global_mode) {
-            if (clen == 0) { if (lane == 0) a.status[b] = ST_PANIC; continue; }   // stream_reader.rs:17
-            uint32_t first = cs[0];
-            if (a.exhaust && (first & 0x0f) > 10) {   // TableLogTooLarge -> None, histogram.rs:439-441, lib.rs:191,219
-                if (lane == 0) { a.status[b] = ST_TABLE_LOG; a.out_len[b] = 0; }
-                continue;
-            }
-            if ((first & 0x0f) == 0x0f) {        // raw escape
-                if (clen != 1 + bn) { if (lane == 0) a.status[b] = ST_LENGTH; continue; }
-                for (uint32_t i = lane; i < bn; i += 32) out[i] = cs[1 + i];
-                if (lane == 0) a.status[b] = 1;
-                continue;
-            }
-            if ((first & 0x0f) == 0x0e) {        // run escape
-                if (clen != 2) { if (lane == 0) a.status[b] = ST_LENGTH; continue; }
-                uint8_t v = cs[1];
-                for (uint32_t i = lane; i < bn; i += 32) out[i] = v;
-                if (lane == 0) a.status[b] = 2;
-                continue;
-            }
 #pragma unroll
             for (int k = 0; k < 8; k++) norm[k * 32 + lane] = 0;
             __syncwarp();
@@ -549,11 +565,6 @@ __global__ void __launch_bounds__(512) k_decode_blocks(DecArgs a)
             if (log2 > a.tlmax) { if (lane == 0) a.status[b] = ST_UNSUPPORTED; continue; }
             warp_spread(norm, log2, table_len, spread, ctr, reinterpret_cast<uint16_t *>(tab), lane);
             warp_build_decode(norm, log2, table_len, spread, ctr, tab, lane);
-        } else if (bn < N) {
-            if (clen != bn) { if (lane == 0) a.status[b] = ST_LENGTH; continue; }
-            if ((uint32_t)lane < bn) out[lane] = cs[lane];
-            if (lane == 0) a.status[b] = 1;
-            continue;
         }
         if (bn < N) { if (lane == 0) a.status[b] = ST_LENGTH; continue; }
         // BitStackReader::new, stack_reader.rs:17-92: the highest set bit of the last byte is the marker

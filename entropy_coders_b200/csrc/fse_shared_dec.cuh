@@ -249,20 +249,11 @@ __global__ void __launch_bounds__(1024) k_decode_sh_global(DecArgs a)
         const size_t off = (size_t)b * a.block_size;
         const uint32_t bn = (uint32_t)min((size_t)a.block_size, a.n - off);
         uint8_t *out = a.dst + off;
-        const unsigned long long o0 = a.offsets[b], o1 = a.offsets[b + 1];
-        int st;
-        if (o1 < o0 || o1 > a.comp_bytes || o1 - o0 > 0xffffffffull) st = ST_LENGTH;
-        else {
-            const uint8_t *cs = a.comp + o0;
-            const uint32_t clen = (uint32_t)(o1 - o0);
-            if (bn < N) {
-                if (clen != bn) st = ST_LENGTH;
-                else {
-                    for (uint32_t i = lane; i < bn; i += 32) out[i] = cs[i];
-                    st = 1;
-                }
-            } else st = sh_decode_dispatch(R, cs, clen, out, bn, log2, tab_saddr, lanepart, wk, lane);
-        }
+        int st = ST_OK;
+        const uint8_t *cs;
+        uint32_t clen;
+        if (!dec_block_prologue(a, b, bn, N, out, lane, cs, clen, st))       // bad offsets and the short raw tail are handled there
+            st = sh_decode_dispatch(R, cs, clen, out, bn, log2, tab_saddr, lanepart, wk, lane);
         __syncwarp();
         if (lane == 0) a.status[b] = st;
     }
