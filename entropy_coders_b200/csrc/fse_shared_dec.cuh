@@ -8,7 +8,7 @@
 //                    (cell parity picks the bank): at most two wavefronts per look-up.
 // 128 KiB either way.  The entry is re-packed for the state chain: the state is kept as the shared-memory ADDRESS of
 // its row, and an entry holds the row address of its new_state, so a transition is
-//   e = lds(a);  nb = e >> 28;  a' = ((e & 0x3ffff) | lane_part) + ((window & ~(~0 << nb)) << log2(4R))
+//   e = lds(a);  nb = e >> 28;  a' = (e & 0xffff) * 4 + lane_part + (window & ~(~0 << nb)) * 4R      (two IMADs)
 // (new_state + bits is an OR in the reference arithmetic: new_state is a multiple of 1 << num_bits).
 #pragma once
 #include "fse_decode128c.cuh"
@@ -29,10 +29,11 @@ __host__ __device__ inline ShDecLayout sh_dec_layout(uint32_t log2, uint32_t R, 
     return l;
 }
 
-constexpr uint32_t SHD_ADDR_MASK = 0x3ffffu;
+// entry = WORD address of the row of new_state (16 bits: shared memory is < 256 KiB) | symbol << 16 | num_bits << 28: the
+// symbol is a whole byte (one PRMT gathers the four symbols of a lane, no shifts) and num_bits is one shift away
 __device__ __forceinline__ uint32_t shd_entry(uint32_t tab_saddr, uint32_t sh, uint32_t new_state, uint32_t sym, uint32_t nb)
 {
-    return (tab_saddr + (new_state << sh)) | (sym << 20) | (nb << 28);
+    return ((tab_saddr + (new_state << sh)) >> 2) | (sym << 16) | (nb << 28);
 }
 // the CTA copies a decode table in the reference layout (new_state | symbol << 16 | num_bits << 24) into the replicated form
 __device__ __forceinline__ void sh_replicate_dec(const uint32_t *__restrict__ tab, uint32_t log2, uint32_t R, uint8_t *tabR, uint32_t tab_saddr,
@@ -46,6 +47,16 @@ __device__ __forceinline__ void sh_replicate_dec(const uint32_t *__restrict__ ta
         const uint32_t w = shd_entry(tab_saddr, sh, r & 0xffffu, (r >> 16) & 0xffu, r >> 24);
         reinterpret_cast<uint4 *>(tabR)[i] = make_uint4(w, w, w, w);
     }
+}
+
+// the next row address: (word address of new_state's row) * 4 + lane part, plus the bits read * row size: one LOP + two IMADs
+template <int SH>
+__device__ __forceinline__ uint32_t shd_next(uint32_t e, uint32_t win, uint32_t n, uint32_t lanepart)
+{
+    uint32_t a;
+    asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(a) : "r"(e & 0xffffu), "r"(lanepart));
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(a) : "r"(win & ~(0xffffffffu << n)), "n"(1 << SH));
+    return a;
 }
 
 struct ShDecWarp {
@@ -133,9 +144,9 @@ __device__ __forceinline__ int sh_decode_payload_warp(const uint8_t *pay, uint32
     bool bad = false;
     uint32_t i0 = 0;
     // next row address: the row of new_state (in the entry) | lane part, plus the bits read; the product is an IMAD (FMA pipe)
-#define SHD_NEXT(e, win, n) (((e & SHD_ADDR_MASK) | lanepart) + ((win) & ~(0xffffffffu << (n))) * (1u << SH))
+#define SHD_NEXT(e, win, n) shd_next<SH>(e, win, n, lanepart)
 #define SHD_NB(e) ((e) >> 28)                               /* (IMAD.HI runs at a quarter of the ALU rate: tools/pipe_bench.cu) */
-#define SHD_SYM(e) ((e) >> 20)                              /* symbol in the low byte */
+#define SHD_SYM(e) (((e) >> 16) & 0xffu)
     // one full round: fse.rs:363-373 on four chains per lane; STORE writes the lane's four symbols
 #define SHD_ROUND(STORE)                                                                                              \
     {                                                                                                                 \
@@ -154,13 +165,13 @@ __device__ __forceinline__ int sh_decode_payload_warp(const uint8_t *pay, uint32
         a2 = SHD_NEXT(e2, w2, n2);                                                                                      \
         a1 = SHD_NEXT(e1, w1, n1);                                                                                      \
         a0 = SHD_NEXT(e0, w0, n0);                                                                                      \
-        const uint32_t sy = __byte_perm(__byte_perm(SHD_SYM(e0), SHD_SYM(e1), 0x0040), __byte_perm(SHD_SYM(e2), SHD_SYM(e3), 0x0040), 0x5410); \
+        const uint32_t sy = __byte_perm(__byte_perm(e0, e1, 0x0062), __byte_perm(e2, e3, 0x0062), 0x5410);   /* byte 2 of e0..e3 */ \
         STORE;                                                                                                          \
         cur -= tot;                                                                                                     \
     }
     if (out_aligned) {
-        uint32_t *ow = reinterpret_cast<uint32_t *>(out) + lane;
-        for (; i0 + 128 <= body; i0 += 128, ow += 32) SHD_ROUND(*ow = sy)
+        uint32_t *const ow = reinterpret_cast<uint32_t *>(out);              // warp uniform; the index stays 32 bits wide
+        for (; i0 + 128 <= body; i0 += 128) SHD_ROUND(ow[(i0 >> 2) + (uint32_t)lane] = sy)
     } else {
         uint8_t *ob = out + 4 * lane;
         for (; i0 + 128 <= body; i0 += 128, ob += 128)
@@ -181,22 +192,22 @@ __device__ __forceinline__ int sh_decode_payload_warp(const uint8_t *pay, uint32
             uint32_t lo, hi;
             ring_bits64(cur - incl, lo, hi);
             const uint64_t w = ((uint64_t)hi << 32) | lo;
-            if (ia < body) { out[ia] = (uint8_t)(e0 >> 20); a0 = SHD_NEXT(e0, (uint32_t)(w >> n123), n0); }
-            if (ia + 1 < body) { out[ia + 1] = (uint8_t)(e1 >> 20); a1 = SHD_NEXT(e1, (uint32_t)(w >> n23), n1); }
-            if (ia + 2 < body) { out[ia + 2] = (uint8_t)(e2 >> 20); a2 = SHD_NEXT(e2, (uint32_t)(w >> n3), n2); }
-            if (ia + 3 < body) { out[ia + 3] = (uint8_t)(e3 >> 20); a3 = SHD_NEXT(e3, (uint32_t)w, n3); }
+            if (ia < body) { out[ia] = (uint8_t)SHD_SYM(e0); a0 = SHD_NEXT(e0, (uint32_t)(w >> n123), n0); }
+            if (ia + 1 < body) { out[ia + 1] = (uint8_t)SHD_SYM(e1); a1 = SHD_NEXT(e1, (uint32_t)(w >> n23), n1); }
+            if (ia + 2 < body) { out[ia + 2] = (uint8_t)SHD_SYM(e2); a2 = SHD_NEXT(e2, (uint32_t)(w >> n3), n2); }
+            if (ia + 3 < body) { out[ia + 3] = (uint8_t)SHD_SYM(e3); a3 = SHD_NEXT(e3, (uint32_t)w, n3); }
             cur -= tot;
         }
     }
 #undef SHD_NEXT
 #undef SHD_NB
-#undef SHD_SYM
     if (!bad) {                                             // Decoder::finish, fse.rs:383-385: i in [body, bn), state i % 128
-        out[body + ((4 * lane - body) & 127)] = (uint8_t)(lds_u32(a0) >> 20);
-        out[body + ((4 * lane + 1 - body) & 127)] = (uint8_t)(lds_u32(a1) >> 20);
-        out[body + ((4 * lane + 2 - body) & 127)] = (uint8_t)(lds_u32(a2) >> 20);
-        out[body + ((4 * lane + 3 - body) & 127)] = (uint8_t)(lds_u32(a3) >> 20);
+        out[body + ((4 * lane - body) & 127)] = (uint8_t)SHD_SYM(lds_u32(a0));
+        out[body + ((4 * lane + 1 - body) & 127)] = (uint8_t)SHD_SYM(lds_u32(a1));
+        out[body + ((4 * lane + 2 - body) & 127)] = (uint8_t)SHD_SYM(lds_u32(a2));
+        out[body + ((4 * lane + 3 - body) & 127)] = (uint8_t)SHD_SYM(lds_u32(a3));
     }
+#undef SHD_SYM
     if (pending) {                                          // never leave a copy in flight into memory the next stream reuses
         tma_ok = tma_ok && mbar_wait(wk.bar, wk.par);
         wk.par ^= 1;
