@@ -141,29 +141,36 @@ __global__ void __launch_bounds__(512, 2) k_decode128c_blocks(DecArgs a)
         __syncwarp();
         const uint32_t ring_saddr = (uint32_t)__cvta_generic_to_shared(ring);
         // up to 52 bits at stream position q (three ring words, 64-bit funnel)
-        auto ring_bits64 = [&](uint32_t q) -> uint64_t {
+        auto ring_lohi = [&](uint32_t q, uint32_t &lo, uint32_t &hi) {
             uint32_t ad = ring_saddr + ((q >> 3) & 0x3fcu);
             uint32_t w0, w1, w2;
             asm volatile("ld.shared.u32 %0, [%3];\n\tld.shared.u32 %1, [%3+4];\n\tld.shared.u32 %2, [%3+8];"
                          : "=r"(w0), "=r"(w1), "=r"(w2) : "r"(ad));
             uint32_t s = q & 31;
-            return ((uint64_t)__funnelshift_r(w1, w2, s) << 32) | __funnelshift_r(w0, w1, s);
+            lo = __funnelshift_r(w0, w1, s);
+            hi = __funnelshift_r(w1, w2, s);
+        };
+        auto ring_bits64 = [&](uint32_t q) -> uint64_t {
+            uint32_t lo, hi;
+            ring_lohi(q, lo, hi);
+            return ((uint64_t)hi << 32) | lo;
         };
 #if FSE_DEC_TMA
         // The ring holds words [lowq, lowq+256).  As soon as the upper half is dead, one lane starts a 512-byte
         // bulk copy of the next lower 128 words into it; the warp waits on the mbarrier only when it gets there.
-        bool pending = false, tma_ok = true;
+        uint32_t pending = 0, tma_ok = 1;                   // 32-bit flags, touched on the rare paths only
         auto stage = [&]() {
-            if (!pending && lowq && (cur >> 5) + 3 < lowq + 128) {
+            if ((cur >> 5) + 3 >= lowq + 128 || !lowq) return;     // one test per round: nothing to do in the upper half
+            if (!pending) {
                 __syncwarp();
                 if (lane == 0) bulk_g2s(ring_saddr + (((lowq - 128) & 255) << 2), origin + (lowq - 128), 512, bar);
-                pending = true;
+                pending = 1;
             }
-            if (pending && (cur >> 5) < lowq + 56) {               // a round takes at most 52 words
-                tma_ok = tma_ok && mbar_wait(bar, par);
+            if ((cur >> 5) < lowq + 56) {                          // a round takes at most 52 words
+                if (!mbar_wait(bar, par)) tma_ok = 0;
                 par ^= 1;
                 lowq -= 128;
-                pending = false;
+                pending = 0;
                 if ((lowq & 255) == 0) {                            // slots 0 and 1 changed: refresh their mirror
                     __syncwarp();
                     if (lane < 2) ring[256 + lane] = ring[lane];
@@ -197,32 +204,42 @@ __global__ void __launch_bounds__(512, 2) k_decode128c_blocks(DecArgs a)
         cur -= N * log2;
         const uint32_t body = bn - N;
         const bool out_aligned = (((uintptr_t)out) & 3) == 0;
-        bool bad = false;
+        uint32_t bad = 0;
         uint32_t i0 = 0;
-        for (; i0 + 128 <= body; i0 += 128) {
-            stage();
-            // fse.rs:363-373, four chains.  new_state + bits is an OR: the entry's base is a multiple of 1 << num_bits
-            uint32_t e0 = lds_u16(tab_saddr + s0 * 2), e1 = lds_u16(tab_saddr + s1 * 2);
-            uint32_t e2 = lds_u16(tab_saddr + s2 * 2), e3 = lds_u16(tab_saddr + s3 * 2);
-            uint32_t y0 = lds_u8(sym_saddr + s0), y1 = lds_u8(sym_saddr + s1), y2 = lds_u8(sym_saddr + s2), y3 = lds_u8(sym_saddr + s3);
-            uint32_t n0 = e0 >> 12, n1 = e1 >> 12, n2 = e2 >> 12, n3 = e3 >> 12;
-            uint32_t n23 = n2 + n3, n123 = n1 + n23, nbs = n0 + n123;
-            uint32_t incl = warp_incl_add_pred(nbs);
-            uint64_t w = ring_bits64(cur - incl);           // state 4l's bits are the uppermost of the lane's window
-            uint32_t tot = __shfl_sync(FULL, incl, 31);
-            if (tot > cur - floor_bits) { bad = true; break; }
-            s0 = (e0 & 0xfffu) | ((uint32_t)(w >> n123) & ~(0xffffffffu << n0));
-            s1 = (e1 & 0xfffu) | ((uint32_t)(w >> n23) & ~(0xffffffffu << n1));
-            s2 = (e2 & 0xfffu) | ((uint32_t)(w >> n3) & ~(0xffffffffu << n2));
-            s3 = (e3 & 0xfffu) | ((uint32_t)w & ~(0xffffffffu << n3));
-            uint32_t sy = y0 | (y1 << 8) | (y2 << 16) | (y3 << 24);
-            if (out_aligned) *reinterpret_cast<uint32_t *>(out + i0 + 4 * lane) = sy;
-            else {
-                out[i0 + 4 * lane] = (uint8_t)sy; out[i0 + 4 * lane + 1] = (uint8_t)(sy >> 8);
-                out[i0 + 4 * lane + 2] = (uint8_t)(sy >> 16); out[i0 + 4 * lane + 3] = (uint8_t)(sy >> 24);
-            }
-            cur -= tot;
+        // one full round: fse.rs:363-373 on four chains per lane.  new_state + bits is an OR: the entry's base is a multiple of
+        // 1 << num_bits.  The four fields come from three funnel shifts of the lane's 64-bit window (n23 <= 24).
+#define DEC128C_ROUND(STORE)                                                                                                  \
+        {                                                                                                                     \
+            stage();                                                                                                          \
+            const uint32_t e0 = lds_u16(tab_saddr + s0 * 2), e1 = lds_u16(tab_saddr + s1 * 2);                                  \
+            const uint32_t e2 = lds_u16(tab_saddr + s2 * 2), e3 = lds_u16(tab_saddr + s3 * 2);                                  \
+            const uint32_t y0 = lds_u8(sym_saddr + s0), y1 = lds_u8(sym_saddr + s1), y2 = lds_u8(sym_saddr + s2), y3 = lds_u8(sym_saddr + s3); \
+            const uint32_t n0 = e0 >> 12, n1 = e1 >> 12, n2 = e2 >> 12, n3 = e3 >> 12;                                          \
+            const uint32_t n23 = n2 + n3, nbs = n0 + n1 + n23;                                                                  \
+            const uint32_t incl = warp_incl_add_pred(nbs);                                                                      \
+            uint32_t lo, hi;                                                                                                    \
+            ring_lohi(cur - incl, lo, hi);              /* state 4l's bits are the uppermost of the lane's window */            \
+            const uint32_t tot = __shfl_sync(FULL, incl, 31);                                                                   \
+            if (tot > cur - floor_bits) { bad = 1; break; }                                                                     \
+            const uint32_t w2 = __funnelshift_r(lo, hi, n3), w1 = __funnelshift_r(lo, hi, n23);                                 \
+            const uint32_t w0 = __funnelshift_r(w1, hi >> n23, n1);                                                             \
+            s0 = (e0 & 0xfffu) | (w0 & ~(0xffffffffu << n0));                                                                   \
+            s1 = (e1 & 0xfffu) | (w1 & ~(0xffffffffu << n1));                                                                   \
+            s2 = (e2 & 0xfffu) | (w2 & ~(0xffffffffu << n2));                                                                   \
+            s3 = (e3 & 0xfffu) | (lo & ~(0xffffffffu << n3));                                                                   \
+            const uint32_t sy = __byte_perm(__byte_perm(y0, y1, 0x0040), __byte_perm(y2, y3, 0x0040), 0x5410);                  \
+            STORE;                                                                                                              \
+            cur -= tot;                                                                                                         \
         }
+        if (out_aligned) {
+            uint32_t *const ow = reinterpret_cast<uint32_t *>(out);          // warp uniform; the index stays 32 bits wide
+            for (; i0 + 128 <= body; i0 += 128) DEC128C_ROUND(ow[(i0 >> 2) + (uint32_t)lane] = sy)
+        } else {
+            for (; i0 + 128 <= body; i0 += 128)
+                DEC128C_ROUND(out[i0 + 4 * lane] = (uint8_t)sy; out[i0 + 4 * lane + 1] = (uint8_t)(sy >> 8);
+                              out[i0 + 4 * lane + 2] = (uint8_t)(sy >> 16); out[i0 + 4 * lane + 3] = (uint8_t)(sy >> 24))
+        }
+#undef DEC128C_ROUND
         if (!bad && i0 < body) {                            // last partial round
             stage();
             uint32_t ia = i0 + 4 * lane;
@@ -232,7 +249,7 @@ __global__ void __launch_bounds__(512, 2) k_decode128c_blocks(DecArgs a)
             uint32_t n23 = n2 + n3, n123 = n1 + n23, nbs = n0 + n123;
             uint32_t incl = warp_incl_add_pred(nbs);
             uint32_t tot = __shfl_sync(FULL, incl, 31);
-            if (tot > cur - floor_bits) bad = true;
+            if (tot > cur - floor_bits) bad = 1;
             else {
                 uint64_t w = ring_bits64(cur - incl);
                 if (ia < body) { out[ia] = sym[s0]; s0 = (e0 & 0xfffu) | ((uint32_t)(w >> n123) & ~(0xffffffffu << n0)); }
@@ -250,10 +267,10 @@ __global__ void __launch_bounds__(512, 2) k_decode128c_blocks(DecArgs a)
         }
 #if FSE_DEC_TMA
         if (pending) {                                      // never leave a copy in flight into memory the next block reuses
-            tma_ok = tma_ok && mbar_wait(bar, par);
+            if (!mbar_wait(bar, par)) tma_ok = 0;
             par ^= 1;
         }
-        if (!tma_ok) bad = true;
+        if (!tma_ok) bad = 1;
 #endif
         cur -= floor_bits;
         if (bad || cur != 0) st = ST_LENGTH;

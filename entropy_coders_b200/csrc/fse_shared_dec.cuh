@@ -102,7 +102,7 @@ __device__ __forceinline__ int sh_decode_payload_warp(const uint8_t *pay, uint32
         lo = __funnelshift_r(w0, w1, s);
         hi = __funnelshift_r(w1, w2, s);
     };
-    bool pending = false, tma_ok = true;
+    uint32_t pending = 0, tma_ok = 1;                        // 32-bit flags: touched on the rare paths only, no bool packing per round
     // The ring holds words [lowq, lowq + 256).  One test per round covers both stages of the refill: nothing to do while
     // the cursor is in the upper half.  Below it, one lane starts a 512-byte bulk copy (TMA) of the next lower 128 words
     // into the dead upper half, and the warp waits on the mbarrier only when a round could reach below lowq.
@@ -111,13 +111,13 @@ __device__ __forceinline__ int sh_decode_payload_warp(const uint8_t *pay, uint32
         if (!pending) {
             __syncwarp();
             if (lane == 0) bulk_g2s(ring_saddr + (((lowq - 128) & 255) << 2), origin + (lowq - 128), 512, wk.bar);
-            pending = true;
+            pending = 1;
         }
         if ((cur >> 5) < lowq + 56) {                          // a round takes at most 52 words
-            tma_ok = tma_ok && mbar_wait(wk.bar, wk.par);
+            if (!mbar_wait(wk.bar, wk.par)) tma_ok = 0;
             wk.par ^= 1;
             lowq -= 128;
-            pending = false;
+            pending = 0;
             if ((lowq & 255) == 0) {
                 __syncwarp();
                 if (lane < 2) ring[256 + lane] = ring[lane];
@@ -141,7 +141,7 @@ __device__ __forceinline__ int sh_decode_payload_warp(const uint8_t *pay, uint32
     cur -= N * log2;
     const uint32_t body = bn - N;
     const bool out_aligned = (((uintptr_t)out) & 3) == 0;
-    bool bad = false;
+    uint32_t bad = 0;
     uint32_t i0 = 0;
     // next row address: the row of new_state (in the entry) | lane part, plus the bits read; the product is an IMAD (FMA pipe)
 #define SHD_NEXT(e, win, n) shd_next<SH>(e, win, n, lanepart)
@@ -158,7 +158,7 @@ __device__ __forceinline__ int sh_decode_payload_warp(const uint8_t *pay, uint32
         uint32_t lo, hi;                                                                                                \
         ring_bits64(cur - incl, lo, hi);        /* state 4l's bits are the uppermost of the lane's window */            \
         const uint32_t tot = __shfl_sync(FULL, incl, 31);                                                               \
-        if (tot > cur - floor_bits) { bad = true; break; }                                                              \
+        if (tot > cur - floor_bits) { bad = 1; break; }                                                                 \
         const uint32_t w2 = __funnelshift_r(lo, hi, n3), w1 = __funnelshift_r(lo, hi, n23);   /* n23 <= 22 */           \
         const uint32_t w0 = __funnelshift_r(w1, hi >> n23, n1);                                                         \
         a3 = SHD_NEXT(e3, lo, n3);                                                                                      \
@@ -187,7 +187,7 @@ __device__ __forceinline__ int sh_decode_payload_warp(const uint8_t *pay, uint32
         const uint32_t n23 = n2 + n3, n123 = n1 + n23, nbs = n0 + n123;
         const uint32_t incl = warp_incl_add_pred(nbs);
         const uint32_t tot = __shfl_sync(FULL, incl, 31);
-        if (tot > cur - floor_bits) bad = true;
+        if (tot > cur - floor_bits) bad = 1;
         else {
             uint32_t lo, hi;
             ring_bits64(cur - incl, lo, hi);
@@ -209,10 +209,10 @@ __device__ __forceinline__ int sh_decode_payload_warp(const uint8_t *pay, uint32
     }
 #undef SHD_SYM
     if (pending) {                                          // never leave a copy in flight into memory the next stream reuses
-        tma_ok = tma_ok && mbar_wait(wk.bar, wk.par);
+        if (!mbar_wait(wk.bar, wk.par)) tma_ok = 0;
         wk.par ^= 1;
     }
-    if (!tma_ok) bad = true;
+    if (!tma_ok) bad = 1;
     cur -= floor_bits;
     return (bad || cur != 0) ? ST_LENGTH : ST_OK;
 }

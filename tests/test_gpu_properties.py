@@ -214,3 +214,69 @@ def test_corrupted_streams_exhaust_mode_never_fault(ctx):
                 exp = None
             if exp is not None and st[i] == 0:
                 assert out_len[i] == len(exp) and out.cpu().numpy()[i, :len(exp)].tobytes() == exp, (trial, i)
+
+
+@settings(max_examples=60 * SCALE, **COMMON)
+@given(byte_strings(min_size=1, max_size=60000), st.sampled_from([(4096, 512), (8192, 1024), (16384, 2048), (32768, 8192), (2048, 2048)]),
+       st.sampled_from([0, 0, 5, 9, 11]), st.integers(0, 15))
+def test_segmented_mode_equals_the_oracle_composition(ctx, data, shape, tl, shift):
+    """segment_size > 0 (CTA-owned replicated tables, builder warp + coder warps): generated data, block / segment shapes,
+    table_log and misaligned sources; every stream equals the oracle's composition and decode returns the input"""
+    import torch
+    from test_gpu_parity import oracle_segments
+    bs, seg = shape
+    buf = torch.empty(data.size + 16, dtype=torch.uint8, device=ctx.device)
+    view = buf[shift:shift + data.size]
+    view.copy_(torch.from_numpy(np.ascontiguousarray(data)))
+    try:
+        exp, est = oracle_segments(data, bs, seg, tl)
+    except AssertionError:
+        return                                               # a block the oracle's normalise rejects for this table_log
+    d, off, st_, total = ctx.compress_blocks(view, bs, tl, 128, segment_size=seg)
+    offh = off.cpu().numpy().astype(np.int64)
+    raw = d[:total].cpu().numpy().tobytes()
+    sth = st_.cpu().numpy()
+    assert len(offh) - 1 == len(exp)
+    for s_, e in enumerate(exp):
+        if est[s_] in (0, 1, 2) and sth[s_] == est[s_]:
+            assert raw[offh[s_]:offh[s_ + 1]] == e, (s_, bs, seg, tl)
+        else:
+            assert sth[s_] == est[s_], (s_, sth[s_], est[s_])
+    out, dst_ = ctx.decompress_blocks(d, total, off, data.size, bs, tl, 128, segment_size=seg)
+    assert (dst_.cpu().numpy() >= 0).all() and np.array_equal(out.cpu().numpy(), data)
+
+
+@settings(max_examples=60 * SCALE, **COMMON)
+@given(byte_strings(min_size=200, max_size=60000), st.sampled_from([130, 1000, 4096, 20000]), st.sampled_from([0, 5, 8, 10, 11]),
+       st.integers(0, 15))
+def test_global_table_mode_equals_the_oracle(ctx, data, bs, tl, shift):
+    """one table for the whole input (CTA-owned bank-replicated tables for table_log <= 11, 32 / 16 copies): header and every
+    header-less block equal the oracle's, any alignment, ragged tail"""
+    import torch
+    h = O.histogram(data)
+    if h.table_len <= 1:
+        return
+    if tl == 0:
+        rc, tle = O.optimal_log2(h)
+        if rc < 0:
+            return
+    else:
+        tle = tl
+    rc, nh = O.normalize(h, tle)
+    if rc < 0 or nh.log2 > 11:
+        return
+    buf = torch.empty(data.size + 16, dtype=torch.uint8, device=ctx.device)
+    view = buf[shift:shift + data.size]
+    view.copy_(torch.from_numpy(np.ascontiguousarray(data)))
+    header, log2 = ctx.set_global_table(ctx.histogram_global(view), tl)
+    assert log2 == nh.log2 and header == O.ncount_write(nh)[0]
+    d, off, st_, total = ctx.compress_blocks(view, bs, tl, 128, table_mode=1)
+    offh = off.cpu().numpy().astype(np.int64)
+    raw = d[:total].cpu().numpy().tobytes()
+    et = O.enc_table(nh)
+    for b in range(len(offh) - 1):
+        blk = data[b * bs:(b + 1) * bs]
+        e = blk.tobytes() if len(blk) < 128 else O.encode_payload(et, blk, 128)[0]
+        assert raw[offh[b]:offh[b + 1]] == e, (b, bs, tl)
+    out, dst_ = ctx.decompress_blocks(d, total, off, data.size, bs, tl, 128, table_mode=1)
+    assert (dst_.cpu().numpy() >= 0).all() and np.array_equal(out.cpu().numpy(), data)
