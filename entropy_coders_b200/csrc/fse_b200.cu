@@ -246,7 +246,6 @@ int fse_b200_create(int device, void *stream, fse_b200_ctx **out)
     cudaFuncSetAttribute(k_encode64_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
     cudaFuncSetAttribute(k_decode64_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
     cudaFuncSetAttribute(k_decode64c_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
-    cudaFuncSetAttribute(k_decode64w_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
     cudaFuncSetAttribute(k_decode128_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 64);   // 16 bytes of static shared memory (block queue)
     cudaFuncSetAttribute(k_decode128c_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 64);   // 16 bytes of static shared memory (block queue)
     cudaFuncSetAttribute(k_encode128_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 64);   // 16 bytes of static shared memory (block queue)
@@ -783,19 +782,17 @@ int fse_b200_decompress_blocks_async(fse_b200_ctx *ctx, const uint8_t *d_comp, s
         CK(cudaGetLastError());
         return FSE_B200_OK;
     }
-    const bool use_wide = dev_opt("FSE_B200_DECODE64_WIDE", 0) != 0;   // measured: compact 0.49 ms vs wide 0.70 ms on c2
-    if (p->n_states == 64 && (tlmax <= 12 || use_wide)) {
-        // two CTAs per SM, each with half of the SM's shared memory
+    if (p->n_states == 64 && tlmax <= 12) {
+        // compact tables, two CTAs per SM, each with half of the SM's shared memory (wide entries measured 0.70 vs 0.49 ms on c2)
         const size_t half = ctx->smem_per_sm / 2 - 1024;            // 1 KiB per CTA is reserved by the runtime
-        const size_t per_warp = (use_wide || tlmax > 12) ? dec64w_layout(tlmax).total : dec64c_layout(tlmax).total;
+        const size_t per_warp = dec64c_layout(tlmax).total;
         int wpc = pick_warps(nblocks, ctx->num_sms * 2, per_warp, std::min(half, ctx->smem_optin), 16);
         int ctas = 2;
         if (wpc < 1) { wpc = pick_warps(nblocks, ctx->num_sms, per_warp, ctx->smem_optin, 16); ctas = 1; }
         if (wpc < 1) return fail(ctx, FSE_B200_ERR_UNSUPPORTED, "table_log too large for shared memory");
         int grid = (int)std::min<size_t>((nblocks + wpc - 1) / wpc, (size_t)ctx->num_sms * ctas);
         Timed t(ctx, FSE_B200_K_DECODE);
-        if (use_wide || tlmax > 12) k_decode64w_blocks<<<grid, wpc * 32, (size_t)wpc * per_warp, ctx->stream>>>(a);
-        else k_decode64c_blocks<<<grid, wpc * 32, (size_t)wpc * per_warp, ctx->stream>>>(a);
+        k_decode64c_blocks<<<grid, wpc * 32, (size_t)wpc * per_warp, ctx->stream>>>(a);
     } else {
         const DecLayout lay = dec_layout(tlmax);
         int wpc = pick_warps(nblocks, ctx->num_sms, lay.total, ctx->smem_optin, 16);
