@@ -176,12 +176,20 @@ size_t num_streams(size_t n, const fse_b200_params *p)
 // ilog2(table_len-1)+2 <= 9 (src/histogram.rs:96-98)
 uint32_t tlmax_for(const fse_b200_params *p) { return p->table_log == 0 ? 11u : std::max(p->table_log, 9u); }
 
-size_t pay_cap_bytes(uint32_t block_size, uint32_t n_states)
+// Payload capacity of one stream.  A stream coded with the table of ITS OWN bytes cannot grow past compress_bound
+// (src/fse.rs:191-193).  A stream coded with a table made from other bytes as well (global table, segments of a block)
+// can cost up to table_log bits per symbol, whatever it holds: the slot is sized for that.
+size_t pay_cap_bytes(const fse_b200_params *p)
 {
-    size_t v = (size_t)block_size + (block_size >> 7) + 2 * (size_t)n_states + 64;
+    const size_t sb = stream_bytes(p), ns = p->n_states ? p->n_states : 32;
+    size_t v = sb + (sb >> 7) + 2 * ns + 64;
+    if (p->table_mode == FSE_B200_TABLE_GLOBAL || p->segment_size) {
+        const size_t tl = p->table_log ? std::max<size_t>(p->table_log, 10) : 11;   // the effective table_log may be raised to 10 (histogram.rs:96-98)
+        v = std::max(v, (sb * tl + 7) / 8 + 2 * ns + 64);
+    }
     return (v + 15) & ~(size_t)15;
 }
-size_t scratch_stride(uint32_t block_size, uint32_t n_states) { return HDR_RESERVE + pay_cap_bytes(block_size, n_states); }
+size_t scratch_stride(const fse_b200_params *p) { return HDR_RESERVE + pay_cap_bytes(p); }
 
 // pick warps per CTA so that the last wave of blocks is as full as possible
 int pick_warps(size_t nblocks, int num_sms, size_t per_warp_smem, size_t smem_limit, int max_warps)
@@ -324,7 +332,7 @@ size_t fse_b200_num_streams(size_t n, const fse_b200_params *p) { return p && p-
 size_t fse_b200_compress_blocks_bound(size_t n, const fse_b200_params *p)
 {
     if (!p || !p->block_size) return 0;
-    return num_streams(n, p) * scratch_stride((uint32_t)stream_bytes(p), p->n_states ? p->n_states : 32) + 16;
+    return num_streams(n, p) * scratch_stride(p) + 16;
 }
 
 // ---------------------------------------------------------------------------------- stages
@@ -540,6 +548,8 @@ static int install_global(fse_b200_ctx *ctx, const uint32_t *meta, uint32_t *h_l
     int rc = build_tables(ctx, ctx->g_norm.as<int32_t>(), m, m + 1, 1, log2, 0, ctx->g_enc_table.as<uint16_t>(),
                           ctx->g_enc_tt.as<uint2>(), nullptr, nullptr, reinterpret_cast<int32_t *>(m + 3), false);
     if (rc) return rc;
+    k_sanitize_global_tt<<<1, 256, 0, ctx->stream>>>(ctx->g_enc_tt.as<uint2>(), ctx->g_norm.as<int32_t>(), log2);
+    ctx->launches++;
     rc = build_tables(ctx, ctx->g_norm.as<int32_t>(), m, m + 1, 1, log2, 1, nullptr, nullptr, nullptr,
                       ctx->g_dec_table.as<uint32_t>(), reinterpret_cast<int32_t *>(m + 3), false);
     if (rc) return rc;
@@ -628,7 +638,9 @@ int fse_b200_compress_blocks_async(fse_b200_ctx *ctx, const uint8_t *d_src, size
         return FSE_B200_OK;
     }
     const uint32_t tlmax = global ? ctx->g_log2 : tlmax_for(p);
-    const size_t stride = scratch_stride((uint32_t)stream_bytes(p), p->n_states);
+    if (global && ctx->g_log2 > (p->table_log ? std::max(p->table_log, 10u) : 11u))
+        return fail(ctx, FSE_B200_ERR_ARG, "global table: pass the table_log the table was installed with (it sizes the block slots)");
+    const size_t stride = scratch_stride(p);
     CK(ctx->hlen.reserve(ns * 4));
     CK(ctx->plen.reserve(ns * 4));
     CK(ctx->scratch.reserve(ns * stride));
@@ -642,7 +654,7 @@ int fse_b200_compress_blocks_async(fse_b200_ctx *ctx, const uint8_t *d_src, size
     a.req_log2 = p->table_log; a.n_states = p->n_states; a.tlmax = tlmax;
     a.counts = ctx->counts.as<uint32_t>();
     a.scratch = ctx->scratch.as<uint8_t>(); a.stride = stride;
-    a.pay_cap_words = (uint32_t)(pay_cap_bytes((uint32_t)stream_bytes(p), p->n_states) / 4);
+    a.pay_cap_words = (uint32_t)(pay_cap_bytes(p) / 4);
     a.seg_size = p->segment_size; a.segs_per_block = p->segment_size ? p->block_size / p->segment_size : 1;
     a.flags = p->flags;
     a.hlen = ctx->hlen.as<uint32_t>(); a.plen = ctx->plen.as<uint32_t>(); a.status = d_status;

@@ -763,6 +763,16 @@ __global__ void __launch_bounds__(32) k_build_tables(const int32_t *__restrict__
     }
 }
 
+// Global-table mode: a symbol the installed table gives no probability must not be able to take a coder outside its
+// tables (its reference transform, fse.rs:170, indexes past the next-state table, and the entries of symbols >= table_len
+// are zero).  Such symbols get a transform with num_bits = table_log and next state = table[0]: what a block that
+// contains one encodes to cannot be decoded (include/fse_b200.h says so, like the crate), but nothing can fault.
+__global__ void k_sanitize_global_tt(uint2 *tt, const int32_t *__restrict__ norm, uint32_t log2)
+{
+    const uint32_t i = threadIdx.x;
+    if (i < 256 && norm[i] == 0) tt[i] = make_uint2((log2 << 16) - (1u << log2), 0xffffffffu);
+}
+
 // widen uint32 counts to uint64 (stage API / global table plumbing)
 __global__ void k_widen_counts(const uint32_t *__restrict__ in, unsigned long long *out, size_t count)
 {

@@ -28,10 +28,14 @@ constexpr uint32_t SH_TL_MAX = 11;
 constexpr uint32_t SH_FS_BIAS = 2048;
 
 // reference transform {bits, find_state} (fse.rs:165-188) -> P
-__device__ __forceinline__ uint32_t sh_pack_tt(uint2 t)
+// A symbol the table does not know (count 0: bits = ((log2 + 1) << 16) - size, fse.rs:170) would code log2 + 1 bits per
+// occurrence; it is clamped to log2 so that a quad never exceeds 4 * log2 bits, the size the lane strings are made for
+// (such a block is undecodable either way: see fse_b200_set_global_table in include/fse_b200.h).
+__device__ __forceinline__ uint32_t sh_pack_tt(uint2 t, uint32_t log2)
 {
-    const uint32_t mbo = (t.x + 65535u) >> 16;                 // bits = (mbo << 16) - y, 0 < y <= 2 * size
+    uint32_t mbo = (t.x + 65535u) >> 16;                       // bits = (mbo << 16) - y, 0 < y <= 2 * size
     const uint32_t y = (mbo << 16) - t.x;
+    mbo = min(mbo, log2);
     const uint32_t H = (mbo << 13) - y;
     return (H << 12) | ((t.y + SH_FS_BIAS) & 0xfffu);
 }
@@ -288,7 +292,7 @@ __device__ __forceinline__ void sh_replicate_enc(const uint16_t *__restrict__ ta
         reinterpret_cast<uint4 *>(tabR)[i] = make_uint4(w, w, w, w);
     }
     for (uint32_t i = tid; i < 256 * 8; i += nthr) {
-        const uint32_t w = sh_pack_tt(tt[i >> 3]);
+        const uint32_t w = sh_pack_tt(tt[i >> 3], log2);
         reinterpret_cast<uint4 *>(ttR)[i] = make_uint4(w, w, w, w);
     }
 }

@@ -973,3 +973,25 @@ def test_crate_decompress_of_highly_skewed_data():
     n = E.fse_decompress2(bytes(comp), out)
     assert n == len(src) and bytes(out) == src.tobytes()
     assert bytes(comp) == O.ref_compress2(src)
+
+
+def test_global_table_with_unknown_symbols_is_memory_safe(ctx):
+    """a byte the installed global table gives no probability (the table was built from other data).  Like the
+    crate's Encoder the kernels do not look for it (documented in fse_b200.h); what must hold is that nothing faults,
+    no other block is disturbed, and every block WITHOUT such a byte still round-trips."""
+    bs = 16384
+    a = O.generate("few", 21, 40 * bs)                       # symbols 0..3 only
+    b = a.copy()
+    b[5 * bs + 100: 5 * bs + 4000] = 77                        # block 5 and block 17 get bytes the table does not know
+    b[17 * bs: 18 * bs] = 200
+    header, log2 = ctx.set_global_table(ctx.histogram_global(dev(ctx, a)), 11)
+    d, off, st, total = ctx.compress_blocks(dev(ctx, b), bs, 11, 128, table_mode=1)
+    out, st2 = ctx.decompress_blocks(d, total, off, b.size, bs, 11, 128, table_mode=1)
+    o = out.cpu().numpy()
+    for blk in range(40):
+        if blk not in (5, 17):
+            assert np.array_equal(o[blk * bs:(blk + 1) * bs], b[blk * bs:(blk + 1) * bs]), blk
+    # and the context is still healthy
+    d, off, st, total = ctx.compress_blocks(dev(ctx, a), bs, 11, 128, table_mode=1)
+    out, st2 = ctx.decompress_blocks(d, total, off, a.size, bs, 11, 128, table_mode=1)
+    assert np.array_equal(out.cpu().numpy(), a) and (st2.cpu().numpy() >= 0).all()
