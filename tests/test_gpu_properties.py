@@ -280,3 +280,54 @@ def test_global_table_mode_equals_the_oracle(ctx, data, bs, tl, shift):
         assert raw[offh[b]:offh[b + 1]] == e, (b, bs, tl)
     out, dst_ = ctx.decompress_blocks(d, total, off, data.size, bs, tl, 128, table_mode=1)
     assert (dst_.cpu().numpy() >= 0).all() and np.array_equal(out.cpu().numpy(), data)
+
+
+@pytest.mark.parametrize("mode", ["global", "segmented"])
+def test_corrupted_streams_never_fault_shared_tables(ctx, mode):
+    """the seeded fuzz of test_corrupted_streams_never_fault through the CTA-owned-table decoders (global table; segmented
+    per-block mode with its builder warp): every stream ends with a status, nothing faults, untouched streams decode, and
+    an intact input still round-trips afterwards"""
+    rng = np.random.default_rng(99 + len(mode))
+    bs, nb = 8192, 6
+    src = O.generate("text", 78, bs * nb)
+    kw = dict(table_mode=1) if mode == "global" else dict(segment_size=1024)
+    tl = 11 if mode == "global" else 0
+    if mode == "global":
+        ctx.set_global_table(ctx.histogram_global(dev(ctx, src)), tl)
+    d, off, st, total = ctx.compress_blocks(dev(ctx, src), bs, tl, 128, **kw)
+    good = d[:total].cpu().numpy().copy()
+    offh = off.cpu().numpy().astype(np.int64)
+    ns = len(offh) - 1
+    unit = bs if mode == "global" else 1024
+    for trial in range(150):
+        bad, boff = good.copy(), offh.copy()
+        kind = trial % 5
+        if kind == 0:
+            for _ in range(int(rng.integers(1, 6))):
+                bad[int(rng.integers(0, bad.size))] ^= np.uint8(1 << int(rng.integers(0, 8)))
+        elif kind == 1:
+            b = int(rng.integers(0, ns))
+            k = int(rng.integers(1, 40))
+            bad[boff[b]:boff[b] + k] = rng.integers(0, 256, k, dtype=np.uint8)[:max(0, min(k, bad.size - boff[b]))]
+        elif kind == 2:
+            b = int(rng.integers(0, ns))
+            k = int(min(rng.integers(1, 64), boff[b + 1] - boff[b]))
+            if k:
+                bad[boff[b + 1] - k:boff[b + 1]] = 0 if trial % 2 else rng.integers(0, 256, k, dtype=np.uint8)
+        elif kind == 3:
+            b = int(rng.integers(1, ns))
+            boff[b] = int(np.clip(boff[b] + rng.integers(-300, 300), boff[b - 1], boff[b + 1]))
+        else:
+            b = int(rng.integers(0, ns))
+            a = int(rng.integers(boff[b], boff[b + 1]))
+            bad[a:min(a + int(rng.integers(1, 2000)), boff[b + 1])] = np.uint8(rng.integers(0, 256))
+        out, st2 = ctx.decompress_blocks(dev(ctx, bad), bad.size, dev(ctx, boff), src.size, bs, tl, 128, **kw)
+        st2 = st2.cpu().numpy()
+        assert st2.shape[0] == ns and ((st2 <= 2) & (st2 >= -11)).all(), (trial, st2)
+        if mode == "global" and kind in (0, 1, 2, 4):        # (in segmented mode a damaged header takes its whole block along)
+            outh = out.cpu().numpy()
+            for b in range(ns):
+                if np.array_equal(bad[boff[b]:boff[b + 1]], good[offh[b]:offh[b + 1]]):
+                    assert st2[b] == 0 and np.array_equal(outh[b * unit:(b + 1) * unit], src[b * unit:(b + 1) * unit]), (trial, b)
+    out, st3 = ctx.decompress_blocks(dev(ctx, good), good.size, dev(ctx, offh), src.size, bs, tl, 128, **kw)
+    assert not st3.cpu().numpy().any() and np.array_equal(out.cpu().numpy(), src)
