@@ -471,14 +471,21 @@ def e2e_leg(env, job, steps):
         ctx2.set_global_table_from_header(hdr)
     tot = offs = None
 
+    phase = [0.0, 0.0]
+
     def e2e_step():
+        ta = time.perf_counter()
         _, o, st, t = ctx2.compress_host(hsrc, w["bs"], w["tlog"], N_STATES, w["tmode"], dst=hdst, segment_size=job.seg)
+        tb = time.perf_counter()
         ctx2.decompress_host(hdst, t, o, sample, w["bs"], w["tlog"], N_STATES, w["tmode"], dst=hout, segment_size=job.seg)
+        phase[0] += tb - ta
+        phase[1] += time.perf_counter() - tb
         return t, o
     for _ in range(2):
         e2e_step()
     ksteps = max(1, min(steps, 3 if sample > GIB else 5))
     barrier(env)
+    phase[0] = phase[1] = 0.0
     t0 = time.perf_counter()
     for _ in range(ksteps):
         tot, offs = e2e_step()
@@ -502,15 +509,38 @@ def e2e_leg(env, job, steps):
         hout[:lb].copy_(dtmp, non_blocking=True)
         ev[2].record()
         torch.cuda.synchronize()
-        bw = torch.tensor([lb / ev[0].elapsed_time(ev[1]) / 1e6, lb / ev[1].elapsed_time(ev[2]) / 1e6], dtype=torch.float64, device=env["dev"])
+        # both directions at once (what the chunked pipelines of the two calls actually see)
+        dtmp2 = torch.empty(lb, dtype=torch.uint8, device=env["dev"])
+        s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+        dv = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        barrier(env)
+        with torch.cuda.stream(s_up):
+            dv[0].record()
+            dtmp.copy_(hsrc[:lb], non_blocking=True)
+            dv[1].record()
+        with torch.cuda.stream(s_dn):
+            dv[2].record()
+            hout[:lb].copy_(dtmp2, non_blocking=True)
+            dv[3].record()
+        torch.cuda.synchronize()
+        bw = torch.tensor([lb / ev[0].elapsed_time(ev[1]) / 1e6, lb / ev[1].elapsed_time(ev[2]) / 1e6,
+                           lb / dv[0].elapsed_time(dv[1]) / 1e6, lb / dv[2].elapsed_time(dv[3]) / 1e6], dtype=torch.float64, device=env["dev"])
         if env["world"] > 1:
             torch.distributed.all_reduce(bw, op=torch.distributed.ReduceOp.MIN)
-        h2d, d2h = float(bw[0].item()), float(bw[1].item())
+        h2d, d2h, h2d_dx, d2h_dx = (float(x) for x in bw.tolist())
         moved = float(sample + tot)                          # per direction and rank: N + C each way over a round trip
+        # the two calls run one after the other (the reference's API shape): compress moves N up while C comes down,
+        # decompress moves C up while N comes down; each call is bounded by its larger transfer at the duplex rate
+        c_s = max(sample / h2d_dx, tot / d2h_dx) / 1e9
+        d_s = max(tot / h2d_dx, sample / d2h_dx) / 1e9
         link = {"h2d_GBps_min_rank": h2d, "d2h_GBps_min_rank": d2h,
+                "h2d_duplex_GBps_min_rank": h2d_dx, "d2h_duplex_GBps_min_rank": d2h_dx,
                 "round_trip_bound_GBps": env["world"] * sample / (moved / (min(h2d, d2h) * 1e9)) / 1e9,
-                "note": "pinned copies of 1 GiB each way on all ranks at once; bound = N / ((N + C) / slower direction), full duplex"}
-        del dtmp
+                "two_call_bound_GBps": env["world"] * sample / (c_s + d_s) / 1e9,
+                "note": "pinned copies of 1 GiB on all ranks at once, one direction at a time and both at once (duplex); "
+                        "round_trip_bound = N / ((N + C) / slower direction) if the two calls could overlap each other; "
+                        "two_call_bound = N / (max(N/up, C/down) + max(C/up, N/down)) at the duplex rates: the calls as the API has them, back to back"}
+        del dtmp, dtmp2
     except Exception as ex:
         link = {"error": repr(ex)}
     res = {"value": env["world"] * sample / e2e_s / 1e9 if w["scaling"] == "weak" or sample != nbytes
@@ -518,6 +548,7 @@ def e2e_leg(env, job, steps):
            "unit": "GB/s", "h2d_bytes_per_step": int(sample + tot + (snb + 1) * 8),
            "d2h_bytes_per_step": int(tot + (snb + 1) * 8 + snb * 4 + sample + snb * 4),
            "steps": ksteps, "bytes_per_rank": sample,
+           "compress_host_ms": phase[0] / ksteps * 1e3, "decompress_host_ms": phase[1] / ksteps * 1e3,
            "pcie": link, "numa_node": env.get("numa"),
            "api": "fse_b200_compress_host + fse_b200_decompress_host, pinned host buffers, rank-local data"}
     ctx2.close()

@@ -63,7 +63,7 @@ struct fse_b200_ctx {
     uint64_t launches = 0;
     std::string err;
     // workspaces
-    DevBuf counts, hlen, plen, scratch, offsets_tmp, status_tmp, misc;
+    DevBuf counts, hist_pieces, hlen, plen, scratch, offsets_tmp, status_tmp, misc;
     DevBuf stage_in, stage_out, stage_off, stage_status;  // host-buffer conveniences
     HostBuf pin;
     // global table
@@ -207,11 +207,33 @@ int pick_warps(size_t nblocks, int num_sms, size_t per_warp_smem, size_t smem_li
     return best;
 }
 
-// Histogram::new per block: 16-bit lane-private columns (one warp per block) up to 1 MiB blocks,
-// 32-bit columns (one CTA per block) beyond
-void launch_hist(fse_b200_ctx *ctx, const uint8_t *d_src, size_t n, uint32_t block_size, size_t nb, uint32_t *d_counts,
-                 uint32_t *d_table_len)
+// Histogram::new per block: 16-bit lane-private columns, one warp per block (blocks up to 1 MiB).  When the blocks are too
+// few to fill the warp slots of the machine (or larger than 1 MiB) each block is counted as k equal pieces, one warp per
+// piece, and the pieces are summed (integer sums: the result is the same).  Blocks that do not split evenly keep the
+// one-CTA-per-block kernel with 32-bit columns.
+int launch_hist(fse_b200_ctx *ctx, const uint8_t *d_src, size_t n, uint32_t block_size, size_t nb, uint32_t *d_counts,
+                uint32_t *d_table_len)
 {
+    const size_t slots = (size_t)ctx->num_sms * HIST16_WARPS;
+    uint32_t k = 1;
+    if (nb < slots || block_size > HIST16_MAX_BLOCK)
+        while ((nb * k < 2 * slots || block_size / k > HIST16_MAX_BLOCK) && block_size % (2 * k) == 0 && (block_size / (2 * k)) % 16 == 0 &&
+               block_size / (2 * k) >= 8192)
+            k *= 2;
+    if (k > 1) {
+        const uint32_t piece = block_size / k;
+        const size_t npieces = (n + piece - 1) / piece;
+        if (npieces <= 0xffffffffull) {
+            CK(ctx->hist_pieces.reserve(npieces * 256 * sizeof(uint32_t)));
+            int grid = (int)std::min<size_t>((npieces + HIST16_WARPS - 1) / HIST16_WARPS, (size_t)ctx->num_sms);
+            k_hist_blocks16<<<grid, HIST16_WARPS * 32, HIST16_SMEM, ctx->stream>>>(d_src, n, piece, (uint32_t)npieces,
+                                                                                   ctx->hist_pieces.as<uint32_t>(), nullptr);
+            k_hist_sum_pieces<<<(int)std::min<size_t>(nb, (size_t)ctx->num_sms * 8), 256, 0, ctx->stream>>>(
+                ctx->hist_pieces.as<uint32_t>(), (uint32_t)npieces, k, (uint32_t)nb, d_counts, d_table_len);
+            ctx->launches++;
+            return FSE_B200_OK;
+        }
+    }
     if (block_size <= HIST16_MAX_BLOCK) {
         int grid = (int)std::min<size_t>((nb + HIST16_WARPS - 1) / HIST16_WARPS, (size_t)ctx->num_sms);
         k_hist_blocks16<<<grid, HIST16_WARPS * 32, HIST16_SMEM, ctx->stream>>>(d_src, n, block_size, (uint32_t)nb, d_counts, d_table_len);
@@ -219,6 +241,7 @@ void launch_hist(fse_b200_ctx *ctx, const uint8_t *d_src, size_t n, uint32_t blo
         int grid = (int)std::min<size_t>(nb, (size_t)ctx->num_sms * 3);
         k_hist_blocks<<<grid, HIST_WARPS * 32, HIST_SMEM, ctx->stream>>>(d_src, n, block_size, (uint32_t)nb, d_counts, d_table_len);
     }
+    return FSE_B200_OK;
 }
 
 }  // namespace
@@ -275,7 +298,7 @@ void fse_b200_destroy(fse_b200_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf *bufs[] = {&ctx->counts, &ctx->hlen, &ctx->plen, &ctx->scratch, &ctx->offsets_tmp, &ctx->status_tmp, &ctx->misc,
+    DevBuf *bufs[] = {&ctx->counts, &ctx->hist_pieces, &ctx->hlen, &ctx->plen, &ctx->scratch, &ctx->offsets_tmp, &ctx->status_tmp, &ctx->misc,
                       &ctx->stage_in, &ctx->stage_out, &ctx->stage_off, &ctx->stage_status, &ctx->g_enc_table,
                       &ctx->g_enc_tt, &ctx->g_dec_table, &ctx->g_norm, &ctx->g_meta, &ctx->g_hdr,
                       &ctx->lut[0], &ctx->lut[1], &ctx->lut[2], &ctx->lut[3]};
@@ -345,7 +368,7 @@ int fse_b200_histogram_blocks(fse_b200_ctx *ctx, const uint8_t *d_src, size_t n,
     size_t nb = fse_b200_num_blocks(n, block_size);
     if (nb == 0) return FSE_B200_OK;
     if (nb > 0xffffffffull) return fail(ctx, FSE_B200_ERR_ARG, "too many blocks");
-    launch_hist(ctx, d_src, n, block_size, nb, d_counts, d_table_len);
+    { int hrc = launch_hist(ctx, d_src, n, block_size, nb, d_counts, d_table_len); if (hrc) return hrc; }
     ctx->launches++;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(ctx->stream));
@@ -363,7 +386,7 @@ static int hist_global_async(fse_b200_ctx *ctx, const uint8_t *d_src, size_t n, 
     CK(cudaMemsetAsync(d_counts64, 0, 256 * sizeof(uint64_t), ctx->stream));
     if (nb == 0) return FSE_B200_OK;
     CK(ctx->counts.reserve(nb * 256 * sizeof(uint32_t)));
-    launch_hist(ctx, d_src, n, piece, nb, ctx->counts.as<uint32_t>(), nullptr);
+    { int hrc = launch_hist(ctx, d_src, n, piece, nb, ctx->counts.as<uint32_t>(), nullptr); if (hrc) return hrc; }
     ctx->launches++;
     k_hist_reduce<<<(int)std::min<size_t>(nb, (size_t)ctx->num_sms * 2), 256, 0, ctx->stream>>>(ctx->counts.as<uint32_t>(), (uint32_t)nb,
                                                                           reinterpret_cast<unsigned long long *>(d_counts64));
@@ -647,7 +670,7 @@ int fse_b200_compress_blocks_async(fse_b200_ctx *ctx, const uint8_t *d_src, size
     if (!global) {
         CK(ctx->counts.reserve(nb * 256 * sizeof(uint32_t)));
         Timed t(ctx, FSE_B200_K_HIST);
-        launch_hist(ctx, d_src, n, p->block_size, nb, ctx->counts.as<uint32_t>(), nullptr);
+        { int hrc = launch_hist(ctx, d_src, n, p->block_size, nb, ctx->counts.as<uint32_t>(), nullptr); if (hrc) return hrc; }
     }
     EncArgs a;
     a.src = d_src; a.n = n; a.block_size = p->block_size; a.nblocks = (uint32_t)nb;

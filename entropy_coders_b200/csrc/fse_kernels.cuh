@@ -149,6 +149,35 @@ __global__ void k_hist_reduce(const uint32_t *__restrict__ counts, uint32_t nblo
     if (s) atomicAdd(out + bin, s);
 }
 
+// sum of the histograms of the `k` pieces of each block (large blocks are counted piecewise so that few blocks still fill
+// the machine: launch_hist) + table_len (src/histogram.rs:52-59).  One CTA of 256 threads per block.
+__global__ void __launch_bounds__(256)
+k_hist_sum_pieces(const uint32_t *__restrict__ piece_counts, uint32_t npieces, uint32_t k, uint32_t nblocks,
+                  uint32_t *__restrict__ counts, uint32_t *__restrict__ table_len)
+{
+    __shared__ int s_hi[8];
+    const uint32_t bin = threadIdx.x;
+    for (uint32_t b = blockIdx.x; b < nblocks; b += gridDim.x) {
+        const uint32_t p0 = b * k, p1 = min(npieces, p0 + k);
+        uint32_t s = 0;
+        for (uint32_t p = p0; p < p1; p++) s += piece_counts[(size_t)p * 256 + bin];
+        counts[(size_t)b * 256 + bin] = s;
+        if (table_len) {
+            int hi = s ? (int)bin : -1;
+#pragma unroll
+            for (int d = 16; d; d >>= 1) hi = max(hi, __shfl_xor_sync(FULL, hi, d));
+            if ((bin & 31) == 0) s_hi[bin >> 5] = hi;
+            __syncthreads();
+            if (bin == 0) {
+                int m = -1;
+                for (int i = 0; i < 8; i++) m = max(m, s_hi[i]);
+                table_len[b] = (uint32_t)(m < 0 ? 0 : m) + 1;
+            }
+            __syncthreads();
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // K2-K4 fused: per block  normalise -> header -> encode table -> reverse-order N-state encode.
 // One warp per block; CTAs are just containers of independent warps.

@@ -590,13 +590,20 @@ def test_exhaust_decode_matches_reference_termination(ctx, n_states):
         assert surplus >= 0
 
 
-def test_histogram_large_blocks_take_the_32bit_path(ctx):
-    """blocks above 1 MiB use 32-bit counter columns (k_hist_blocks)"""
+@pytest.mark.parametrize("block_size", [2 << 20, (2 << 20) + 48, (1 << 20) + 4099, 3 << 18, 1 << 17])
+def test_histogram_of_few_or_large_blocks(ctx, block_size):
+    """few blocks, or blocks above 1 MiB, are counted in pieces (one warp per piece, k_hist_sum_pieces); sizes that do not
+    split evenly keep 32-bit counter columns (k_hist_blocks): counts and table_len either way, ragged tail included"""
     src = O.generate("geo", 3, (5 << 20) + 99)
-    counts, tlen = ctx.histogram_blocks(dev(ctx, src), 2 << 20)
+    src[src > 200] = 7                                        # table_len below 256
+    counts, tlen = ctx.histogram_blocks(dev(ctx, src), block_size)
     counts = counts.cpu().numpy().view(np.uint32)
+    tlen = tlen.cpu().numpy()
+    assert counts.shape[0] == -(-src.size // block_size)
     for b in range(counts.shape[0]):
-        assert np.array_equal(counts[b], np.bincount(src[b * (2 << 20):(b + 1) * (2 << 20)], minlength=256))
+        exp = np.bincount(src[b * block_size:(b + 1) * block_size], minlength=256)
+        assert np.array_equal(counts[b], exp)
+        assert tlen[b] == int(np.max(np.nonzero(exp)[0])) + 1
 
 
 def test_argument_errors(ctx):
