@@ -293,6 +293,13 @@ class Context:
         self._ck(self._L.fse_b200_set_global_table_from_header(self._h, buf, len(header), C.byref(l2)))
         return int(l2.value)
 
+    def global_table_covers(self, src):
+        """-> number of bytes of src (device uint8) whose value the installed global table has no entry for (0 = every
+        block of src can be coded with it; the encode kernels themselves do not look)"""
+        unknown = C.c_uint64()
+        self._ck(self._L.fse_b200_global_table_covers(self._h, _ptr(src), src.numel(), C.byref(unknown)))
+        return int(unknown.value)
+
     # ------------------------------------------------------------------ host buffers (numpy / pinned torch)
     def compress_host(self, src, block_size, table_log=0, n_states=32, table_mode=TABLE_PER_BLOCK, dst=None, segment_size=0, flags=0):
         """src, dst: host uint8 arrays (numpy or CPU torch).  -> (dst, offsets, status, total).  A block that could not

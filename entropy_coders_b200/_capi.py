@@ -18,6 +18,7 @@ SYMBOLS = [
     "fse_b200_ncount_read", "fse_b200_build_encode_tables", "fse_b200_build_decode_tables",
     "fse_b200_compress_blocks", "fse_b200_compress_blocks_async", "fse_b200_decompress_blocks",
     "fse_b200_decompress_blocks_async", "fse_b200_decompress_exhaust", "fse_b200_set_global_table", "fse_b200_set_global_table_from_header",
+    "fse_b200_global_table_covers",
     "fse_b200_compress_host", "fse_b200_decompress_host", "fse_b200_generate",
     "fse_b200_bitstack_write", "fse_b200_bitstack_read", "fse_b200_bitstream_read",
     "fse_b200_frame_bound", "fse_b200_frame_compress_host", "fse_b200_frame_info", "fse_b200_frame_decompress_host",
@@ -83,6 +84,7 @@ def lib():
     L.fse_b200_decompress_exhaust.argtypes = [vp, vp, sz, vp, sz, PP, vp, vp, vp]
     L.fse_b200_set_global_table.argtypes = [vp, vp, u32, vp, C.POINTER(sz), C.POINTER(u32)]
     L.fse_b200_set_global_table_from_header.argtypes = [vp, vp, sz, C.POINTER(u32)]
+    L.fse_b200_global_table_covers.argtypes = [vp, vp, sz, C.POINTER(u64)]
     L.fse_b200_compress_host.argtypes = [vp, vp, sz, PP, vp, sz, vp, vp, C.POINTER(u64)]
     L.fse_b200_decompress_host.argtypes = [vp, vp, sz, vp, sz, PP, vp, sz, vp]
     L.fse_b200_generate.argtypes = [vp, i32, u64, u64, vp, sz]

@@ -641,6 +641,27 @@ int fse_b200_set_global_table_from_header(fse_b200_ctx *ctx, const uint8_t *h_he
     return install_global(ctx, meta, h_log2);
 }
 
+int fse_b200_global_table_covers(fse_b200_ctx *ctx, const uint8_t *d_src, size_t n, uint64_t *h_unknown)
+{
+    if (!ctx || (!d_src && n) || !h_unknown) return fail(ctx, FSE_B200_ERR_ARG, "global_table_covers: bad argument");
+    if (!ctx->g_valid) return fail(ctx, FSE_B200_ERR_ARG, "global table not installed");
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->misc.reserve(256 * sizeof(uint64_t)));
+    int rc = hist_global_async(ctx, d_src, n, ctx->misc.as<uint64_t>());
+    if (rc) return rc;
+    CK(ctx->pin.reserve(256 * sizeof(uint64_t) + 256 * sizeof(int32_t)));
+    uint64_t *h_counts = reinterpret_cast<uint64_t *>(ctx->pin.p);
+    int32_t *h_norm = reinterpret_cast<int32_t *>(h_counts + 256);
+    CK(cudaMemcpyAsync(h_counts, ctx->misc.p, 256 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(h_norm, ctx->g_norm.p, 256 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    uint64_t unknown = 0;
+    for (uint32_t s = 0; s < 256; s++)
+        if (s >= ctx->g_table_len || h_norm[s] == 0) unknown += h_counts[s];
+    *h_unknown = unknown;
+    return FSE_B200_OK;
+}
+
 // ---------------------------------------------------------------------------------- pipelines
 
 int fse_b200_compress_blocks_async(fse_b200_ctx *ctx, const uint8_t *d_src, size_t n, const fse_b200_params *p,

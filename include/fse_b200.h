@@ -249,6 +249,9 @@ int fse_b200_set_global_table(fse_b200_ctx *ctx, const uint64_t *d_counts64, uin
 /* The table must give every byte value that occurs in the data a non-zero count (build it from the histogram of the
  * data, as fse_b200_frame_compress_host does): like the crate's Encoder, the encode kernels do not look for symbols the
  * table does not know, and a block that contains one is reported with status 0 but cannot be decoded. */
+/* The check the encode kernels leave out: *h_unknown receives the number of bytes of d_src whose value has no entry in
+ * the installed global table (0 = every block of d_src can be coded with it).  One histogram pass over d_src. */
+int fse_b200_global_table_covers(fse_b200_ctx *ctx, const uint8_t *d_src, size_t n, uint64_t *h_unknown);
 /* Same, from a stored header (decode side). */
 int fse_b200_set_global_table_from_header(fse_b200_ctx *ctx, const uint8_t *h_header, size_t header_bytes,
                                           uint32_t *h_log2);

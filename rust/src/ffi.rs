@@ -135,6 +135,9 @@ extern "C" {
     pub fn fse_b200_set_global_table_from_header(
         ctx: *mut fse_b200_ctx, h_header: *const u8, header_bytes: usize, h_log2: *mut u32,
     ) -> c_int;
+    pub fn fse_b200_global_table_covers(
+        ctx: *mut fse_b200_ctx, d_src: *const u8, n: usize, h_unknown: *mut u64,
+    ) -> c_int;
 
     pub fn fse_b200_compress_host(
         ctx: *mut fse_b200_ctx, h_src: *const u8, n: usize, p: *const fse_b200_params, h_dst: *mut u8, dst_cap: usize,

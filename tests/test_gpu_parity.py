@@ -992,6 +992,9 @@ def test_global_table_with_unknown_symbols_is_memory_safe(ctx):
     b[5 * bs + 100: 5 * bs + 4000] = 77                        # block 5 and block 17 get bytes the table does not know
     b[17 * bs: 18 * bs] = 200
     header, log2 = ctx.set_global_table(ctx.histogram_global(dev(ctx, a)), 11)
+    # the check the kernels leave out is an entry point of its own (fse_b200_global_table_covers)
+    assert ctx.global_table_covers(dev(ctx, a)) == 0
+    assert ctx.global_table_covers(dev(ctx, b)) == 3900 + bs
     d, off, st, total = ctx.compress_blocks(dev(ctx, b), bs, 11, 128, table_mode=1)
     out, st2 = ctx.decompress_blocks(d, total, off, b.size, bs, 11, 128, table_mode=1)
     o = out.cpu().numpy()

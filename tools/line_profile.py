@@ -1,6 +1,6 @@
 """Instructions executed and stall samples per source function of one kernel: joins `nvdisasm -g -c` of the cubin
 (line info, needs -lineinfo) with `ncu -i rep --page source --csv --kernel-name K` (per-instruction counters), in order.
-python tools/line_profile.py kernel_mangled_name source.csv [launches_in_csv]"""
+python tools/line_profile.py kernel_mangled_name source.csv [unused] [library.so]"""
 import csv, re, subprocess, sys, os, collections, tempfile
 name, src_csv = sys.argv[1], sys.argv[2]
 nl = int(sys.argv[3]) if len(sys.argv) > 3 else 2
@@ -22,8 +22,9 @@ rows = list(csv.reader(open(src_csv)))
 hdr = next(r for r in rows if r and r[0] == "Address")
 iex, ismp = hdr.index("Instructions Executed"), hdr.index("# Samples")
 data = [r for r in rows if len(r) > iex and r[0].startswith("0x")]
-data = data[:len(data) // nl]
-assert len(data) == len(ins), (len(data), len(ins))
+# the csv holds one instruction table per captured launch of the kernel: keep the last one
+assert len(ins) and len(data) % len(ins) == 0, (len(data), len(ins))
+data = data[-len(ins):]
 # function ranges from the sources: "name(" at column 0..4 preceded by __device__/__global__
 funcs = {}
 for f in set(i[0] for i in ins if i):
