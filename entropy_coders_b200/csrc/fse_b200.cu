@@ -713,7 +713,13 @@ int fse_b200_compress_blocks_async(fse_b200_ctx *ctx, const uint8_t *d_src, size
     if (wpc < 1) return fail(ctx, FSE_B200_ERR_UNSUPPORTED, "table_log too large for shared memory");
     wpc = std::max(1, std::min(wpc, dev_opt("FSE_B200_ENC_WPC", wpc)));
     int grid = (int)std::min<size_t>((nb + wpc - 1) / wpc, (size_t)ctx->num_sms);
-    if (p->n_states == 128) grid = (int)std::min<size_t>(nb, (size_t)ctx->num_sms);
+    if (p->n_states == 128) {
+        grid = (int)std::min<size_t>(nb, (size_t)ctx->num_sms);
+        // a warp codes whole blocks: keep the number of passes the CTA needs, with the fewest warps that give it
+        const size_t per_cta = (nb + grid - 1) / grid, passes = (per_cta + wpc - 1) / wpc;
+        wpc = (int)((per_cta + passes - 1) / passes);
+        wpc = std::max(1, std::min(wpc, dev_opt("FSE_B200_ENC_WPC", wpc)));
+    }
     if (p->segment_size) {
         // one table per block, its segments coded by the warps of one CTA against bank-replicated tables
         if (tlmax > SH_TL_MAX) return fail(ctx, FSE_B200_ERR_UNSUPPORTED, "segment_size needs table_log <= 11");
@@ -823,15 +829,38 @@ int fse_b200_decompress_blocks_async(fse_b200_ctx *ctx, const uint8_t *d_comp, s
     if (p->n_states == 128) {
         if (tlmax > 13) return fail(ctx, FSE_B200_ERR_UNSUPPORTED, "n_states 128 needs table_log <= 13");
         const size_t half = ctx->smem_per_sm / 2 - 1024;
-        const bool compact = tlmax <= 12 && !dev_opt("FSE_B200_DECODE128_WIDE", 0);
+        // Two table forms.  Compact (u16 transform + u8 symbol: two look-ups per symbol, 3 * size bytes) keeps more warps
+        // per SM; wide (the reference's 32-bit DecodeTransform: one look-up, 4 * size bytes) does less work per symbol.
+        // Wide wins when it fits as many warps (table_log <= 10), and at table_log 11 (24 against 32 warps per SM) on inputs
+        // with at least two blocks per warp slot, where the coarser whole-block passes stop mattering (c4: 8.55 against
+        // 9.73 ms on 65 536 blocks, 1.232 against 1.263 ms on 8 192; c2's 4 096 blocks: 0.485 against 0.379 ms); at
+        // table_log 12 (12 against 16 warps) it loses; table_log 13 has the wide form only.
+        auto warps_for = [&](size_t per_warp, int &ctas_out) {
+            int w = (int)std::min<size_t>(16, (std::min(half, ctx->smem_optin) - 64) / per_warp);
+            ctas_out = 2;
+            if (w < 1) { w = (int)std::min<size_t>(16, (ctx->smem_optin - 64) / per_warp); ctas_out = 1; }
+            return w;
+        };
+        int ctas_c = 2, ctas_w = 2;
+        const int wpc_c = tlmax <= 12 ? warps_for(dec64c_layout(tlmax).total, ctas_c) : 0;
+        const int wpc_w = warps_for(dec64w_layout(tlmax).total, ctas_w);
+        bool compact = wpc_c >= 1 && !(wpc_w * ctas_w >= wpc_c * ctas_c ||
+                                       (tlmax <= 11 && nblocks >= (size_t)2 * ctx->num_sms * ctas_w * std::max(wpc_w, 1)));
+        const int force = dev_opt("FSE_B200_DECODE128_WIDE", -1);
+        if (force == 0 && wpc_c >= 1) compact = true;
+        if (force == 1) compact = false;
         const size_t per_warp = compact ? dec64c_layout(tlmax).total : dec64w_layout(tlmax).total;
         // balanced CTA queues (every CTA gets nblocks / grid blocks): take every warp that fits, two CTAs per SM
-        int wpc = (int)std::min<size_t>(16, (std::min(half, ctx->smem_optin) - 64) / per_warp);
-        int ctas = 2;
-        if (wpc < 1) { wpc = (int)std::min<size_t>(16, (ctx->smem_optin - 64) / per_warp); ctas = 1; }
+        int wpc = compact ? wpc_c : wpc_w;
+        int ctas = compact ? ctas_c : ctas_w;
         if (wpc < 1) return fail(ctx, FSE_B200_ERR_UNSUPPORTED, "table_log too large for shared memory");
-        wpc = std::max(1, std::min(wpc, dev_opt("FSE_B200_WPC", wpc)));
         int grid = (int)std::min<size_t>(nblocks, (size_t)ctx->num_sms * ctas);
+        {   // a warp decodes whole blocks: keep the number of passes the CTA needs, with the fewest warps that give it
+            // (c2: 13.8 blocks per CTA decode in 0.378 ms with 14 warps, 0.397 ms with 16)
+            const size_t per_cta = (nblocks + grid - 1) / grid, passes = (per_cta + wpc - 1) / wpc;
+            wpc = (int)((per_cta + passes - 1) / passes);
+        }
+        wpc = std::max(1, std::min(wpc, dev_opt("FSE_B200_WPC", wpc)));
         Timed t(ctx, FSE_B200_K_DECODE);
         if (compact) k_decode128c_blocks<<<grid, wpc * 32, (size_t)wpc * per_warp, ctx->stream>>>(a);
         else k_decode128_blocks<<<grid, wpc * 32, (size_t)wpc * per_warp, ctx->stream>>>(a);

@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(512, 2) k_decode128c_blocks(DecArgs a)
     uint16_t *tab = reinterpret_cast<uint16_t *>(my + lay.tab);
     uint8_t *sym = my + lay.sym;                            // the spread = the symbol of every cell
     int32_t *norm = reinterpret_cast<int32_t *>(my + lay.scratch);
-    uint32_t *ctr = reinterpret_cast<uint32_t *>(my + lay.scratch + 1024);
+    uint32_t *ctr = reinterpret_cast<uint32_t *>(my + lay.scratch);          // norm's own array (warp_spread<true>)
     uint32_t *ring = reinterpret_cast<uint32_t *>(my + lay.scratch);   // 256 words + 2 mirror words
     const uint32_t tab_saddr = (uint32_t)__cvta_generic_to_shared(tab);
     const uint32_t sym_saddr = (uint32_t)__cvta_generic_to_shared(sym);
@@ -105,8 +105,8 @@ __global__ void __launch_bounds__(512, 2) k_decode128c_blocks(DecArgs a)
             const int rc = warp_ncount_read(cs, clen, reinterpret_cast<uint32_t *>(tab), norm, lane, log2, table_len, consumed);
             if (rc < 0) { if (lane == 0) a.status[b] = rc; continue; }
             if (log2 > a.tlmax || log2 > 12) { if (lane == 0) a.status[b] = ST_UNSUPPORTED; continue; }
-            warp_spread(norm, log2, table_len, sym, ctr, tab, lane);
-            warp_build_decode16(norm, log2, table_len, sym, ctr, tab, lane);
+            warp_spread<true>(norm, log2, table_len, sym, ctr, tab, lane);
+            warp_build_decode16<false>(norm, log2, table_len, sym, ctr, tab, lane);
         }
         if (bn < N) { if (lane == 0) a.status[b] = ST_LENGTH; continue; }
         const uint8_t *pay = cs + consumed;

@@ -18,7 +18,7 @@ namespace fsed {
 struct Dec64cLayout {
     uint32_t tab;      // uint16[size]
     uint32_t sym;      // uint8[size]
-    uint32_t scratch;  // build: norm i32[256] | ctr u32[256]; decode: ring u32[256]
+    uint32_t scratch;  // build: norm i32[256], then the counters u32[256] in the same array; decode: ring u32[258]
     uint32_t total;
 };
 __host__ __device__ inline Dec64cLayout dec64c_layout(uint32_t tlmax)
@@ -28,12 +28,14 @@ __host__ __device__ inline Dec64cLayout dec64c_layout(uint32_t tlmax)
     l.tab = 0;
     l.sym = size * 2;
     l.scratch = size * 3;
-    l.total = size * 3 + 2048 + 16;     // + one mbarrier per warp (fse_decode128c.cuh)
+    l.total = size * 3 + 1040 + 16;     // + one mbarrier per warp (fse_decode128c.cuh); 16 warps per CTA at table_log 11
     return l;
 }
 
 // Inclusive warp prefix sum with the classic predicated add: shfl.up returns "source lane valid" as a
-// predicate, so each step is SHFL + @p IADD (no select, nothing on the ALU pipe).
+// predicate, so each step is SHFL + @p IADD (no select, nothing on the ALU pipe).  A radix-4 form (three dependent
+// shuffle levels, distances 1 2 3 | 4 8 12 | 16, 7 + 7 instructions) was measured in round 2: c4 8.46 against 8.54 ms,
+// c5 6.87 against 6.94, c2 0.387 against 0.378: the scan's latency is not what the decoders wait for.
 __device__ __forceinline__ uint32_t warp_incl_add_pred(uint32_t v)
 {
 #pragma unroll
@@ -56,17 +58,20 @@ __device__ __forceinline__ uint32_t lds_u32_4(uint32_t saddr)
 }
 
 // DecodeTable::update, fse.rs:328-337, compact form
+template <bool INIT = true>     // false: ctr already holds the counters (warp_spread<true>)
 __device__ __forceinline__ void warp_build_decode16(const int32_t *norm, uint32_t log2, uint32_t table_len,
                                                     const uint8_t *spread, uint32_t *ctr, uint16_t *table, int lane)
 {
     const uint32_t size = 1u << log2;
+    if (INIT) {
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-        int i = lane * 8 + k;
-        int32_t x = (i < (int)table_len) ? norm[i] : 0;
-        ctr[i] = (x < 0) ? 1u : (uint32_t)x;
+        for (int k = 0; k < 8; k++) {
+            int i = lane * 8 + k;
+            int32_t x = (i < (int)table_len) ? norm[i] : 0;
+            ctr[i] = (x < 0) ? 1u : (uint32_t)x;
+        }
+        __syncwarp();
     }
-    __syncwarp();
     for (uint32_t c0 = 0; c0 < size; c0 += 32) {
         uint32_t cell = c0 + lane;
         uint32_t s = spread[cell];
@@ -91,7 +96,7 @@ __global__ void __launch_bounds__(512, 2) k_decode64c_blocks(DecArgs a)
     uint16_t *tab = reinterpret_cast<uint16_t *>(my + lay.tab);
     uint8_t *sym = my + lay.sym;
     int32_t *norm = reinterpret_cast<int32_t *>(my + lay.scratch);
-    uint32_t *ctr = reinterpret_cast<uint32_t *>(my + lay.scratch + 1024);
+    uint32_t *ctr = reinterpret_cast<uint32_t *>(my + lay.scratch);          // norm's own array (warp_spread<true>)
     uint32_t *ring = reinterpret_cast<uint32_t *>(my + lay.scratch);
     const uint32_t N = 64;
 
@@ -127,8 +132,8 @@ __global__ void __launch_bounds__(512, 2) k_decode64c_blocks(DecArgs a)
             const int rc = warp_ncount_read(cs, clen, reinterpret_cast<uint32_t *>(tab), norm, lane, log2, table_len, consumed);
             if (rc < 0) { if (lane == 0) a.status[b] = rc; continue; }
             if (log2 > a.tlmax || log2 > 12) { if (lane == 0) a.status[b] = ST_UNSUPPORTED; continue; }
-            warp_spread(norm, log2, table_len, sym, ctr, tab, lane);     // sym is the spread; tab doubles as posmap
-            warp_build_decode16(norm, log2, table_len, sym, ctr, tab, lane);
+            warp_spread<true>(norm, log2, table_len, sym, ctr, tab, lane);     // sym is the spread; tab doubles as posmap
+            warp_build_decode16<false>(norm, log2, table_len, sym, ctr, tab, lane);
         }
         if (bn < N) { if (lane == 0) a.status[b] = ST_LENGTH; continue; }
         const uint8_t *pay = cs + consumed;

@@ -11,7 +11,7 @@ namespace fsed {
 struct Dec64wLayout {
     uint32_t tab;      // uint32[size]
     uint32_t sym;      // uint8[size], aliased with tab's last quarter
-    uint32_t scratch;  // build: norm i32[256] | ctr u32[256]; decode: ring u32[257]
+    uint32_t scratch;  // build: norm i32[256], then the counters u32[256] in the same array; decode: ring u32[258]
     uint32_t total;
 };
 __host__ __device__ inline Dec64wLayout dec64w_layout(uint32_t tlmax)
@@ -21,7 +21,7 @@ __host__ __device__ inline Dec64wLayout dec64w_layout(uint32_t tlmax)
     l.tab = 0;
     l.sym = size * 3;
     l.scratch = size * 4;
-    l.total = size * 4 + 2048;
+    l.total = size * 4 + 1040;
     return l;
 }
 

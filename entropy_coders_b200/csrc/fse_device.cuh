@@ -548,7 +548,11 @@ __device__ __forceinline__ int warp_ncount_read(const uint8_t *src, uint32_t nby
 //   cum     : uint32[256] out: exclusive prefix of |norm| (EncodeTable's cumul / symbol_tt total);
 //             its storage holds the list of present symbols until the end of the call
 //   posmap  : uint16[size] scratch (rank -> cell, bit 15 = a symbol starts here)
+// norm is read into registers before anything is written, so `cum` may be norm's own storage.  CTR_OUT (decoders): `cum`
+// receives the running counters DecodeTable::update starts from (fse.rs:327-328: the count, 1 for -1) instead of the
+// prefix, which lets norm, the symbol list and the counters share one 1 KiB array.
 // ------------------------------------------------------------------------------------------
+template <bool CTR_OUT = false>
 __device__ __forceinline__ void warp_spread(const int32_t *norm, uint32_t log2, uint32_t table_len, uint8_t *spread,
                                             uint32_t *cum, uint16_t *posmap, int lane)
 {
@@ -609,7 +613,7 @@ __device__ __forceinline__ void warp_spread(const int32_t *norm, uint32_t log2, 
     }
     __syncwarp();
 #pragma unroll
-    for (int k = 0; k < 8; k++) cum[lane * 8 + k] = abase + apre[k];
+    for (int k = 0; k < 8; k++) cum[lane * 8 + k] = CTR_OUT ? (x[k] < 0 ? 1u : (uint32_t)x[k]) : abase + apre[k];
     __syncwarp();
 }
 
@@ -655,17 +659,20 @@ __device__ __forceinline__ void warp_build_encode(const int32_t *norm, uint32_t 
 // DecodeTable::update, src/fse.rs:294-337: entry = new_state | symbol << 16 | num_bits << 24
 // (the little-endian image of DecodeTransform {u16 new_state, u8 symbol, u8 num_bits}, fse.rs:260-265).
 //   ctr: uint32[256] scratch (symbol_next, fse.rs:295-310; u32 so the dead wrap of Q5 cannot happen)
+template <bool INIT = true>     // false: ctr already holds the counters (warp_spread<true>)
 __device__ __forceinline__ void warp_build_decode(const int32_t *norm, uint32_t log2, uint32_t table_len,
                                                   const uint8_t *spread, uint32_t *ctr, uint32_t *table, int lane)
 {
     const uint32_t size = 1u << log2;
+    if (INIT) {
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-        int i = lane * 8 + k;
-        int32_t x = (i < (int)table_len) ? norm[i] : 0;
-        ctr[i] = (x < 0) ? 1u : (uint32_t)x;
+        for (int k = 0; k < 8; k++) {
+            int i = lane * 8 + k;
+            int32_t x = (i < (int)table_len) ? norm[i] : 0;
+            ctr[i] = (x < 0) ? 1u : (uint32_t)x;
+        }
+        __syncwarp();
     }
-    __syncwarp();
     for (uint32_t c0 = 0; c0 < size; c0 += 32) {
         uint32_t cell = c0 + lane;
         uint32_t s = spread[cell];

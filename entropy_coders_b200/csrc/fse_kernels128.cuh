@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(512, 2) k_decode128_blocks(DecArgs a)
     uint32_t *tab = reinterpret_cast<uint32_t *>(my + lay.tab);
     uint8_t *sym = my + lay.sym;                            // the spread, consumed in place by the table build
     int32_t *norm = reinterpret_cast<int32_t *>(my + lay.scratch);
-    uint32_t *ctr = reinterpret_cast<uint32_t *>(my + lay.scratch + 1024);
+    uint32_t *ctr = reinterpret_cast<uint32_t *>(my + lay.scratch);          // norm's own array (warp_spread<true>)
     uint32_t *ring = reinterpret_cast<uint32_t *>(my + lay.scratch);   // 256 words + 2 mirror words
     const uint32_t tab_saddr = (uint32_t)__cvta_generic_to_shared(tab);
     const uint32_t N = 128;
@@ -72,8 +72,8 @@ __global__ void __launch_bounds__(512, 2) k_decode128_blocks(DecArgs a)
             __syncwarp();
             if (rc < 0) { if (lane == 0) a.status[b] = rc; continue; }
             if (log2 > a.tlmax || log2 > 13) { if (lane == 0) a.status[b] = ST_UNSUPPORTED; continue; }
-            warp_spread(norm, log2, table_len, sym, ctr, reinterpret_cast<uint16_t *>(tab), lane);
-            warp_build_decode(norm, log2, table_len, sym, ctr, tab, lane);
+            warp_spread<true>(norm, log2, table_len, sym, ctr, reinterpret_cast<uint16_t *>(tab), lane);
+            warp_build_decode<false>(norm, log2, table_len, sym, ctr, tab, lane);
         }
         if (bn < N) { if (lane == 0) a.status[b] = ST_LENGTH; continue; }
         const uint8_t *pay = cs + consumed;

@@ -144,15 +144,16 @@ def test_reference_termination_rule(ctx, data, n_states):
         assert out.cpu().numpy()[0, :len(exp)].tobytes() == exp and exp[:data.size] == data.tobytes()
 
 
-@pytest.mark.parametrize("n_states", [1, 32, 64, 128])
-def test_corrupted_streams_never_fault(ctx, n_states):
+@pytest.mark.parametrize("n_states,tl", [(1, 0), (32, 0), (64, 0), (128, 0), (128, 9), (128, 13)])
+def test_corrupted_streams_never_fault(ctx, n_states, tl):
     """seeded fuzz of the decoders: bit flips, byte smashes, truncations and offset damage.  Every block ends with a
     status (an error, or 0 with whatever bytes the damaged stream describes), the launch itself never fails, and an intact
-    stream still decodes afterwards (compute-sanitizer is closed on this pool; this is the memory-safety net)."""
-    rng = np.random.default_rng(1000 + n_states)
+    stream still decodes afterwards (compute-sanitizer is closed on this pool; this is the memory-safety net).  128 states:
+    table_log 0 takes the compact-table decoder, 9 and 13 the wide-entry one."""
+    rng = np.random.default_rng(1000 + n_states + tl)
     bs, nb = (2048 if n_states == 1 else 8192), 6
     src = O.generate("text", 77, bs * nb)
-    d, off, st, total = ctx.compress_blocks(dev(ctx, src), bs, 0, n_states)
+    d, off, st, total = ctx.compress_blocks(dev(ctx, src), bs, tl, n_states)
     good = d[:total].cpu().numpy().copy()
     offh = off.cpu().numpy().astype(np.int64)
     for trial in range(150):
@@ -176,7 +177,7 @@ def test_corrupted_streams_never_fault(ctx, n_states):
             b = int(rng.integers(0, nb))
             a = int(rng.integers(boff[b], boff[b + 1]))
             bad[a:min(a + int(rng.integers(1, 2000)), boff[b + 1])] = np.uint8(rng.integers(0, 256))
-        out, st2 = ctx.decompress_blocks(dev(ctx, bad), bad.size, dev(ctx, boff), src.size, bs, 0, n_states)
+        out, st2 = ctx.decompress_blocks(dev(ctx, bad), bad.size, dev(ctx, boff), src.size, bs, tl, n_states)
         st2 = st2.cpu().numpy()
         assert st2.shape[0] == nb and ((st2 <= 2) & (st2 >= -11)).all(), (trial, st2)
         if kind in (0, 1, 2, 4):                             # blocks that were not touched still decode exactly
@@ -184,7 +185,7 @@ def test_corrupted_streams_never_fault(ctx, n_states):
             for b in range(nb):
                 if np.array_equal(bad[boff[b]:boff[b + 1]], good[offh[b]:offh[b + 1]]):
                     assert st2[b] == 0 and np.array_equal(outh[b * bs:(b + 1) * bs], src[b * bs:(b + 1) * bs]), (trial, b)
-    out, st3 = ctx.decompress_blocks(dev(ctx, good), good.size, dev(ctx, offh), src.size, bs, 0, n_states)
+    out, st3 = ctx.decompress_blocks(dev(ctx, good), good.size, dev(ctx, offh), src.size, bs, tl, n_states)
     assert not st3.cpu().numpy().any() and np.array_equal(out.cpu().numpy(), src)
 
 
