@@ -16,46 +16,102 @@
 #endif
 namespace fsed {
 
-// Two forms of the per-symbol transform table, chosen per block when its tables are built:
-//  * PK = 0: the reference's {bits, find_state} pair (fse.rs:80-84) with find_state pre-scaled to a shared byte address,
-//    one 64-bit load per look-up.  Best when few symbols dominate (most lanes read the same entry: a broadcast).
-//  * PK = 1 (table_log <= 11): p = bits | find_state << 20.  bits < 2^20 and bits + state never carries into bit 20, so
-//    t = p + state keeps find_state in the top 12 bits and (t >> 16) & 15 is the reference's (bits + state) >> 16
-//    (fse.rs:228).  One 32-bit load (a whole warp per wavefront instead of half a warp), two copies interleaved by lane
-//    parity to halve the lanes per bank; three more integer instructions per symbol.  Measured against PK = 0 on the
-//    encode kernel: text -8 %, uniform bytes -11 %, geometric -2 %, four symbols +0.6 % (there nearly every 64-bit
-//    load is a broadcast): hence the choice per block, by the collision probability of the normalised counts.
-#ifndef FSE_TT_THR
-#define FSE_TT_THR 2u     /* packed form iff sum p^2 < 1 / FSE_TT_THR */
-#endif
+// Two forms of the per-symbol transform table:
+//  * PK = 0 (table_log 12, 13; global-table mode of this kernel): the reference's {bits, find_state} pair (fse.rs:80-84)
+//    with find_state pre-scaled to a shared byte address, one 64-bit load per look-up.
+//  * PK = 1 (table_log <= 11): the transform re-packed for few ALU-pipe instructions (round 2; the form the CTA-owned
+//    tables of fse_shared_enc.cuh introduced):
+//      P = H << 12 | (find_state + 2048),   H = (max_bits << 13) - (count << max_bits)
+//      t = P + (state << 12)                 one IMAD (FMA pipe)
+//      nb = t >> 25                          = (bits + state) >> 16 of fse.rs:228: state - (count << max_bits) lies in
+//                                              (-2^12, 2^12), so a 13-bit fraction decides max_bits vs max_bits - 1
+//      u = (t & 0xfff) + (state >> nb)       = find_state + 2048 + (state >> nb): the table index, biased by 2048
+//    and the emitted bits are never masked out of the state: a funnel shift moves the low nb bits of the raw state into
+//    the top of a pair accumulator (quad_field_raw).  One 32-bit load (a whole warp per wavefront instead of half a
+////    warp), two copies interleaved by lane parity to halve the lanes per bank.  Against round 1's packed form (p = bits |
+//    find_state << 20, which lost to PK = 0 on few-symbol data and was chosen per block): c4 encode 9.48 -> 8.87 ms,
+//    c2 0.405 -> 0.389 ms, few-symbol 1 GiB 1.29 -> 1.18 ms (table_log 11), 1.10 -> 1.00 ms (9): used whenever it fits.
 constexpr uint32_t TT_REPL_LOG2 = 1;
 constexpr uint32_t TT_PACKED_MAX_LOG2 = 11;
-__device__ __forceinline__ uint32_t tt_pack(uint2 t) { return (t.x & 0xfffffu) | (t.y << 20); }
-struct Enc128Tab { uint32_t tt, tab; };    // shared byte addresses: transforms (this lane's copy when packed), next-state table
+constexpr uint32_t SH_FS_BIAS = 2048;
+// reference transform {bits, find_state} (fse.rs:165-188) -> P
+// A symbol the table does not know (count 0: bits = ((log2 + 1) << 16) - size, fse.rs:170) would code log2 + 1 bits per
+// occurrence; it is clamped to log2 so that a quad never exceeds 4 * log2 bits, the size the lane strings are made for
+// (such a block is undecodable either way: see fse_b200_set_global_table in include/fse_b200.h).
+__device__ __forceinline__ uint32_t sh_pack_tt(uint2 t, uint32_t log2)
+{
+    uint32_t mbo = (t.x + 65535u) >> 16;                       // bits = (mbo << 16) - y, 0 < y <= 2 * size
+    const uint32_t y = (mbo << 16) - t.x;
+    mbo = min(mbo, log2);
+    const uint32_t H = (mbo << 13) - y;
+    return (H << 12) | ((t.y + SH_FS_BIAS) & 0xfffu);
+}
+// the quad (chains 3, 2, 1, 0 in stream order) as one field: value (hi:lo) right aligned, length in hi[26..31];
+// s = the OLD states, b = bits each emits
+constexpr uint32_t QUAD_LEN_SHIFT = 26;              // a quad field: 52 value bits, 6 length bits
+constexpr uint32_t QUAD_HI_MASK = (1u << QUAD_LEN_SHIFT) - 1u;
+__device__ __forceinline__ uint2 quad_field_raw(uint32_t s3, uint32_t b3, uint32_t s2, uint32_t b2, uint32_t s1, uint32_t b1,
+                                                uint32_t s0, uint32_t b0)
+{
+    // a pair accumulates top aligned: funnel the low b bits of the raw state in from above, no masks
+    uint32_t pa = __funnelshift_r(0u, s3, b3);
+    pa = __funnelshift_r(pa, s2, b2);
+    uint32_t pb = __funnelshift_r(0u, s1, b1);
+    pb = __funnelshift_r(pb, s0, b0);
+    const uint32_t na = b3 + b2, nbb = b1 + b0;
+    const uint32_t va = __funnelshift_r(pa, 0u, 0u - na);      // pa >> (32 - na); na == 0: pa == 0
+    const uint32_t vb = __funnelshift_r(pb, 0u, 0u - nbb);
+    uint2 f;
+    f.x = va | (vb << na);
+    f.y = __funnelshift_l(vb, 0u, na) | ((na + nbb) << QUAD_LEN_SHIFT);
+    return f;
+}
+
+struct Enc128Tab { uint32_t tt, tab; };    // shared byte addresses: transforms (this lane's copy when packed), next-state
+                                           // table (PK = 1: biased by -2 * SH_FS_BIAS)
 template <int PK>
 __device__ __forceinline__ void enc128_step(const Enc128Tab &e, uint32_t sym, uint32_t &state, uint32_t &v, uint32_t &bo)
 {
-    if (PK) {
-        const uint32_t t = lds_u32(e.tt + (sym << (2 + TT_REPL_LOG2))) + state;
-        bo = (t >> 16) & 15u;
-        const uint32_t q = state >> bo;
-        v = state - (q << bo);
-        state = lds_u16(e.tab + (((uint32_t)((int32_t)t >> 20) + q) << 1));
-    } else {
-        enc_step(e.tt, sym, state, v, bo);
-    }
+    enc_step(e.tt, sym, state, v, bo);                         // PK = 0 only; PK = 1 goes through pk_step_at
 }
 template <int PK>
 __device__ __forceinline__ uint32_t enc128_first(const Enc128Tab &e, uint32_t sym)
 {
-    if (PK) {
+    if (PK) {                                                  // fse.rs:210-218: bo = max_bits, value = count << max_bits
         const uint32_t p = lds_u32(e.tt + (sym << (2 + TT_REPL_LOG2)));
-        const uint32_t bits = p & 0xfffffu;
-        const uint32_t bo = (bits + (1u << 15)) >> 16;
-        const uint32_t value = (bo << 16) - bits;
-        return lds_u16(e.tab + (((uint32_t)((int32_t)p >> 20) + (value >> bo)) << 1));
+        const uint32_t H = p >> 12;
+        const uint32_t mbo = (H + 8191u) >> 13;
+        const uint32_t x = ((mbo << 13) - H) >> mbo;
+        return lds_u16(e.tab + (((p & 0xfffu) + x) << 1));
     }
     return enc_first64(e.tt, sym);
+}
+// PK = 1: shared address of the lane's copy of P[byte K of x] (PRMT on the ALU pipe + IMAD on the FMA pipe), and one
+// transition (fse.rs:227-239); the caller emits the low nb bits of the OLD state
+template <int K>
+__device__ __forceinline__ uint32_t pk_tt_addr(const Enc128Tab &e, uint32_t x)
+{
+    uint32_t a;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(a) : "r"(__byte_perm(x, 0u, 0x4440u + K)), "n"(4 << TT_REPL_LOG2), "r"(e.tt));
+    return a;
+}
+__device__ __forceinline__ uint32_t pk_step_at(const Enc128Tab &e, uint32_t tt_addr, uint32_t s, uint32_t &nb)
+{
+    const uint32_t t = lds_u32(tt_addr) + (s << 12);
+    nb = t >> 25;
+    const uint32_t u = (t & 0xfffu) + (s >> nb);
+    uint32_t a;
+    asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(a) : "r"(u), "r"(e.tab));
+    return lds_u16(a);
+}
+__device__ __forceinline__ void pk_elem_checked(const uint8_t *__restrict__ bsrc, int32_t i, int32_t bn, const Enc128Tab &e,
+                                                uint32_t &s, uint32_t &sold, uint32_t &nb)
+{
+    sold = 0; nb = 0;
+    if (i < 0 || i >= bn) return;
+    const uint32_t sym = __ldg(bsrc + i);
+    if (i >= bn - 128) s = enc128_first<1>(e, sym);
+    else { sold = s; s = pk_step_at(e, e.tt + (sym << (2 + TT_REPL_LOG2)), s, nb); }
 }
 
 // element classes of a symbol index for N = 128 (cf. enc_element_checked)
@@ -72,9 +128,6 @@ __device__ __forceinline__ void enc_element_checked128(const uint8_t *__restrict
 
 // BitRow with the word emission written as predicated PTX: 9 instructions per field instead of the 13 the
 // compiler makes of the C++ version (it materialises every conditional update as add + move).
-constexpr uint32_t QUAD_LEN_SHIFT = 26;              // a quad field: 52 value bits, 6 length bits
-constexpr uint32_t QUAD_HI_MASK = (1u << QUAD_LEN_SHIFT) - 1u;
-
 struct BitRowS {
     uint32_t base, wp, lo, pos;      // shared byte addresses of the row start / next word, accumulator, bits held
     __device__ __forceinline__ void init(uint32_t *row, uint32_t carry_word, uint32_t carry_bits)
@@ -172,12 +225,20 @@ __device__ void encode128_payload_warp(const uint8_t *__restrict__ bsrc, uint32_
             for (int r = 0; r < 16; r++) {
                 uint32_t v3, b3, v2, b2, v1, b1, v0, b0;
                 const uint32_t x = sy[r];
+                uint2 f;
                 if (r == 0 && g0 == 0) {                           // Encoder::new_first_symbol: no bits
                     s3 = enc128_first<PK>(tt_saddr, x >> 24);
                     s2 = enc128_first<PK>(tt_saddr, (x >> 16) & 0xff);
                     s1 = enc128_first<PK>(tt_saddr, (x >> 8) & 0xff);
                     s0 = enc128_first<PK>(tt_saddr, x & 0xff);
-                    v3 = v2 = v1 = v0 = b3 = b2 = b1 = b0 = 0;
+                    f = make_uint2(0u, 0u);
+                } else if (PK) {
+                    const uint32_t o3 = s3, o2 = s2, o1 = s1, o0 = s0;
+                    s3 = pk_step_at(tt_saddr, pk_tt_addr<3>(tt_saddr, x), o3, b3);   // decreasing index order: 4m+3 first
+                    s2 = pk_step_at(tt_saddr, pk_tt_addr<2>(tt_saddr, x), o2, b2);
+                    s1 = pk_step_at(tt_saddr, pk_tt_addr<1>(tt_saddr, x), o1, b1);
+                    s0 = pk_step_at(tt_saddr, pk_tt_addr<0>(tt_saddr, x), o0, b0);
+                    f = quad_field_raw(o3, b3, o2, b2, o1, b1, o0, b0);
                 } else {
 #if FSE_DIAG == 2                                               // timing experiment: no table look-ups
                     v3 = x >> 27; b3 = 5; v2 = (x >> 16) & 31; b2 = 5; v1 = (x >> 8) & 31; b1 = 5; v0 = x & 31; b0 = 6;
@@ -187,9 +248,7 @@ __device__ void encode128_payload_warp(const uint8_t *__restrict__ bsrc, uint32_
                     enc128_step<PK>(tt_saddr, (x >> 8) & 0xff, s1, v1, b1);
                     enc128_step<PK>(tt_saddr, x & 0xff, s0, v0, b0);
 #endif
-                }
-                uint2 f;
-                {                                                  // the quad as one field of <= 52 bits: (hi:lo), length in hi[26..31]
+                    // the quad as one field of <= 52 bits: (hi:lo), length in hi[26..31]
                     const uint32_t p1 = v3 | (v2 << b3), n1 = b3 + b2, p0 = v1 | (v0 << b1);
                     f.x = p1 | (p0 << n1);
                     f.y = __funnelshift_l(p0, 0u, n1) | ((n1 + b1 + b0) << QUAD_LEN_SHIFT);
@@ -202,12 +261,19 @@ __device__ void encode128_payload_warp(const uint8_t *__restrict__ bsrc, uint32_
                 int32_t m = mtop - (int32_t)((g0 + r) << 5);
                 int32_t i = m < 0 ? -8 : 4 * m;
                 uint32_t v3, b3, v2, b2, v1, b1, v0, b0;
-                enc_element_checked128<PK>(bsrc, i + 3, (int32_t)bn, tt_saddr, s3, v3, b3);
-                enc_element_checked128<PK>(bsrc, i + 2, (int32_t)bn, tt_saddr, s2, v2, b2);
-                enc_element_checked128<PK>(bsrc, i + 1, (int32_t)bn, tt_saddr, s1, v1, b1);
-                enc_element_checked128<PK>(bsrc, i, (int32_t)bn, tt_saddr, s0, v0, b0);
                 uint2 f;
-                {                                                  // the quad as one field of <= 52 bits: (hi:lo), length in hi[26..31]
+                if (PK) {
+                    pk_elem_checked(bsrc, i + 3, (int32_t)bn, tt_saddr, s3, v3, b3);     // v = the old state here
+                    pk_elem_checked(bsrc, i + 2, (int32_t)bn, tt_saddr, s2, v2, b2);
+                    pk_elem_checked(bsrc, i + 1, (int32_t)bn, tt_saddr, s1, v1, b1);
+                    pk_elem_checked(bsrc, i, (int32_t)bn, tt_saddr, s0, v0, b0);
+                    f = quad_field_raw(v3, b3, v2, b2, v1, b1, v0, b0);
+                } else {
+                    enc_element_checked128<PK>(bsrc, i + 3, (int32_t)bn, tt_saddr, s3, v3, b3);
+                    enc_element_checked128<PK>(bsrc, i + 2, (int32_t)bn, tt_saddr, s2, v2, b2);
+                    enc_element_checked128<PK>(bsrc, i + 1, (int32_t)bn, tt_saddr, s1, v1, b1);
+                    enc_element_checked128<PK>(bsrc, i, (int32_t)bn, tt_saddr, s0, v0, b0);
+                    // the quad as one field of <= 52 bits: (hi:lo), length in hi[26..31]
                     const uint32_t p1 = v3 | (v2 << b3), n1 = b3 + b2, p0 = v1 | (v0 << b1);
                     f.x = p1 | (p0 << n1);
                     f.y = __funnelshift_l(p0, 0u, n1) | ((n1 + b1 + b0) << QUAD_LEN_SHIFT);
@@ -349,19 +415,11 @@ __global__ void __launch_bounds__(512) k_encode128_blocks(EncArgs a)
                 hl = (hbits + 7) >> 3;
                 warp_spread(norm, log2, table_len, spread, cum, tab, lane);
                 warp_build_encode(norm, log2, table_len, spread, cum, tab, tt, lane);
-                {
-                    // collision probability of the block's distribution: unless one symbol dominates (sum p^2 >= 1/2) -> packed form
-                    uint32_t sq = 0;
-#pragma unroll
-                    for (int k = 0; k < 8; k++) { const int32_t x = norm[lane * 8 + k]; sq += (uint32_t)(x * x); }
-#pragma unroll
-                    for (int d = 16; d; d >>= 1) sq += __shfl_xor_sync(FULL, sq, d);
-                    packed = log2 <= TT_PACKED_MAX_LOG2 && (uint64_t)sq * FSE_TT_THR < ((uint64_t)1 << (2 * log2));
-                }
+                packed = log2 <= TT_PACKED_MAX_LOG2;          // the re-packed form wins on every distribution measured (below)
                 if (packed) {                                // two interleaved copies of the 32-bit form, in place
                     uint32_t pk[8];
 #pragma unroll
-                    for (int k = 0; k < 8; k++) pk[k] = tt_pack(tt[k * 32 + lane]);
+                    for (int k = 0; k < 8; k++) pk[k] = sh_pack_tt(tt[k * 32 + lane], log2);
                     __syncwarp();
 #pragma unroll
                     for (int k = 0; k < 8; k++)
@@ -385,7 +443,7 @@ __global__ void __launch_bounds__(512) k_encode128_blocks(EncArgs a)
             uint32_t pbits;
             bool ovf;
                         if (packed) {
-                const Enc128Tab et{tt_saddr + 4u * ((uint32_t)lane & ((1u << TT_REPL_LOG2) - 1u)), tab_saddr};
+                const Enc128Tab et{tt_saddr + 4u * ((uint32_t)lane & ((1u << TT_REPL_LOG2) - 1u)), tab_saddr - 2u * SH_FS_BIAS};
                 encode128_payload_warp<1>(bsrc, bn, log2, et, fld, rows, pay, a.pay_cap_words, lane, pbits, ovf);
             } else {
                 const Enc128Tab et{tt_saddr, tab_saddr};

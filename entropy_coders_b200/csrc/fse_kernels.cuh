@@ -451,6 +451,9 @@ __global__ void __launch_bounds__(1024) k_scan_sizes(const uint32_t *__restrict_
     if (tid == 0) offsets[nblocks] = carry;
 }
 
+#ifndef GATHER_UNROLL
+#define GATHER_UNROLL 2
+#endif
 // byte copy with 4-byte aligned destination stores and funnel-shifted source words
 __device__ __forceinline__ void block_copy_bytes(uint8_t *dst, const uint8_t *src /*4-aligned*/, uint32_t len, int tid, int nthr)
 {
@@ -462,7 +465,21 @@ __device__ __forceinline__ void block_copy_bytes(uint8_t *dst, const uint8_t *sr
     const uint32_t *sw = reinterpret_cast<const uint32_t *>(src) + (head >> 2);   // vector k = src bytes head+16k ..
     uint4 *dv = reinterpret_cast<uint4 *>(dst + head);
     const uint32_t sh = (head & 3) * 8;
-    for (uint32_t k = tid; k < nvec; k += nthr) {
+    // GATHER_UNROLL vectors per thread in flight: the copy is bound by the bytes it keeps in flight, not by instructions
+    uint32_t k = tid;
+    for (; k + (GATHER_UNROLL - 1) * nthr < nvec; k += GATHER_UNROLL * nthr) {
+        uint32_t x[GATHER_UNROLL][5];
+#pragma unroll
+        for (int u = 0; u < GATHER_UNROLL; u++) {
+            const uint32_t *w = sw + 4 * (k + u * nthr);
+            x[u][0] = w[0]; x[u][1] = w[1]; x[u][2] = w[2]; x[u][3] = w[3]; x[u][4] = sh ? w[4] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < GATHER_UNROLL; u++)
+            dv[k + u * nthr] = make_uint4(__funnelshift_r(x[u][0], x[u][1], sh), __funnelshift_r(x[u][1], x[u][2], sh),
+                                          __funnelshift_r(x[u][2], x[u][3], sh), __funnelshift_r(x[u][3], x[u][4], sh));
+    }
+    for (; k < nvec; k += nthr) {
         const uint32_t *w = sw + 4 * k;
         uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = sh ? w[4] : 0u;
         dv[k] = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh),

@@ -25,20 +25,8 @@
 namespace fsed {
 
 constexpr uint32_t SH_TL_MAX = 11;
-constexpr uint32_t SH_FS_BIAS = 2048;
-
-// reference transform {bits, find_state} (fse.rs:165-188) -> P
-// A symbol the table does not know (count 0: bits = ((log2 + 1) << 16) - size, fse.rs:170) would code log2 + 1 bits per
-// occurrence; it is clamped to log2 so that a quad never exceeds 4 * log2 bits, the size the lane strings are made for
-// (such a block is undecodable either way: see fse_b200_set_global_table in include/fse_b200.h).
-__device__ __forceinline__ uint32_t sh_pack_tt(uint2 t, uint32_t log2)
-{
-    uint32_t mbo = (t.x + 65535u) >> 16;                       // bits = (mbo << 16) - y, 0 < y <= 2 * size
-    const uint32_t y = (mbo << 16) - t.x;
-    mbo = min(mbo, log2);
-    const uint32_t H = (mbo << 13) - y;
-    return (H << 12) | ((t.y + SH_FS_BIAS) & 0xfffu);
-}
+// sh_pack_tt (reference transform -> P), SH_FS_BIAS and quad_field_raw live in fse_encode128.cuh: the private-table
+// kernel uses the same arithmetic.
 
 // NSR = copies of the next-state table: 32 (lane l reads copy l, one wavefront, size * 64 bytes) or 16 (lanes l and
 // l + 16 share copy l & 15 in banks l & 15 / (l & 15) + 16, at most two wavefronts, size * 32 bytes: room for twice the warps)
@@ -92,22 +80,10 @@ __device__ __forceinline__ uint32_t sh_enc_first(const ShEnc &e, uint32_t sym)
     return lds_u16(sh_tab_addr<NSR>(e, (p & 0xfffu) + x));
 }
 
-// the quad (chains 3, 2, 1, 0 in stream order) as one field: value (hi:lo) right aligned, length in hi[26..31]
 __device__ __forceinline__ uint2 sh_quad_field(uint32_t s3, uint32_t b3, uint32_t s2, uint32_t b2, uint32_t s1, uint32_t b1,
                                                uint32_t s0, uint32_t b0)
 {
-    // a pair accumulates top aligned: funnel the low b bits of the raw state in from above, no masks
-    uint32_t pa = __funnelshift_r(0u, s3, b3);
-    pa = __funnelshift_r(pa, s2, b2);
-    uint32_t pb = __funnelshift_r(0u, s1, b1);
-    pb = __funnelshift_r(pb, s0, b0);
-    const uint32_t na = b3 + b2, nbb = b1 + b0;
-    const uint32_t va = __funnelshift_r(pa, 0u, 0u - na);      // pa >> (32 - na); na == 0: pa == 0
-    const uint32_t vb = __funnelshift_r(pb, 0u, 0u - nbb);
-    uint2 f;
-    f.x = va | (vb << na);
-    f.y = __funnelshift_l(vb, 0u, na) | ((na + nbb) << QUAD_LEN_SHIFT);
-    return f;
+    return quad_field_raw(s3, b3, s2, b2, s1, b1, s0, b0);
 }
 
 template <int ROUNDS> struct ShEncStage {
