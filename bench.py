@@ -531,15 +531,20 @@ def e2e_leg(env, job, steps):
         moved = float(sample + tot)                          # per direction and rank: N + C each way over a round trip
         # the two calls run one after the other (the reference's API shape): compress moves N up while C comes down,
         # decompress moves C up while N comes down; each call is bounded by its larger transfer at the duplex rate
-        c_s = max(sample / h2d_dx, tot / d2h_dx) / 1e9
-        d_s = max(tot / h2d_dx, sample / d2h_dx) / 1e9
+        def two_calls(up, down):
+            c_s = max(sample / up, tot / down) / 1e9
+            d_s = max(tot / up, sample / down) / 1e9
+            return env["world"] * sample / (c_s + d_s) / 1e9
         link = {"h2d_GBps_min_rank": h2d, "d2h_GBps_min_rank": d2h,
                 "h2d_duplex_GBps_min_rank": h2d_dx, "d2h_duplex_GBps_min_rank": d2h_dx,
                 "round_trip_bound_GBps": env["world"] * sample / (moved / (min(h2d, d2h) * 1e9)) / 1e9,
-                "two_call_bound_GBps": env["world"] * sample / (c_s + d_s) / 1e9,
+                "two_call_bound_GBps": two_calls(h2d, d2h),
+                "two_call_duplex_GBps": two_calls(h2d_dx, d2h_dx),
                 "note": "pinned copies of 1 GiB on all ranks at once, one direction at a time and both at once (duplex); "
                         "round_trip_bound = N / ((N + C) / slower direction) if the two calls could overlap each other; "
-                        "two_call_bound = N / (max(N/up, C/down) + max(C/up, N/down)) at the duplex rates: the calls as the API has them, back to back"}
+                        "two_call_* = N / (max(N/up, C/down) + max(C/up, N/down)): the calls as the API has them, back to back, "
+                        "at the one-way rates (the bound) and at the rates with both directions saturated (the smaller "
+                        "transfer of a call loads the other direction only part of the time: e2e lies between the two)"}
         del dtmp, dtmp2
     except Exception as ex:
         link = {"error": repr(ex)}
