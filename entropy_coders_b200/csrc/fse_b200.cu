@@ -281,9 +281,7 @@ int fse_b200_create(int device, void *stream, fse_b200_ctx **out)
     cudaFuncSetAttribute(k_decode128c_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 64);   // 16 bytes of static shared memory (block queue)
     cudaFuncSetAttribute(k_encode128_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 64);   // 16 bytes of static shared memory (block queue)
     cudaFuncSetAttribute(k_build_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
-    cudaFuncSetAttribute(k_encode_sh_global<16, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 64);
     cudaFuncSetAttribute(k_encode_sh_global<16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 64);
-    cudaFuncSetAttribute(k_encode_sh_global<8, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 64);
     cudaFuncSetAttribute(k_decode_sh_global, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 64);
     cudaFuncSetAttribute(k_encode_sh_blocks<16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 64);
     cudaFuncSetAttribute(k_decode_sh_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 64);
@@ -731,17 +729,13 @@ int fse_b200_compress_blocks_async(fse_b200_ctx *ctx, const uint8_t *d_src, size
         k_encode_sh_blocks<16, 16><<<g, (w + 1) * 32, fixed + w * pw, ctx->stream>>>(a);
     } else if (global && p->n_states == 128 && tlmax <= SH_TL_MAX) {
         // one table for the job: CTA-owned, bank-replicated tables (fse_shared_enc.cuh), one CTA per SM
-        const int rounds = dev_opt("FSE_B200_SH_ROUNDS", 16), nsr = dev_opt("FSE_B200_SH_NSR", 16);
-        const size_t fixed = rounds == 8 ? sh_enc_layout<8, 32>(tlmax, 0).total
-                                         : (nsr == 32 ? sh_enc_layout<16, 32>(tlmax, 0).total : sh_enc_layout<16, 16>(tlmax, 0).total);
-        const size_t pw = rounds == 8 ? ShEncStage<8>::BYTES : ShEncStage<16>::BYTES;
+        // 16 rounds per chunk, 16 copies of the next-state table (32 copies / 8 rounds measured slower: DESIGN.md 4)
+        const size_t fixed = sh_enc_layout<16, 16>(tlmax, 0).total, pw = ShEncStage<16>::BYTES;
         int w = (int)std::min<size_t>(16, (ctx->smem_optin - 64 - fixed) / pw);
         w = std::max(1, std::min(w, dev_opt("FSE_B200_SH_WARPS", w)));
         const int g = (int)std::min<size_t>(nb, (size_t)ctx->num_sms);
         Timed t(ctx, FSE_B200_K_ENCODE);
-        if (rounds == 8) k_encode_sh_global<8, 32><<<g, w * 32, fixed + w * pw, ctx->stream>>>(a);
-        else if (nsr == 32) k_encode_sh_global<16, 32><<<g, w * 32, fixed + w * pw, ctx->stream>>>(a);
-        else k_encode_sh_global<16, 16><<<g, w * 32, fixed + w * pw, ctx->stream>>>(a);
+        k_encode_sh_global<16, 16><<<g, w * 32, fixed + w * pw, ctx->stream>>>(a);
     } else {
         Timed t(ctx, FSE_B200_K_ENCODE);
         if (p->n_states == 128) k_encode128_blocks<<<grid, wpc * 32, (size_t)wpc * per_warp, ctx->stream>>>(a);
