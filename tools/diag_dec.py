@@ -1,4 +1,5 @@
-"""development: time the decode kernel for a workload shape (kind, block size, total bytes); FSE_B200_DECODE128=c|w picks the tables"""
+"""development: time the decode kernel for a workload shape (kind, block size, MiB); with a -DFSE_DEV build (FSE_B200_LIB),
+FSE_B200_DECODE128_WIDE=0|1 forces the table form and FSE_B200_WPC caps the warps per CTA"""
 import sys, torch
 sys.path.insert(0, ".")
 import entropy_coders_b200 as E
