@@ -53,14 +53,28 @@ N_STATES = 128
 SEGMENT_SIZE = 0          # > 0: code every block as block_size / SEGMENT_SIZE independent 128-state streams (fse_shared_enc.cuh); measured slower
 
 
-def kernel_names(tmode, seg):
-    """the kernels behind the timed spans (fse_b200.cu dispatch at n_states 128, table_log <= 11)"""
-    if tmode == 1:
+def kernel_names(tmode, seg, tlog=0, nblocks=0, num_sms=148, smem_per_sm=233472, smem_optin=232448):
+    """the kernels behind the timed spans: the dispatch rules of fse_b200.cu (compress / decompress_blocks_async) restated"""
+    n, tl = N_STATES, (tlog or 11)
+    if n == 128 and tmode == 1 and tl <= 11:
         enc, dec = "k_encode_sh_global", "k_decode_sh_global"          # CTA-owned bank-replicated tables
-    elif seg:
+    elif n == 128 and seg:
         enc, dec = "k_encode_sh_blocks", "k_decode_sh_blocks"
+    elif n == 128:
+        enc = "k_encode128_blocks"                                     # one private table set per warp
+        half = smem_per_sm // 2 - 1024
+
+        def warps(per_warp):
+            w = min(16, (min(half, smem_optin) - 64) // per_warp)
+            return (w, 2) if w >= 1 else (min(16, (smem_optin - 64) // per_warp), 1)
+        size = 1 << max(tl, 9)
+        (wc, cc), (ww, cw) = (warps(3 * size + 1056) if tl <= 12 else (0, 2)), warps(4 * size + 1040)
+        wide = wc < 1 or ww * cw >= wc * cc or (tl <= 11 and nblocks >= 2 * num_sms * cw * max(ww, 1))
+        dec = "k_decode128_blocks" if wide else "k_decode128c_blocks"  # 32-bit entries / compact tables
+    elif n == 64:
+        enc, dec = "k_encode64_blocks", ("k_decode64c_blocks" if tl <= 12 else "k_decode64_blocks")
     else:
-        enc, dec = "k_encode128_blocks", "k_decode128c_blocks"         # one private table set per warp
+        enc, dec = "k_encode_blocks", "k_decode_blocks"
     return {"hist": "k_hist_blocks16", "encode": enc, "decode": dec, "scan": "k_scan_sizes", "gather": "k_gather"}
 
 
@@ -440,7 +454,7 @@ def measure(env, job, steps, warmup, sample_clocks=False):
         "encode_GBps": job.nbytes / (enc_ms * 1e-3) / 1e9, "decode_GBps": job.nbytes / (dec_ms * 1e-3) / 1e9,
         "compressed_ratio": total_all / job.total_bytes, "compressed_bytes_rank0": total,
         "kernel_ms_per_step": {k: tm[k][0] / steps for k in tm},
-        "roofline": {"bound": "hbm", "kernel": kernel_names(job.w["tmode"], job.seg)[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": kernel_names(job.w["tmode"], job.seg, job.w["tlog"], job.nb)[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": dom_ms,
                      "direction_frac": {"encode": (job.nbytes + total) / (enc_ms * 1e-3) / 1e9 / peak,
@@ -574,7 +588,7 @@ def traffic_probe(wl, tlog, dom_kernel):
            sys.executable, os.path.abspath(__file__), "--probe", "--workload", wl]
     if tlog is not None:
         cmd += ["--table-log", str(tlog)]
-    cmd += ["--segment-size", str(SEGMENT_SIZE)]
+    cmd += ["--segment-size", str(SEGMENT_SIZE), "--n-states", str(N_STATES)]
     try:
         subprocess.run(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=420, check=True)
         import csv
@@ -732,6 +746,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--table-log", type=int, default=None, help="override the workload's table_log (BASELINE config 3 sweeps 9/11/12)")
+    ap.add_argument("--n-states", type=int, default=None, help="interleaved states per block (default 128; 1 and 2 are the reference's own formats)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-configs", action="store_true")
@@ -740,7 +755,9 @@ def main():
     ap.add_argument("--segment-size", type=int, default=None,
                     help="bytes per independently coded segment of a block (per-block tables); 0 = one stream per block")
     args = ap.parse_args()
-    global SEGMENT_SIZE
+    global SEGMENT_SIZE, N_STATES
+    if args.n_states is not None:
+        N_STATES = args.n_states
     if args.segment_size is not None:
         SEGMENT_SIZE = args.segment_size
     if args.impl == "reference":
