@@ -135,28 +135,37 @@ __global__ void __launch_bounds__(512, 2) k_decode128_blocks(DecArgs a)
         const bool out_aligned = (((uintptr_t)out) & 3) == 0;
         bool bad = false;
         uint32_t i0 = 0;
-        for (; i0 + 128 <= body; i0 += 128) {
-            if ((cur >> 5) < lowq + 56 && lowq) refill();   // a round takes at most 52 words
-            uint32_t e0 = lds_u32(tab_saddr + s0 * 4), e1 = lds_u32(tab_saddr + s1 * 4);   // fse.rs:363-373, four chains
-            uint32_t e2 = lds_u32(tab_saddr + s2 * 4), e3 = lds_u32(tab_saddr + s3 * 4);
-            uint32_t n0 = e0 >> 24, n1 = e1 >> 24, n2 = e2 >> 24, n3 = e3 >> 24;
-            uint32_t n23 = n2 + n3, n123 = n1 + n23, nbs = n0 + n123;
-            uint32_t incl = warp_incl_add_pred(nbs);
-            uint64_t w = ring_bits64(cur - incl);           // state 4l's bits are the uppermost of the lane's window
-            uint32_t tot = __shfl_sync(FULL, incl, 31);
-            if (tot > cur - floor_bits) { bad = true; break; }
-            s0 = (e0 & 0xffffu) + ((uint32_t)(w >> n123) & ~(0xffffffffu << n0));
-            s1 = (e1 & 0xffffu) + ((uint32_t)(w >> n23) & ~(0xffffffffu << n1));
-            s2 = (e2 & 0xffffu) + ((uint32_t)(w >> n3) & ~(0xffffffffu << n2));
-            s3 = (e3 & 0xffffu) + ((uint32_t)w & ~(0xffffffffu << n3));
-            uint32_t sy = __byte_perm(__byte_perm(e0, e1, 0x0062), __byte_perm(e2, e3, 0x0062), 0x5410);   // byte 2 of e0..e3
-            if (out_aligned) *reinterpret_cast<uint32_t *>(out + i0 + 4 * lane) = sy;
-            else {
-                out[i0 + 4 * lane] = (uint8_t)sy; out[i0 + 4 * lane + 1] = (uint8_t)(sy >> 8);
-                out[i0 + 4 * lane + 2] = (uint8_t)(sy >> 16); out[i0 + 4 * lane + 3] = (uint8_t)(sy >> 24);
-            }
-            cur -= tot;
+        // refill when fewer than 56 words lie between the read position and the ring's lowest word (a round takes at most
+        // 52); the threshold only changes in refill(), and is 0 (never reached) once the ring holds the first word
+        uint32_t thr = lowq ? (lowq + 56) << 5 : 0u;
+#define DEC128W_ROUND(STORE)                                                                                          \
+        {                                                                                                             \
+            if (cur < thr) { refill(); thr = lowq ? (lowq + 56) << 5 : 0u; }                                          \
+            uint32_t e0 = lds_u32(tab_saddr + s0 * 4), e1 = lds_u32(tab_saddr + s1 * 4);   /* fse.rs:363-373, four chains */ \
+            uint32_t e2 = lds_u32(tab_saddr + s2 * 4), e3 = lds_u32(tab_saddr + s3 * 4);                                \
+            uint32_t n0 = e0 >> 24, n1 = e1 >> 24, n2 = e2 >> 24, n3 = e3 >> 24;                                        \
+            uint32_t n23 = n2 + n3, n123 = n1 + n23, nbs = n0 + n123;                                                   \
+            uint32_t incl = warp_incl_add_pred(nbs);                                                                    \
+            uint64_t w = ring_bits64(cur - incl);           /* state 4l's bits are the uppermost of the lane's window */ \
+            uint32_t tot = __shfl_sync(FULL, incl, 31);                                                                 \
+            if (tot > cur - floor_bits) { bad = true; break; }                                                          \
+            s0 = (e0 & 0xffffu) + ((uint32_t)(w >> n123) & ~(0xffffffffu << n0));                                       \
+            s1 = (e1 & 0xffffu) + ((uint32_t)(w >> n23) & ~(0xffffffffu << n1));                                        \
+            s2 = (e2 & 0xffffu) + ((uint32_t)(w >> n3) & ~(0xffffffffu << n2));                                         \
+            s3 = (e3 & 0xffffu) + ((uint32_t)w & ~(0xffffffffu << n3));                                                 \
+            uint32_t sy = __byte_perm(__byte_perm(e0, e1, 0x0062), __byte_perm(e2, e3, 0x0062), 0x5410);   /* byte 2 of e0..e3 */ \
+            STORE;                                                                                                      \
+            cur -= tot;                                                                                                 \
         }
+        if (out_aligned) {
+            uint32_t *const ow = reinterpret_cast<uint32_t *>(out) + lane;   // the index stays 32 bits wide
+            for (; i0 + 128 <= body; i0 += 128) DEC128W_ROUND(ow[i0 >> 2] = sy)
+        } else {
+            for (; i0 + 128 <= body; i0 += 128)
+                DEC128W_ROUND(out[i0 + 4 * lane] = (uint8_t)sy; out[i0 + 4 * lane + 1] = (uint8_t)(sy >> 8);
+                              out[i0 + 4 * lane + 2] = (uint8_t)(sy >> 16); out[i0 + 4 * lane + 3] = (uint8_t)(sy >> 24))
+        }
+#undef DEC128W_ROUND
         if (!bad && i0 < body) {                            // last partial round
             if ((cur >> 5) < lowq + 56 && lowq) refill();
             uint32_t ia = i0 + 4 * lane;
