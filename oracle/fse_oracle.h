@@ -97,7 +97,7 @@ int fse_or_optimal_log2(const fse_or_hist *h, uint32_t *log2_out);             /
 /* returns FSE_OR_OK, or 1 when normalize_slow was taken (:144-145), or <0 */
 int fse_or_normalize(const fse_or_hist *h, uint32_t log2, fse_or_norm *out);   /* :95-261 */
 int fse_or_norm_new(const uint8_t *data, size_t n, fse_or_norm *out);          /* :299-303 */
-/* libzstd's FSE_normalizeCount (not the crate's arithmetic; parity unpinned, see fse_oracle.c) */
+/* libzstd's FSE_normalizeCount (not the crate's arithmetic; pinned against libzstd's own output, see fse_oracle.c) */
 int fse_or_normalize_zstd(const fse_or_hist *h, uint32_t table_log, int use_low_prob_count, fse_or_norm *out);
 size_t fse_or_write_bound(const fse_or_norm *nh);                              /* :330-337 */
 /* appends at dst[0..]; returns bytes written (>=0) or <0; *bits_out = header bits */

@@ -1,6 +1,7 @@
-"""the second normaliser, libzstd's FSE_normalizeCount.  No libzstd with FSE symbols exists in this image,
-so the oracle's restatement is pinned by vectors derived by hand from the published algorithm (each derivation is spelled
-out below), and the GPU kernel is compared with the oracle on random histograms."""
+"""the second normaliser, libzstd's FSE_normalizeCount.  No libzstd exports the function, so the oracle's
+restatement is pinned here by vectors derived by hand from the published algorithm (each derivation is spelled out below)
+and the GPU kernel is compared with the oracle on random histograms; tests/test_zstd_interop.py adds libzstd's own output
+on real histograms (read back out of the frames it writes)."""
 import numpy as np
 import pytest
 
