@@ -10,7 +10,38 @@ import pytest
 import oracle_lib as O
 import zstd_interop as ZI
 
-pytestmark = pytest.mark.skipif(ZI.zstd() is None, reason="libzstd not available")
+needs_zstd = pytest.mark.skipif(ZI.zstd() is None, reason="libzstd not available")
+
+
+def _golden():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "zstd_weight_streams.json")) as f:
+        return json.load(f)["streams"]
+
+
+def test_oracle_decodes_the_committed_libzstd_streams():
+    """tests/golden/zstd_weight_streams.json (make_zstd_vectors.py): bytes libzstd 1.5.5 wrote, and what they decode to"""
+    g = _golden()
+    assert len(g) >= 6
+    for v in g:
+        blob = bytes.fromhex(v["blob"])
+        rc, nh, consumed = O.ncount_read(blob)
+        assert rc == 0 and nh.log2 == v["table_log"] and consumed == v["header_bytes"]
+        assert list(nh.table[:nh.table_len]) == v["norm"]
+        assert O.decompress_n_exhaust(blob, 2, 255).hex() == v["weights"]
+        counts = np.bincount(np.frombuffer(bytes.fromhex(v["weights"]), dtype=np.uint8), minlength=256).tolist()
+        rcz, nz = O.normalize_zstd(O.hist_from_counts(counts), v["table_log"], use_low_prob_count=False)
+        assert rcz == 0 and list(nz.table[:len(v["norm"])]) == v["norm"]
+
+
+@pytest.mark.gpu
+def test_gpu_decodes_the_committed_libzstd_streams():
+    import entropy_coders_b200 as E
+    for v in _golden():
+        out = bytearray()
+        n = E.fse_decompress2(bytes.fromhex(v["blob"]), out)
+        assert n == len(out) and bytes(out).hex() == v["weights"]
 
 CASES = [(1, 4000, 90, 0.93, 20), (2, 6000, 120, 0.95, 0), (3, 3000, 60, 0.90, 64), (4, 12000, 200, 0.97, 10),
          (5, 5000, 150, 0.985, 30), (6, 2500, 40, 0.85, 97)]
@@ -26,6 +57,7 @@ def _zstd_weight_blob(case):
     return src, info, bytes(info["tree"][1:1 + h])
 
 
+@needs_zstd
 def test_oracle_decodes_the_fse_streams_libzstd_writes():
     used = 0
     for case in CASES:
@@ -41,6 +73,7 @@ def test_oracle_decodes_the_fse_streams_libzstd_writes():
     assert used >= 4
 
 
+@needs_zstd
 def test_normalize_zstd_equals_libzstd_on_real_histograms():
     """HUF_compressWeights: FSE_normalizeCount(norm, tableLog, count, n, maxSymbol, useLowProbCount = 0); the header of the
     weight stream carries its result, the decoded weights give its input"""
@@ -59,6 +92,7 @@ def test_normalize_zstd_equals_libzstd_on_real_histograms():
     assert used >= 4
 
 
+@needs_zstd
 @pytest.mark.parametrize("table_log", [5, 6])
 @pytest.mark.parametrize("seed", list(range(11, 31)))
 def test_libzstd_decodes_the_fse_streams_the_oracle_writes(seed, table_log):
@@ -68,6 +102,7 @@ def test_libzstd_decodes_the_fse_streams_the_oracle_writes(seed, table_log):
     assert ZI.zstd_decompress(ZI.craft_frame(lits, blob, weights), 2048) == lits
 
 
+@needs_zstd
 def test_the_streams_sent_to_libzstd_cover_low_probability_symbols():
     """the -1 counts (spread from the top of the table, fse.rs:122-125 / FSE_buildDTable's highThreshold) are part of
     what the previous test sends"""
@@ -80,6 +115,7 @@ def test_the_streams_sent_to_libzstd_cover_low_probability_symbols():
     assert seen >= 3
 
 
+@needs_zstd
 @pytest.mark.gpu
 def test_gpu_decodes_the_fse_streams_libzstd_writes():
     import entropy_coders_b200 as E
@@ -98,6 +134,7 @@ def test_gpu_decodes_the_fse_streams_libzstd_writes():
     assert used >= 4
 
 
+@needs_zstd
 @pytest.mark.gpu
 @pytest.mark.parametrize("table_log", [5, 6])
 def test_libzstd_decodes_the_fse_streams_the_gpu_writes(table_log):
@@ -116,6 +153,7 @@ def test_libzstd_decodes_the_fse_streams_the_gpu_writes(table_log):
     ctx.close()
 
 
+@needs_zstd
 @pytest.mark.gpu
 def test_gpu_normalize_zstd_equals_libzstd_on_real_histograms():
     import entropy_coders_b200 as E
