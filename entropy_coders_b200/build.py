@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SRC = os.path.join(HERE, "csrc", "fse_b200.cu")
-DEPS = [SRC, os.path.join(HERE, "csrc", "fse_bitio.cuh"), os.path.join(HERE, "csrc", "fse_zstd_norm.cuh"), os.path.join(HERE, "csrc", "fse_shared_enc.cuh"), os.path.join(HERE, "csrc", "fse_shared_dec.cuh"), os.path.join(HERE, "csrc", "fse_decode128c.cuh"), os.path.join(HERE, "csrc", "fse_encode128.cuh"), os.path.join(HERE, "csrc", "fse_kernels128.cuh"), os.path.join(HERE, "csrc", "fse_decode64w.cuh"), os.path.join(HERE, "csrc", "fse_hist16.cuh"), os.path.join(HERE, "csrc", "fse_decode64c.cuh"), os.path.join(HERE, "csrc", "fse_kernels64.cuh"), os.path.join(HERE, "csrc", "fse_kernels.cuh"), os.path.join(HERE, "csrc", "fse_device.cuh"),
+DEPS = [SRC, os.path.join(HERE, "csrc", "fse_bitio.cuh"), os.path.join(HERE, "csrc", "fse_zstd_norm.cuh"), os.path.join(HERE, "csrc", "fse_shared_enc.cuh"), os.path.join(HERE, "csrc", "fse_shared_dec.cuh"), os.path.join(HERE, "csrc", "fse_tps.cuh"), os.path.join(HERE, "csrc", "fse_decode128c.cuh"), os.path.join(HERE, "csrc", "fse_encode128.cuh"), os.path.join(HERE, "csrc", "fse_kernels128.cuh"), os.path.join(HERE, "csrc", "fse_decode64w.cuh"), os.path.join(HERE, "csrc", "fse_hist16.cuh"), os.path.join(HERE, "csrc", "fse_decode64c.cuh"), os.path.join(HERE, "csrc", "fse_kernels64.cuh"), os.path.join(HERE, "csrc", "fse_kernels.cuh"), os.path.join(HERE, "csrc", "fse_device.cuh"),
         os.path.join(ROOT, "include", "fse_b200.h")]
 OUT = os.path.join(HERE, "libfse_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -6,6 +6,7 @@
 #include "fse_hist16.cuh"
 #include "fse_shared_enc.cuh"
 #include "fse_shared_dec.cuh"
+#include "fse_tps.cuh"
 #include "fse_bitio.cuh"
 #include "fse_zstd_norm.cuh"
 
@@ -64,6 +65,7 @@ struct fse_b200_ctx {
     std::string err;
     // workspaces
     DevBuf counts, hist_pieces, hlen, plen, scratch, offsets_tmp, status_tmp, misc;
+    DevBuf tps_enc_tab, tps_enc_tt, tps_dec_tab, tps_meta;      // per-block tables of the thread-per-stream coders (fse_tps.cuh)
     DevBuf stage_in, stage_out, stage_off, stage_status;  // host-buffer conveniences
     HostBuf pin;
     // global table
@@ -281,6 +283,8 @@ int fse_b200_create(int device, void *stream, fse_b200_ctx **out)
     cudaFuncSetAttribute(k_decode128c_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 64);   // 16 bytes of static shared memory (block queue)
     cudaFuncSetAttribute(k_encode128_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 64);   // 16 bytes of static shared memory (block queue)
     cudaFuncSetAttribute(k_build_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
+    cudaFuncSetAttribute(k_tps_prepare_enc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
+    cudaFuncSetAttribute(k_tps_prepare_dec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
     cudaFuncSetAttribute(k_encode_sh_global<16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 64);
     cudaFuncSetAttribute(k_decode_sh_global, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 64);
     cudaFuncSetAttribute(k_encode_sh_blocks<16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 64);
@@ -296,7 +300,7 @@ void fse_b200_destroy(fse_b200_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf *bufs[] = {&ctx->counts, &ctx->hist_pieces, &ctx->hlen, &ctx->plen, &ctx->scratch, &ctx->offsets_tmp, &ctx->status_tmp, &ctx->misc,
+    DevBuf *bufs[] = {&ctx->tps_enc_tab, &ctx->tps_enc_tt, &ctx->tps_dec_tab, &ctx->tps_meta, &ctx->counts, &ctx->hist_pieces, &ctx->hlen, &ctx->plen, &ctx->scratch, &ctx->offsets_tmp, &ctx->status_tmp, &ctx->misc,
                       &ctx->stage_in, &ctx->stage_out, &ctx->stage_off, &ctx->stage_status, &ctx->g_enc_table,
                       &ctx->g_enc_tt, &ctx->g_dec_table, &ctx->g_norm, &ctx->g_meta, &ctx->g_hdr,
                       &ctx->lut[0], &ctx->lut[1], &ctx->lut[2], &ctx->lut[3]};
@@ -736,6 +740,16 @@ int fse_b200_compress_blocks_async(fse_b200_ctx *ctx, const uint8_t *d_src, size
         const int g = (int)std::min<size_t>(nb, (size_t)ctx->num_sms);
         Timed t(ctx, FSE_B200_K_ENCODE);
         k_encode_sh_global<16, 16><<<g, w * 32, fixed + w * pw, ctx->stream>>>(a);
+    } else if (!global && p->n_states <= 2 && !p->flags && tlmax <= 12 && nb >= (size_t)dev_opt("FSE_B200_TPS_MIN", (int)TPS_MIN_BLOCKS)) {
+        // the reference's own one- / two-state streams, many of them: one thread per stream (fse_tps.cuh)
+        CK(ctx->tps_enc_tab.reserve((nb << tlmax) * sizeof(uint16_t)));
+        CK(ctx->tps_enc_tt.reserve(nb * 256 * sizeof(uint2)));
+        CK(ctx->tps_meta.reserve(nb * sizeof(uint4)));
+        TpsTables g{ctx->tps_enc_tab.as<uint16_t>(), ctx->tps_enc_tt.as<uint2>(), nullptr, ctx->tps_meta.as<uint4>()};
+        Timed t(ctx, FSE_B200_K_ENCODE);
+        k_tps_prepare_enc<<<grid, wpc * 32, (size_t)wpc * per_warp, ctx->stream>>>(a, g);
+        k_tps_encode<<<(unsigned)((nb + 31) / 32), 32, 0, ctx->stream>>>(a, g);      // one warp per CTA: few blocks still reach every SM
+        ctx->launches++;
     } else {
         Timed t(ctx, FSE_B200_K_ENCODE);
         if (p->n_states == 128) k_encode128_blocks<<<grid, wpc * 32, (size_t)wpc * per_warp, ctx->stream>>>(a);
@@ -877,6 +891,19 @@ int fse_b200_decompress_blocks_async(fse_b200_ctx *ctx, const uint8_t *d_comp, s
         int wpc = pick_warps(nblocks, ctx->num_sms, lay.total, ctx->smem_optin, 16);
         if (wpc < 1) return fail(ctx, FSE_B200_ERR_UNSUPPORTED, "table_log too large for shared memory");
         int grid = (int)std::min<size_t>((nblocks + wpc - 1) / wpc, (size_t)ctx->num_sms);
+        if (!global && !a.exhaust && p->n_states <= 2 && tlmax <= 12 &&
+            nblocks >= (size_t)dev_opt("FSE_B200_TPS_MIN", (int)(TPS_MIN_BLOCKS * p->n_states))) {      // decode, 2 states: even at 4 096 blocks
+            // the reference's own one- / two-state streams, many of them: one thread per stream (fse_tps.cuh)
+            CK(ctx->tps_dec_tab.reserve((nblocks << tlmax) * sizeof(uint32_t)));
+            CK(ctx->tps_meta.reserve(nblocks * sizeof(uint4)));
+            TpsTables g{nullptr, nullptr, ctx->tps_dec_tab.as<uint32_t>(), ctx->tps_meta.as<uint4>()};
+            Timed t(ctx, FSE_B200_K_DECODE);
+            k_tps_prepare_dec<<<grid, wpc * 32, (size_t)wpc * lay.total, ctx->stream>>>(a, g);
+            k_tps_decode<<<(unsigned)((nblocks + 31) / 32), 32, 0, ctx->stream>>>(a, g);
+            ctx->launches++;
+            CK(cudaGetLastError());
+            return FSE_B200_OK;
+        }
         Timed t(ctx, FSE_B200_K_DECODE);
         if (p->n_states == 64) k_decode64_blocks<<<grid, wpc * 32, (size_t)wpc * lay.total, ctx->stream>>>(a);
         else k_decode_blocks<<<grid, wpc * 32, (size_t)wpc * lay.total, ctx->stream>>>(a);

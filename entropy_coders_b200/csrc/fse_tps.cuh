@@ -1,0 +1,320 @@
+// fse_tps.cuh -- the reference's OWN stream formats (one or two states per stream: fse_compress / fse_compress2,
+// src/lib.rs:112-248) when there are many streams: one THREAD per stream.
+//
+// A stream with one or two states is one or two serial chains (fse.rs:227-239, :363-373): a warp per block has one or two
+// lanes at work (c4, 65 536 blocks: 26 GB/s encode, 14 GB/s decode at two states).  With thousands of blocks the
+// parallelism is across streams, so here every lane runs its own block exactly as the CPU does -- states and the 64-bit bit
+// accumulator (writer.rs:140-149) / the stack window (stack_reader.rs:97-172) in registers -- against that block's tables in
+// GLOBAL memory: a look-up costs L1 / L2 / DRAM latency instead of shared-memory latency, and thousands of chains hide
+// it.  The tables are built by one warp per block with the code of the warp-per-block kernels (k_tps_prepare_*), which
+// also settles every block that needs no coder (escapes, errors).  Same bytes as k_encode_blocks / k_decode_blocks
+// (tests/test_gpu_parity.py::test_many_streams_*); chosen by the dispatcher from TPS_MIN_BLOCKS blocks on.
+// Measured (tools/tps_sweep.py, 128 KiB geometric blocks, two states; warp per block in brackets): 4 096 blocks encode
+// 40.8 (28.6) GB/s, decode 14.5 (15.8); 8 192: 58 (29) / 29 (16); 16 384: 72 (32) / 25 (18); c4's 65 536: 51 (26) / 44 (14),
+// one state 48 (13) / 43 (7).  A thread takes the same ~13 / 37 ms for its 128 KiB whatever the block count is (one
+// dependent look-up per symbol pair), until the tables outgrow the L2 (decode: 8 KiB per block) and the look-ups go to DRAM.
+#pragma once
+#include "fse_kernels.cuh"
+
+namespace fsed {
+
+constexpr uint32_t TPS_MIN_BLOCKS = 4096;
+
+// per block: x = table_log, y = header bytes (encode) / header bytes consumed (decode), z = 1 when the coder has work
+struct TpsTables {
+    uint16_t *enc_tab;      // [nblocks << tlmax]
+    uint2 *enc_tt;          // [nblocks * 256]
+    uint32_t *dec_tab;      // [nblocks << tlmax]
+    uint4 *meta;            // [nblocks]
+};
+
+// ---------------------------------------------------------------------------------- encode
+// one warp per block: k_encode_blocks up to the tables (same escapes, same header bytes), tables to global memory
+__global__ void __launch_bounds__(512) k_tps_prepare_enc(EncArgs a, TpsTables g)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    const EncLayout lay = enc_layout(a.tlmax);
+    uint8_t *my = smem_raw + (size_t)warp * lay.total;
+    uint16_t *tab = reinterpret_cast<uint16_t *>(my + lay.tab);
+    uint2 *tt = reinterpret_cast<uint2 *>(my + lay.tt);
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(my + lay.work);
+    int32_t *norm = reinterpret_cast<int32_t *>(my + lay.work + 1024);
+    uint32_t *cum = reinterpret_cast<uint32_t *>(my + lay.work + 2048);
+    uint8_t *spread = my + lay.work + 3072;
+    uint32_t *rows = reinterpret_cast<uint32_t *>(my + lay.rows);
+    const uint32_t N = a.n_states;
+    for (uint32_t b = blockIdx.x * wpc + warp; b < a.nblocks; b += gridDim.x * wpc) {
+        const size_t off = (size_t)b * a.block_size;
+        const uint32_t bn = (uint32_t)min((size_t)a.block_size, a.n - off);
+        const uint8_t *bsrc = a.src + off;
+        uint8_t *bs = a.scratch + (size_t)b * a.stride;
+        uint32_t *hdr_words = reinterpret_cast<uint32_t *>(bs);
+        uint32_t log2 = 0;
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 8; k++) cnt[k * 32 + lane] = a.counts[(size_t)b * 256 + k * 32 + lane];
+        __syncwarp();
+        uint32_t table_len;
+        int rc = warp_normalize(cnt, (uint64_t)bn, a.req_log2, norm, lane, log2, table_len);
+        uint32_t hl = 0, ready = 0;
+        int st = ST_OK;
+        if (rc < 0) {                                    // blocks the reference panics on: escapes (include/fse_b200.h)
+            if (table_len <= 1) { if (lane == 0) { bs[0] = 0x0E; bs[1] = 0x00; } hl = 2; st = 2; }
+            else if (bn <= 4) { if ((uint32_t)lane < bn) bs[1 + lane] = bsrc[lane]; if (lane == 0) bs[0] = 0x0F; hl = 1 + bn; st = 1; }
+            else st = rc;
+        } else if (bn < N) {                             // fewer symbols than states: lib.rs:121,154,156
+            if ((uint32_t)lane < bn) bs[1 + lane] = bsrc[lane];
+            if (lane == 0) bs[0] = 0x0F;
+            hl = 1 + bn; st = 1;
+        } else if (log2 > a.tlmax) {
+            st = ST_UNSUPPORTED;
+        } else {
+            const uint32_t hbits = warp_ncount_write(norm, log2, table_len, rows, hdr_words, lane);
+            hl = (hbits + 7) >> 3;
+            warp_spread(norm, log2, table_len, spread, cum, tab, lane);
+            warp_build_encode(norm, log2, table_len, spread, cum, tab, tt, lane);
+            __syncwarp();
+            uint16_t *gt = g.enc_tab + ((size_t)b << a.tlmax);
+            uint2 *gs = g.enc_tt + (size_t)b * 256;
+            for (uint32_t i = lane; i < (1u << log2) / 2; i += 32)
+                reinterpret_cast<uint32_t *>(gt)[i] = reinterpret_cast<const uint32_t *>(tab)[i];
+#pragma unroll
+            for (int k = 0; k < 8; k++) gs[k * 32 + lane] = tt[k * 32 + lane];
+            ready = 1;
+        }
+        if (lane == 0) {
+            g.meta[b] = make_uint4(log2, hl, ready, 0u);
+            a.hlen[b] = hl;
+            a.plen[b] = 0;
+            a.status[b] = st;
+        }
+    }
+}
+
+// one thread per block: Encoder::new_first_symbol for the highest symbol of each state, encode_raw downwards, finish
+// (fse.rs:210-250), marker bit (lib.rs:141,181); BitStackWriter as a 64-bit accumulator flushed in 32-bit words
+__global__ void __launch_bounds__(32) k_tps_encode(EncArgs a, TpsTables g)
+{
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.nblocks) return;
+    const uint4 m = g.meta[b];
+    if (!m.z) return;
+    const uint32_t log2 = m.x, N = a.n_states;
+    const size_t off = (size_t)b * a.block_size;
+    const uint32_t bn = (uint32_t)min((size_t)a.block_size, a.n - off);
+    const uint8_t *__restrict__ src = a.src + off;
+    const uint16_t *__restrict__ tab = g.enc_tab + ((size_t)b << a.tlmax);
+    const uint2 *__restrict__ tt = g.enc_tt + (size_t)b * 256;
+    uint32_t *pay = reinterpret_cast<uint32_t *>(a.scratch + (size_t)b * a.stride + HDR_RESERVE);
+    const uint32_t cap = a.pay_cap_words;
+    unsigned long long acc = 0;
+    uint32_t cnt = 0, wp = 0;
+    auto put = [&](uint32_t v, uint32_t nb) {                 // v < 2^nb, nb <= 16, cnt < 32
+        acc |= (unsigned long long)v << cnt;
+        cnt += nb;
+        if (cnt >= 32) {
+            if (wp < cap) __stcs(pay + wp, (uint32_t)acc);
+            wp++;
+            acc >>= 32;
+            cnt -= 32;
+        }
+    };
+    auto step = [&](uint32_t &s, uint32_t sym) {              // fse.rs:227-239
+        const uint2 t = __ldg(tt + sym);
+        const uint32_t nb = (t.x + s) >> 16;
+        put(s & ((1u << nb) - 1u), nb);
+        s = __ldg(tab + ((int32_t)(s >> nb) + (int32_t)t.y));
+    };
+    int32_t i = (int32_t)bn - 1;
+    if (N == 2) {
+        // state i & 1 codes symbol i; the two highest symbols initialise the states
+        uint32_t sa = enc_first(tab, tt, __ldg(src + i));     // parity of bn - 1
+        uint32_t sb = enc_first(tab, tt, __ldg(src + i - 1));
+        i -= 2;
+        // Two independent chains.  Only the next-state look-up depends on the state: the symbols are fetched two pairs
+        // ahead and their transforms one pair ahead, so that a pair costs one memory latency, not three.
+        uint32_t ya = 0, yb = 0, ya2 = 0, yb2 = 0;
+        uint2 ta = make_uint2(0u, 0u), tb = ta;
+        if (i >= 1) { ya = __ldg(src + i); yb = __ldg(src + i - 1); ta = __ldg(tt + ya); tb = __ldg(tt + yb); }
+        if (i >= 3) { ya2 = __ldg(src + i - 2); yb2 = __ldg(src + i - 3); }
+        for (; i >= 1; i -= 2) {
+            const uint2 ca = ta, cb = tb;
+            if (i >= 3) { ta = __ldg(tt + ya2); tb = __ldg(tt + yb2); }
+            if (i >= 5) { ya2 = __ldg(src + i - 4); yb2 = __ldg(src + i - 5); }
+            const uint32_t na = (ca.x + sa) >> 16, nb = (cb.x + sb) >> 16;
+            const uint32_t va = sa & ((1u << na) - 1u), vb = sb & ((1u << nb) - 1u);
+            sa = __ldg(tab + ((int32_t)(sa >> na) + (int32_t)ca.y));
+            sb = __ldg(tab + ((int32_t)(sb >> nb) + (int32_t)cb.y));
+            put(va, na);
+            put(vb, nb);
+        }
+        if (i == 0) step(sa, __ldg(src));                     // sa is the state of symbol 0's parity here
+        // final states 1, 0: state of parity 1 first.  sa belongs to parity (bn - 1) & 1.
+        const uint32_t mask = (1u << log2) - 1u;
+        const uint32_t s1 = ((bn - 1) & 1) ? sa : sb, s0 = ((bn - 1) & 1) ? sb : sa;
+        put(s1 & mask, log2);
+        put(s0 & mask, log2);
+    } else {
+        uint32_t s = enc_first(tab, tt, __ldg(src + i));
+        i--;
+        uint32_t y2 = 0;                                      // the same prefetch for the single chain
+        uint2 t = make_uint2(0u, 0u);
+        if (i >= 0) t = __ldg(tt + __ldg(src + i));
+        if (i >= 1) y2 = __ldg(src + i - 1);
+        for (; i >= 0; i--) {
+            const uint2 c = t;
+            if (i >= 1) t = __ldg(tt + y2);
+            if (i >= 2) y2 = __ldg(src + i - 2);
+            const uint32_t nb = (c.x + s) >> 16;
+            put(s & ((1u << nb) - 1u), nb);
+            s = __ldg(tab + ((int32_t)(s >> nb) + (int32_t)c.y));
+        }
+        put(s & ((1u << log2) - 1u), log2);
+    }
+    put(1u, 1u);
+    const uint32_t bits = wp * 32 + cnt;
+    if (cnt) { if (wp < cap) pay[wp] = (uint32_t)acc; wp++; }
+    if (wp > cap) { a.hlen[b] = 0; a.plen[b] = 0; a.status[b] = ST_CAPACITY; return; }
+    a.plen[b] = (bits + 7) >> 3;
+}
+
+// ---------------------------------------------------------------------------------- decode
+__global__ void __launch_bounds__(512) k_tps_prepare_dec(DecArgs a, TpsTables g)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    const DecLayout lay = dec_layout(a.tlmax);
+    uint8_t *my = smem_raw + (size_t)warp * lay.total;
+    uint32_t *tab = reinterpret_cast<uint32_t *>(my + lay.tab);
+    int32_t *norm = reinterpret_cast<int32_t *>(my + lay.norm);
+    uint32_t *ctr = reinterpret_cast<uint32_t *>(my + lay.ctr);
+    uint8_t *spread = my + lay.spread;
+    const uint32_t N = a.n_states;
+    for (uint32_t b = blockIdx.x * wpc + warp; b < a.nblocks; b += gridDim.x * wpc) {
+        const size_t off = (size_t)b * a.block_size;
+        const uint32_t bn = (uint32_t)min((size_t)a.block_size, a.n - off);
+        uint8_t *out = a.dst + off;
+        int st = ST_OK;
+        const uint8_t *cs;
+        uint32_t clen, log2 = 0, consumed = 0, ready = 0;
+        __syncwarp();
+        if (!dec_block_prologue(a, b, bn, N, out, lane, cs, clen, st)) {      // else: bad offsets, escape blocks: settled
+#pragma unroll
+            for (int k = 0; k < 8; k++) norm[k * 32 + lane] = 0;
+            __syncwarp();
+            uint32_t table_len = 0;
+            int rc = 0;
+            if (lane == 0) rc = ncount_read_serial(cs, clen, norm, log2, table_len, consumed);
+            rc = __shfl_sync(FULL, rc, 0);
+            log2 = __shfl_sync(FULL, log2, 0);
+            table_len = __shfl_sync(FULL, table_len, 0);
+            consumed = __shfl_sync(FULL, consumed, 0);
+            __syncwarp();
+            if (rc < 0) st = rc;
+            else if (log2 > a.tlmax) st = ST_UNSUPPORTED;
+            else if (bn < N) st = ST_LENGTH;
+            else {
+                warp_spread(norm, log2, table_len, spread, ctr, reinterpret_cast<uint16_t *>(tab), lane);
+                warp_build_decode(norm, log2, table_len, spread, ctr, tab, lane);
+                __syncwarp();
+                uint32_t *gt = g.dec_tab + ((size_t)b << a.tlmax);
+                for (uint32_t i = lane; i < (1u << log2); i += 32) gt[i] = tab[i];
+                ready = 1;
+            }
+        }
+        if (lane == 0) {
+            g.meta[b] = make_uint4(log2, consumed, ready, 0u);
+            a.status[b] = st;
+        }
+    }
+}
+
+// one thread per block: BitStackReader::new (marker), Decoder::new for states 0 .. N-1, decode_symbol for the body,
+// finish for the last N symbols (fse.rs:341-386, lib.rs:187-248), length driven.  The stack is read through a 64-bit
+// window of two aligned words, the next lower word is loaded one refill ahead.
+__global__ void __launch_bounds__(32) k_tps_decode(DecArgs a, TpsTables g)
+{
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.nblocks) return;
+    const uint4 m = g.meta[b];
+    if (!m.z) return;
+    const uint32_t log2 = m.x, consumed = m.y, N = a.n_states;
+    const size_t off = (size_t)b * a.block_size;
+    const uint32_t bn = (uint32_t)min((size_t)a.block_size, a.n - off);
+    uint8_t *out = a.dst + off;
+    const uint32_t *__restrict__ tab = g.dec_tab + ((size_t)b << a.tlmax);
+    const unsigned long long o0 = a.offsets[b], o1 = a.offsets[b + 1];
+    const uint8_t *pay = a.comp + o0 + consumed;
+    const uint32_t plen = (uint32_t)(o1 - o0) - consumed;
+    if (plen == 0 || pay[plen - 1] == 0) { a.status[b] = ST_NO_MARKER; return; }       // stack_reader.rs:17-92
+    const uint32_t bias = (uint32_t)((uintptr_t)pay & 3);
+    const uint32_t *__restrict__ origin = reinterpret_cast<const uint32_t *>(pay - bias);
+    uint32_t cur = (plen - 1) * 8 + ilog2u(pay[plen - 1]) + 8 * bias;                   // marker position
+    const uint32_t floor_bits = 8 * bias;
+    if (cur - floor_bits < N * log2) { a.status[b] = ST_LENGTH; return; }               // lib.rs:197,224-225
+    // window: lo = word q0, hi = word q0 + 1, nx = word q0 - 1; bits at and above the marker are never used
+    uint32_t q0 = cur >> 5;
+    // the payload and the output are touched once: streaming loads / stores, so that the tables keep their place in the caches
+    uint32_t lo = __ldcs(origin + q0), hi = 0u, nx = q0 ? __ldcs(origin + q0 - 1) : 0u;
+    bool bad = false;
+    auto read = [&](uint32_t n) -> uint32_t {                 // n <= 16
+        if (cur - floor_bits < n) { bad = true; return 0u; }
+        cur -= n;
+        if ((cur >> 5) < q0) {                                // one word down at most
+            hi = lo; lo = nx; q0--;
+            nx = q0 ? __ldcs(origin + q0 - 1) : 0u;
+        }
+        return __funnelshift_r(lo, hi, cur & 31) & ((1u << n) - 1u);
+    };
+    const uint32_t body = bn - N;
+    const bool aligned = (((uintptr_t)out) & 3) == 0;
+    uint32_t i = 0;
+    if (N == 2) {
+        uint32_t s0 = read(log2), s1 = read(log2);            // Decoder::new, fse.rs:349-352: state 0 first
+        uint32_t e0 = __ldg(tab + s0), e1 = __ldg(tab + s1);
+        uint32_t word = 0;
+        for (; i + 2 <= body && !bad; i += 2) {               // fse.rs:363-373 on the two chains
+            const uint32_t b0 = read(e0 >> 24);
+            const uint32_t y0 = (e0 >> 16) & 0xffu;
+            s0 = (e0 & 0xffffu) + b0;
+            e0 = __ldg(tab + s0);
+            const uint32_t b1 = read(e1 >> 24);
+            const uint32_t y1 = (e1 >> 16) & 0xffu;
+            s1 = (e1 & 0xffffu) + b1;
+            e1 = __ldg(tab + s1);
+            if (aligned) {
+                word |= (y0 | (y1 << 8)) << ((i & 2) * 8);
+                if (i & 2) { __stcs(reinterpret_cast<uint32_t *>(out + (i & ~3u)), word); word = 0; }
+            } else {
+                out[i] = (uint8_t)y0;
+                out[i + 1] = (uint8_t)y1;
+            }
+        }
+        if (aligned && (i & 2) && !bad) { out[i - 2] = (uint8_t)word; out[i - 1] = (uint8_t)(word >> 8); }   // half a word pending
+        if (!bad && i < body) {                               // one more body symbol: state 0's turn (i is even)
+            const uint32_t b0 = read(e0 >> 24);
+            out[i] = (uint8_t)(e0 >> 16);
+            s0 = (e0 & 0xffffu) + b0;
+            e0 = __ldg(tab + s0);
+            i++;
+        }
+        if (!bad) {                                           // Decoder::finish: symbols body, body + 1 from states (i & 1), ...
+            out[i] = (uint8_t)(((i & 1) ? e1 : e0) >> 16);
+            out[i + 1] = (uint8_t)(((i & 1) ? e0 : e1) >> 16);
+        }
+    } else {
+        uint32_t s = read(log2);
+        uint32_t e = __ldg(tab + s);
+        for (; i < body && !bad; i++) {
+            const uint32_t bits = read(e >> 24);
+            out[i] = (uint8_t)(e >> 16);
+            s = (e & 0xffffu) + bits;
+            e = __ldg(tab + s);
+        }
+        if (!bad) out[i] = (uint8_t)(e >> 16);
+    }
+    a.status[b] = (bad || cur != floor_bits) ? ST_LENGTH : ST_OK;
+}
+
+}  // namespace fsed

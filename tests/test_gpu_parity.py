@@ -1005,3 +1005,71 @@ def test_global_table_with_unknown_symbols_is_memory_safe(ctx):
     d, off, st, total = ctx.compress_blocks(dev(ctx, a), bs, 11, 128, table_mode=1)
     out, st2 = ctx.decompress_blocks(d, total, off, a.size, bs, 11, 128, table_mode=1)
     assert np.array_equal(out.cpu().numpy(), a) and (st2.cpu().numpy() >= 0).all()
+
+
+# ------------------------------------------------------------------------------------ thread-per-stream coders (fse_tps.cuh)
+
+@pytest.mark.parametrize("n_states", [1, 2])
+@pytest.mark.parametrize("block_size,table_log", [(1000, 0), (1001, 9), (777, 0), (2048, 12)])
+def test_many_streams_in_the_reference_formats(ctx, n_states, block_size, table_log):
+    """>= 4096 blocks of one or two states take the thread-per-stream kernels: every block's bytes equal the oracle's
+    fse_compress / fse_compress2 (odd and even lengths: the state of a symbol is its index's parity), escapes included,
+    and the decoder returns the input"""
+    nb = 4500
+    n = nb * block_size - 333                                  # ragged last block
+    src = O.generate("text" if block_size & 1 else "geo", 0xC0FFEE10 + n_states + block_size, n)
+    src[5 * block_size:6 * block_size] = 0                     # all-zero block: 0x0E escape (histogram.rs:98)
+    src[9 * block_size:10 * block_size] = 65                   # one symbol: still FSE, zero payload bits per symbol
+    blocks, st, (d, off, total) = gpu_blocks(ctx, src, block_size, table_log, n_states)
+    scratch, sizes, status = O.compress_blocks(src, block_size, table_log, n_states, threads=8)
+    assert len(blocks) == nb == len(sizes)
+    for b in range(nb):
+        if status[b] == 0:
+            assert st[b] == 0 and blocks[b] == scratch[b, :int(sizes[b])].tobytes(), "block %d differs" % b
+        else:
+            assert st[b] in (1, 2), (b, st[b], status[b])     # what the reference panics on is stored with an escape
+    out, dst_ = ctx.decompress_blocks(d, total, dev(ctx, off), n, block_size, table_log, n_states)
+    dst_ = dst_.cpu().numpy()
+    assert ((dst_ == 0) | (dst_ == 1) | (dst_ == 2)).all() and np.array_equal(out.cpu().numpy(), src)
+
+
+@pytest.mark.parametrize("n_states", [1, 2])
+def test_many_streams_decode_the_oracles_streams_and_survive_damage(ctx, n_states):
+    """the thread-per-stream decoder on streams written by the oracle, then the seeded damage of
+    test_corrupted_streams_never_fault: every block ends with a status, untouched blocks decode exactly"""
+    bs, nb = 600, 4200
+    src = O.generate("text", 31 + n_states, bs * nb)
+    scratch, sizes, status = O.compress_blocks(src, bs, 0, n_states, threads=8)
+    assert not status.any()
+    good = np.concatenate([scratch[b, :int(sizes[b])] for b in range(nb)])
+    offh = np.zeros(nb + 1, dtype=np.int64)
+    offh[1:] = np.cumsum(sizes)
+    out, st = ctx.decompress_blocks(dev(ctx, good), good.size, dev(ctx, offh), src.size, bs, 0, n_states)
+    assert not st.cpu().numpy().any() and np.array_equal(out.cpu().numpy(), src)
+    rng = np.random.default_rng(77 + n_states)
+    for trial in range(40):
+        bad, boff = good.copy(), offh.copy()
+        kind = trial % 4
+        touched = set()
+        for _ in range(60):
+            b = int(rng.integers(0, nb))
+            touched.add(b)
+            if kind == 0:
+                bad[int(rng.integers(boff[b], boff[b + 1]))] ^= np.uint8(1 << int(rng.integers(0, 8)))
+            elif kind == 1:
+                k = int(rng.integers(1, 30))
+                bad[boff[b]:boff[b] + k] = rng.integers(0, 256, k, dtype=np.uint8)
+            elif kind == 2:
+                k = int(min(rng.integers(1, 40), boff[b + 1] - boff[b]))
+                bad[boff[b + 1] - k:boff[b + 1]] = 0 if trial & 4 else rng.integers(0, 256, k, dtype=np.uint8)
+            else:
+                a = int(rng.integers(boff[b], boff[b + 1]))
+                bad[a:min(a + int(rng.integers(1, 300)), boff[b + 1])] = np.uint8(rng.integers(0, 256))
+        out, st2 = ctx.decompress_blocks(dev(ctx, bad), bad.size, dev(ctx, boff), src.size, bs, 0, n_states)
+        st2, outh = st2.cpu().numpy(), out.cpu().numpy()
+        assert ((st2 <= 2) & (st2 >= -11)).all()
+        for b in range(0, nb, 7):
+            if b not in touched:
+                assert st2[b] == 0 and np.array_equal(outh[b * bs:(b + 1) * bs], src[b * bs:(b + 1) * bs]), (trial, b)
+    out, st = ctx.decompress_blocks(dev(ctx, good), good.size, dev(ctx, offh), src.size, bs, 0, n_states)
+    assert not st.cpu().numpy().any() and np.array_equal(out.cpu().numpy(), src)
