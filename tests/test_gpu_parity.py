@@ -1012,10 +1012,10 @@ def test_global_table_with_unknown_symbols_is_memory_safe(ctx):
 @pytest.mark.parametrize("n_states", [1, 2])
 @pytest.mark.parametrize("block_size,table_log", [(1000, 0), (1001, 9), (777, 0), (2048, 12)])
 def test_many_streams_in_the_reference_formats(ctx, n_states, block_size, table_log):
-    """>= 4096 blocks of one or two states take the thread-per-stream kernels: every block's bytes equal the oracle's
+    """>= 4096 blocks per state of one or two states take the thread-per-stream kernels: every block's bytes equal the oracle's
     fse_compress / fse_compress2 (odd and even lengths: the state of a symbol is its index's parity), escapes included,
     and the decoder returns the input"""
-    nb = 4500
+    nb = 4500 * n_states                                       # the decoder switches at 4 096 blocks per state
     n = nb * block_size - 333                                  # ragged last block
     src = O.generate("text" if block_size & 1 else "geo", 0xC0FFEE10 + n_states + block_size, n)
     src[5 * block_size:6 * block_size] = 0                     # all-zero block: 0x0E escape (histogram.rs:98)
@@ -1037,7 +1037,7 @@ def test_many_streams_in_the_reference_formats(ctx, n_states, block_size, table_
 def test_many_streams_decode_the_oracles_streams_and_survive_damage(ctx, n_states):
     """the thread-per-stream decoder on streams written by the oracle, then the seeded damage of
     test_corrupted_streams_never_fault: every block ends with a status, untouched blocks decode exactly"""
-    bs, nb = 600, 4200
+    bs, nb = 600, 4200 * n_states
     src = O.generate("text", 31 + n_states, bs * nb)
     scratch, sizes, status = O.compress_blocks(src, bs, 0, n_states, threads=8)
     assert not status.any()
