@@ -966,6 +966,13 @@ static int worst_status(const int32_t *st, size_t nb)
 
 static const size_t PIPE_CHUNK_BYTES = 32u << 20;
 
+// blocks a chunk must hold: one- and two-state streams are coded one thread per stream from 4 096 blocks per state on
+// (fse_tps.cuh), so their chunks are that large
+static size_t pipe_min_blocks(const fse_b200_params *p)
+{
+    return (p->n_states <= 2 && p->table_mode == FSE_B200_TABLE_PER_BLOCK && !p->flags) ? (size_t)TPS_MIN_BLOCKS * p->n_states : 1;
+}
+
 static int pipe_setup(fse_b200_ctx *ctx, size_t nchunks)
 {
     if (!ctx->s_in) CK(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
@@ -988,7 +995,7 @@ int fse_b200_compress_host(fse_b200_ctx *ctx, const uint8_t *h_src, size_t n, co
     const size_t bs = p->block_size, S = bs / stream_bytes(p);
     const size_t ns = num_streams(n, p);
     // chunks of whole blocks; small inputs are one chunk
-    const size_t cblocks = (n > 2 * PIPE_CHUNK_BYTES && bs <= PIPE_CHUNK_BYTES) ? std::max<size_t>(1, PIPE_CHUNK_BYTES / bs)
+    const size_t cblocks = (n > 2 * PIPE_CHUNK_BYTES && bs <= PIPE_CHUNK_BYTES) ? std::max<size_t>(pipe_min_blocks(p), PIPE_CHUNK_BYTES / bs)
                                                                                  : std::max<size_t>(1, fse_b200_num_blocks(n, p->block_size));
     const size_t cbytes = cblocks * bs, cstreams = cblocks * S;
     const size_t nchunks = std::max<size_t>(1, (n + cbytes - 1) / cbytes);
@@ -1071,7 +1078,7 @@ int fse_b200_decompress_host(fse_b200_ctx *ctx, const uint8_t *h_comp, size_t co
     if (h_offsets[ns] > comp_bytes) return fail(ctx, FSE_B200_ERR_ARG, "decompress_host: offsets exceed comp_bytes");
     const size_t bs = p->block_size, S = bs / stream_bytes(p);
     const size_t nb = fse_b200_num_blocks(n, p->block_size);
-    const size_t cblocks = (n > 2 * PIPE_CHUNK_BYTES && bs <= PIPE_CHUNK_BYTES) ? std::max<size_t>(1, PIPE_CHUNK_BYTES / bs) : nb;
+    const size_t cblocks = (n > 2 * PIPE_CHUNK_BYTES && bs <= PIPE_CHUNK_BYTES) ? std::max<size_t>(pipe_min_blocks(p), PIPE_CHUNK_BYTES / bs) : nb;
     const size_t cbytes = cblocks * bs, cstreams = cblocks * S;
     const size_t nchunks = (nb + cblocks - 1) / cblocks;
     rc = pipe_setup(ctx, nchunks);

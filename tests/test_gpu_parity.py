@@ -1073,3 +1073,17 @@ def test_many_streams_decode_the_oracles_streams_and_survive_damage(ctx, n_state
                 assert st2[b] == 0 and np.array_equal(outh[b * bs:(b + 1) * bs], src[b * bs:(b + 1) * bs]), (trial, b)
     out, st = ctx.decompress_blocks(dev(ctx, good), good.size, dev(ctx, offh), src.size, bs, 0, n_states)
     assert not st.cpu().numpy().any() and np.array_equal(out.cpu().numpy(), src)
+
+
+def test_host_buffer_api_in_the_reference_formats_many_blocks(ctx):
+    """the chunked host path with two states: its chunks hold >= 8 192 blocks so that they take the thread-per-stream
+    kernels; same bytes and offsets as the device call, and the round trip"""
+    n, bs = (96 << 20) + 777, 4096
+    src = ctx.generate("geo", 32, n)
+    hsrc = src.cpu().numpy()
+    d, off, st, total = ctx.compress_blocks(src, bs, 0, 2)
+    hd, hoff, hst, htotal = ctx.compress_host(hsrc, bs, 0, 2)
+    assert htotal == total and np.array_equal(hoff.astype(np.int64), off.cpu().numpy())
+    assert np.array_equal(hd[:htotal], d[:total].cpu().numpy()) and np.array_equal(hst, st.cpu().numpy())
+    out, st2 = ctx.decompress_host(hd, htotal, hoff, n, bs, 0, 2)
+    assert (st2 >= 0).all() and np.array_equal(out, hsrc)
