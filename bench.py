@@ -75,7 +75,7 @@ def kernel_names(tmode, seg, tlog=0, nblocks=0, num_sms=148, smem_per_sm=233472,
         enc, dec = "k_encode64_blocks", ("k_decode64c_blocks" if tl <= 12 else "k_decode64_blocks")
     elif n <= 2 and tmode == 0 and tl <= 12 and nblocks >= 4096:
         enc = "k_tps_encode"                                           # one thread per stream (fse_tps.cuh)
-        dec = "k_tps_decode" if nblocks >= 4096 * n else "k_decode_blocks"
+        dec = "k_tps_decode"
     else:
         enc, dec = "k_encode_blocks", "k_decode_blocks"
     return {"hist": "k_hist_blocks16", "encode": enc, "decode": dec, "scan": "k_scan_sizes", "gather": "k_gather"}

@@ -892,7 +892,7 @@ int fse_b200_decompress_blocks_async(fse_b200_ctx *ctx, const uint8_t *d_comp, s
         if (wpc < 1) return fail(ctx, FSE_B200_ERR_UNSUPPORTED, "table_log too large for shared memory");
         int grid = (int)std::min<size_t>((nblocks + wpc - 1) / wpc, (size_t)ctx->num_sms);
         if (!global && !a.exhaust && p->n_states <= 2 && tlmax <= 12 &&
-            nblocks >= (size_t)dev_opt("FSE_B200_TPS_MIN", (int)(TPS_MIN_BLOCKS * p->n_states))) {      // decode, 2 states: even at 4 096 blocks
+            nblocks >= (size_t)dev_opt("FSE_B200_TPS_MIN", (int)TPS_MIN_BLOCKS)) {
             // the reference's own one- / two-state streams, many of them: one thread per stream (fse_tps.cuh)
             CK(ctx->tps_dec_tab.reserve((nblocks << tlmax) * sizeof(uint32_t)));
             CK(ctx->tps_meta.reserve(nblocks * sizeof(uint4)));
@@ -970,7 +970,7 @@ static const size_t PIPE_CHUNK_BYTES = 32u << 20;
 // (fse_tps.cuh), so their chunks are that large
 static size_t pipe_min_blocks(const fse_b200_params *p)
 {
-    return (p->n_states <= 2 && p->table_mode == FSE_B200_TABLE_PER_BLOCK && !p->flags) ? (size_t)TPS_MIN_BLOCKS * p->n_states : 1;
+    return (p->n_states <= 2 && p->table_mode == FSE_B200_TABLE_PER_BLOCK && !p->flags) ? (size_t)TPS_MIN_BLOCKS * 2 : 1;
 }
 
 static int pipe_setup(fse_b200_ctx *ctx, size_t nchunks)

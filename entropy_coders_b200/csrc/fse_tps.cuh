@@ -10,8 +10,8 @@
 // also settles every block that needs no coder (escapes, errors).  Same bytes as k_encode_blocks / k_decode_blocks
 // (tests/test_gpu_parity.py::test_many_streams_*); chosen by the dispatcher from TPS_MIN_BLOCKS blocks on.
 // Measured (tools/tps_sweep.py, 128 KiB geometric blocks, two states; warp per block in brackets): 4 096 blocks encode
-// 40.8 (28.6) GB/s, decode 14.5 (15.8); 8 192: 58 (29) / 29 (16); 16 384: 72 (32) / 25 (18); c4's 65 536: 51 (26) / 44 (14),
-// one state 48 (13) / 43 (7).  A thread takes the same ~13 / 37 ms for its 128 KiB whatever the block count is (one
+// 41 (29) GB/s, decode 18 (16); 8 192: 58 (29) / 34 (16); 16 384: 71 (32) / 29 (18); c4's 65 536: 51 (26) / 44 (14),
+// one state 48 (13) / 43 (7).  A thread takes the same ~13 / 30 ms for its 128 KiB whatever the block count is (one
 // dependent look-up per symbol pair), until the tables outgrow the L2 (decode: 8 KiB per block) and the look-ups go to DRAM.
 #pragma once
 #include "fse_kernels.cuh"
@@ -106,6 +106,7 @@ __global__ void __launch_bounds__(32) k_tps_encode(EncArgs a, TpsTables g)
     const uint8_t *__restrict__ src = a.src + off;
     const uint16_t *__restrict__ tab = g.enc_tab + ((size_t)b << a.tlmax);
     const uint2 *__restrict__ tt = g.enc_tt + (size_t)b * 256;
+    asm volatile("" : "+l"(tab), "+l"(tt), "+l"(src));        // one base register each: a look-up address is one IMAD.WIDE
     uint32_t *pay = reinterpret_cast<uint32_t *>(a.scratch + (size_t)b * a.stride + HDR_RESERVE);
     const uint32_t cap = a.pay_cap_words;
     unsigned long long acc = 0;
@@ -244,6 +245,7 @@ __global__ void __launch_bounds__(32) k_tps_decode(DecArgs a, TpsTables g)
     const uint32_t bn = (uint32_t)min((size_t)a.block_size, a.n - off);
     uint8_t *out = a.dst + off;
     const uint32_t *__restrict__ tab = g.dec_tab + ((size_t)b << a.tlmax);
+    asm volatile("" : "+l"(tab));                             // one base register: a look-up address is one IMAD.WIDE
     const unsigned long long o0 = a.offsets[b], o1 = a.offsets[b + 1];
     const uint8_t *pay = a.comp + o0 + consumed;
     const uint32_t plen = (uint32_t)(o1 - o0) - consumed;
@@ -254,18 +256,27 @@ __global__ void __launch_bounds__(32) k_tps_decode(DecArgs a, TpsTables g)
     const uint32_t floor_bits = 8 * bias;
     if (cur - floor_bits < N * log2) { a.status[b] = ST_LENGTH; return; }               // lib.rs:197,224-225
     // window: lo = word q0, hi = word q0 + 1, nx = word q0 - 1; bits at and above the marker are never used
-    uint32_t q0 = cur >> 5;
+    // Every lane runs a different stream: whatever is conditional here is written as selects (a branch would diverge on
+    // nearly every read).  qbit = bit index of lo's first bit; pw points at lo's word.
+    const uint32_t *pw = origin + (cur >> 5);
+    uint32_t qbit = cur & ~31u;
     // the payload and the output are touched once: streaming loads / stores, so that the tables keep their place in the caches
-    uint32_t lo = __ldcs(origin + q0), hi = 0u, nx = q0 ? __ldcs(origin + q0 - 1) : 0u;
-    bool bad = false;
+    uint32_t lo = __ldcs(pw), hi = 0u, nx = qbit ? __ldcs(pw - 1) : 0u;
+    uint32_t bad = 0;
     auto read = [&](uint32_t n) -> uint32_t {                 // n <= 16
-        if (cur - floor_bits < n) { bad = true; return 0u; }
+        const bool ok = cur - floor_bits >= n;
+        bad |= ok ? 0u : 1u;
+        n = ok ? n : 0u;
         cur -= n;
-        if ((cur >> 5) < q0) {                                // one word down at most
-            hi = lo; lo = nx; q0--;
-            nx = q0 ? __ldcs(origin + q0 - 1) : 0u;
+        const bool need = cur < qbit;                         // one word down at most
+        hi = need ? lo : hi;
+        lo = need ? nx : lo;
+        if (need) {
+            qbit -= 32;
+            pw--;
+            nx = qbit ? __ldcs(pw - 1) : 0u;
         }
-        return __funnelshift_r(lo, hi, cur & 31) & ((1u << n) - 1u);
+        return __funnelshift_r(lo, hi, cur & 31) & ~(0xffffffffu << n);
     };
     const uint32_t body = bn - N;
     const bool aligned = (((uintptr_t)out) & 3) == 0;
