@@ -742,14 +742,20 @@ int fse_b200_compress_blocks_async(fse_b200_ctx *ctx, const uint8_t *d_src, size
         k_encode_sh_global<16, 16><<<g, w * 32, fixed + w * pw, ctx->stream>>>(a);
     } else if (!global && p->n_states <= 2 && !p->flags && tlmax <= 12 && nb >= (size_t)dev_opt("FSE_B200_TPS_MIN", (int)TPS_MIN_BLOCKS)) {
         // the reference's own one- / two-state streams, many of them: one thread per stream (fse_tps.cuh)
-        CK(ctx->tps_enc_tab.reserve((nb << tlmax) * sizeof(uint16_t)));
-        CK(ctx->tps_enc_tt.reserve(nb * 256 * sizeof(uint2)));
-        CK(ctx->tps_meta.reserve(nb * sizeof(uint4)));
-        TpsTables g{ctx->tps_enc_tab.as<uint16_t>(), ctx->tps_enc_tt.as<uint2>(), nullptr, ctx->tps_meta.as<uint4>()};
+        const size_t wave = std::min<size_t>(nb, (size_t)dev_opt("FSE_B200_TPS_WAVE", (int)(p->n_states == 2 ? TPS_ENC_WAVE : 4 * TPS_ENC_WAVE)));
+        CK(ctx->tps_enc_tab.reserve((wave << tlmax) * sizeof(uint16_t)));
+        CK(ctx->tps_enc_tt.reserve(wave * 256 * sizeof(uint2)));
+        CK(ctx->tps_meta.reserve(wave * sizeof(uint4)));
         Timed t(ctx, FSE_B200_K_ENCODE);
-        k_tps_prepare_enc<<<grid, wpc * 32, (size_t)wpc * per_warp, ctx->stream>>>(a, g);
-        k_tps_encode<<<(unsigned)((nb + 31) / 32), 32, 0, ctx->stream>>>(a, g);      // one warp per CTA: few blocks still reach every SM
-        ctx->launches++;
+        for (size_t first = 0; first < nb; first += wave) {
+            const uint32_t count = (uint32_t)std::min(wave, nb - first);
+            TpsTables g{ctx->tps_enc_tab.as<uint16_t>(), ctx->tps_enc_tt.as<uint2>(), nullptr, ctx->tps_meta.as<uint4>(), (uint32_t)first, count};
+            const int pg = (int)std::min<size_t>((count + wpc - 1) / wpc, (size_t)ctx->num_sms);
+            k_tps_prepare_enc<<<pg, wpc * 32, (size_t)wpc * per_warp, ctx->stream>>>(a, g);
+            k_tps_encode<<<(count + 31) / 32, 32, 0, ctx->stream>>>(a, g);      // one warp per CTA: few blocks still reach every SM
+            ctx->launches += 2;
+        }
+        ctx->launches--;                                     // the caller counts one
     } else {
         Timed t(ctx, FSE_B200_K_ENCODE);
         if (p->n_states == 128) k_encode128_blocks<<<grid, wpc * 32, (size_t)wpc * per_warp, ctx->stream>>>(a);
@@ -896,7 +902,7 @@ int fse_b200_decompress_blocks_async(fse_b200_ctx *ctx, const uint8_t *d_comp, s
             // the reference's own one- / two-state streams, many of them: one thread per stream (fse_tps.cuh)
             CK(ctx->tps_dec_tab.reserve((nblocks << tlmax) * sizeof(uint32_t)));
             CK(ctx->tps_meta.reserve(nblocks * sizeof(uint4)));
-            TpsTables g{nullptr, nullptr, ctx->tps_dec_tab.as<uint32_t>(), ctx->tps_meta.as<uint4>()};
+            TpsTables g{nullptr, nullptr, ctx->tps_dec_tab.as<uint32_t>(), ctx->tps_meta.as<uint4>(), 0u, (uint32_t)nblocks};
             Timed t(ctx, FSE_B200_K_DECODE);
             k_tps_prepare_dec<<<grid, wpc * 32, (size_t)wpc * lay.total, ctx->stream>>>(a, g);
             k_tps_decode<<<(unsigned)((nblocks + 31) / 32), 32, 0, ctx->stream>>>(a, g);

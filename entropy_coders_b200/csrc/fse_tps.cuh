@@ -19,6 +19,11 @@
 namespace fsed {
 
 constexpr uint32_t TPS_MIN_BLOCKS = 4096;
+// The two-state encoder takes the blocks in waves of this many: the tables of a wave (6 KiB per block) stay in the L2 while
+// its threads run (c4, 65 536 blocks at once: 158 ms; in waves of 16 384: 109 ms; 8 192: 141; 32 768: 113).  One state: four
+// times as many (a single chain per thread needs the threads more than the L2).  The decoder's tables are 8 KiB per block
+// and a thread takes longer: there one wave of everything is the faster way (measured), its look-ups go to DRAM.
+constexpr uint32_t TPS_ENC_WAVE = 16384;
 
 // per block: x = table_log, y = header bytes (encode) / header bytes consumed (decode), z = 1 when the coder has work
 struct TpsTables {
@@ -26,6 +31,7 @@ struct TpsTables {
     uint2 *enc_tt;          // [nblocks * 256]
     uint32_t *dec_tab;      // [nblocks << tlmax]
     uint4 *meta;            // [nblocks]
+    uint32_t first, count;  // this launch covers blocks [first, first + count); tables and meta are indexed by b - first
 };
 
 // ---------------------------------------------------------------------------------- encode
@@ -44,7 +50,8 @@ __global__ void __launch_bounds__(512) k_tps_prepare_enc(EncArgs a, TpsTables g)
     uint8_t *spread = my + lay.work + 3072;
     uint32_t *rows = reinterpret_cast<uint32_t *>(my + lay.rows);
     const uint32_t N = a.n_states;
-    for (uint32_t b = blockIdx.x * wpc + warp; b < a.nblocks; b += gridDim.x * wpc) {
+    for (uint32_t r = blockIdx.x * wpc + warp; r < g.count; r += gridDim.x * wpc) {
+        const uint32_t b = g.first + r;
         const size_t off = (size_t)b * a.block_size;
         const uint32_t bn = (uint32_t)min((size_t)a.block_size, a.n - off);
         const uint8_t *bsrc = a.src + off;
@@ -75,8 +82,8 @@ __global__ void __launch_bounds__(512) k_tps_prepare_enc(EncArgs a, TpsTables g)
             warp_spread(norm, log2, table_len, spread, cum, tab, lane);
             warp_build_encode(norm, log2, table_len, spread, cum, tab, tt, lane);
             __syncwarp();
-            uint16_t *gt = g.enc_tab + ((size_t)b << a.tlmax);
-            uint2 *gs = g.enc_tt + (size_t)b * 256;
+            uint16_t *gt = g.enc_tab + ((size_t)r << a.tlmax);
+            uint2 *gs = g.enc_tt + (size_t)r * 256;
             for (uint32_t i = lane; i < (1u << log2) / 2; i += 32)
                 reinterpret_cast<uint32_t *>(gt)[i] = reinterpret_cast<const uint32_t *>(tab)[i];
 #pragma unroll
@@ -84,7 +91,7 @@ __global__ void __launch_bounds__(512) k_tps_prepare_enc(EncArgs a, TpsTables g)
             ready = 1;
         }
         if (lane == 0) {
-            g.meta[b] = make_uint4(log2, hl, ready, 0u);
+            g.meta[r] = make_uint4(log2, hl, ready, 0u);
             a.hlen[b] = hl;
             a.plen[b] = 0;
             a.status[b] = st;
@@ -96,16 +103,17 @@ __global__ void __launch_bounds__(512) k_tps_prepare_enc(EncArgs a, TpsTables g)
 // (fse.rs:210-250), marker bit (lib.rs:141,181); BitStackWriter as a 64-bit accumulator flushed in 32-bit words
 __global__ void __launch_bounds__(32) k_tps_encode(EncArgs a, TpsTables g)
 {
-    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= a.nblocks) return;
-    const uint4 m = g.meta[b];
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= g.count) return;
+    const uint32_t b = g.first + r;
+    const uint4 m = g.meta[r];
     if (!m.z) return;
     const uint32_t log2 = m.x, N = a.n_states;
     const size_t off = (size_t)b * a.block_size;
     const uint32_t bn = (uint32_t)min((size_t)a.block_size, a.n - off);
     const uint8_t *__restrict__ src = a.src + off;
-    const uint16_t *__restrict__ tab = g.enc_tab + ((size_t)b << a.tlmax);
-    const uint2 *__restrict__ tt = g.enc_tt + (size_t)b * 256;
+    const uint16_t *__restrict__ tab = g.enc_tab + ((size_t)r << a.tlmax);
+    const uint2 *__restrict__ tt = g.enc_tt + (size_t)r * 256;
     asm volatile("" : "+l"(tab), "+l"(tt), "+l"(src));        // one base register each: a look-up address is one IMAD.WIDE
     uint32_t *pay = reinterpret_cast<uint32_t *>(a.scratch + (size_t)b * a.stride + HDR_RESERVE);
     const uint32_t cap = a.pay_cap_words;
