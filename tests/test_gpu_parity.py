@@ -1087,3 +1087,16 @@ def test_host_buffer_api_in_the_reference_formats_many_blocks(ctx):
     assert np.array_equal(hd[:htotal], d[:total].cpu().numpy()) and np.array_equal(hst, st.cpu().numpy())
     out, st2 = ctx.decompress_host(hd, htotal, hoff, n, bs, 0, 2)
     assert (st2 >= 0).all() and np.array_equal(out, hsrc)
+
+
+def test_many_streams_across_encoder_waves(ctx):
+    """two states, more blocks than one wave of the thread-per-stream encoder (16 384): bytes of every block vs the oracle"""
+    bs, nb = 500, 20000
+    src = O.generate("text", 0xC0FFEE20, bs * nb - 123)
+    blocks, st, (d, off, total) = gpu_blocks(ctx, src, bs, 0, 2)
+    scratch, sizes, status = O.compress_blocks(src, bs, 0, 2, threads=8)
+    assert len(blocks) == nb and not status.any() and not st.any()
+    for b in range(nb):
+        assert blocks[b] == scratch[b, :int(sizes[b])].tobytes(), "block %d differs" % b
+    out, dst_ = ctx.decompress_blocks(d, total, dev(ctx, off), src.size, bs, 0, 2)
+    assert not dst_.cpu().numpy().any() and np.array_equal(out.cpu().numpy(), src)
