@@ -101,7 +101,10 @@ def mem_available_gib():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region"""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region.  nvidia-smi needs ~0.1 s before its first
+    row, so it is started before the warm-up and every row is stamped on arrival; stop(t0, t1) keeps the rows that arrived
+    inside the timed region.  A region too short for three rows (strong-scaled shards) is followed by the same steps,
+    untimed, until there are three: those rows are taken under the same load and counted separately."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -120,20 +123,25 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
 
-    def stop(self):
+    def count(self, t0, t1):
+        return sum(1 for t, _ in list(self.rows) if t0 <= t <= t1)
+
+    def stop(self, t0, t1, t2=None):
+        """rows of [t0, t1] (the timed region), plus those of (t1, t2] (the same load continued) when given"""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, reasons, inside = [], [], set(), 0
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for t, r in self.rows:
+            if not (t0 <= t <= (t2 if t2 is not None else t1)):
+                continue
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
@@ -142,12 +150,16 @@ class ClockSampler:
                 mx.append(float(f[1]))
             except ValueError:
                 continue
+            inside += t <= t1
             for nme, v in zip(names, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(nme)
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        out = {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+               "reasons": sorted(reasons), "samples": len(sm), "samples_in_timed_region": inside}
+        if t2 is not None:
+            out["note"] = "timed region of %.0f ms: the rest of the rows were taken while the same steps went on, untimed" % ((t1 - t0) * 1e3)
+        return out
 
 
 # ---------------------------------------------------------------------------------------------- CPU legs (oracle/)
@@ -421,19 +433,24 @@ def measure(env, job, steps, warmup, sample_clocks=False):
     barrier(env)
     total = job.check()
     sampler = ClockSampler(env["local"]) if (sample_clocks and rank == 0) else None
+    if sampler:
+        sampler.start()                                      # before two more warm-up steps: nvidia-smi needs ~0.1 s to its first row
+    if sample_clocks:                                        # on every rank (a step may carry the size exchange)
+        for _ in range(2):
+            job.step()
+        job.finish()
     ctx.set_timing(True)
     l0 = ctx.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier(env)
-    if sampler:
-        sampler.start()
+    t0 = time.time()
     e0.record(stream)
     for _ in range(steps):
         job.step()
     job.finish()
     e1.record(stream)
     barrier(env)
-    clocks = sampler.stop() if sampler else None
+    t1 = time.time()
     ms = e0.elapsed_time(e1)
     launches = ctx.launches - l0
     tm = ctx.get_timing()
@@ -445,6 +462,19 @@ def measure(env, job, steps, warmup, sample_clocks=False):
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM)
     ms_step = float(tmax[0].item()) / steps
     total_all = float(t[1].item()) if world > 1 else float(total)
+    clocks = None
+    if sample_clocks:
+        # a timed region too short for three nvidia-smi rows (20 ms apart) is followed by the same steps, untimed, on every
+        # rank (the decision depends on the all-reduced time only), and the rows of that stretch are taken as well
+        t2 = None
+        if ms_step * steps < 250.0:
+            for _ in range(int(300.0 / ms_step) + 1):
+                job.step()
+            job.finish()
+            barrier(env)
+            t2 = time.time()
+        if sampler:
+            clocks = sampler.stop(t0, t1, t2)
     enc_ms = sum(tm[k][0] for k in ("hist", "encode", "scan", "gather")) / steps
     dec_ms = tm["decode"][0] / steps
     peak, peak_src = peaks()
