@@ -11,7 +11,8 @@
  * for the NCount header, the spread, both tables and the two-state stream format
  * of fse_compress2 / fse_decompress2 -- a real libzstd (1.5.5, the FSE the crate
  * ports) in both directions: it decodes the FSE streams libzstd writes and libzstd
- * decodes the streams it writes (tests/test_zstd_interop.py).
+ * decodes the streams it writes, and its tables of up to 512 entries decode the
+ * sequence streams of ordinary zstd frames (tests/test_zstd_interop.py).
  */
 #include "fse_oracle.h"
 
@@ -205,8 +206,9 @@ int fse_or_norm_new(const uint8_t *data, size_t n, fse_or_norm *out)
  * normalize differs from it in three places: the `to_distribute != 0 &&` guard (histogram.rs:144), low-probability symbols
  * are always -1 (zstd: -1 only with useLowProbCount), and the table_log range (zstd: 5..12 and >= FSE_minTableLog).
  * No libzstd build in this image exports FSE_normalizeCount, but its output is visible in the frames libzstd writes: the
- * function is pinned against libzstd 1.5.5 on the weight histograms of real Huffman tree descriptions
- * (tests/test_zstd_interop.py, useLowProbCount = 0) next to the hand-derived vectors of tests/test_zstd_normalize.py.  Returns 0, 3 (one symbol holds every count: zstd's "rle special case", norm untouched = 0)
+ * function is pinned against libzstd 1.5.5 on the weight histograms of real Huffman tree descriptions (useLowProbCount = 0)
+ * and on the sequence-code histograms of real frames (useLowProbCount = 1, table_log 7 - 9), tests/test_zstd_interop.py,
+ * next to the hand-derived vectors of tests/test_zstd_normalize.py.  Returns 0, 3 (one symbol holds every count: zstd's "rle special case", norm untouched = 0)
  * or a negative status. */
 static int zstd_normalize_m2(int32_t *norm, uint32_t table_log, const uint64_t *count, uint64_t total, uint32_t max_symbol,
                              int32_t low_prob_count)

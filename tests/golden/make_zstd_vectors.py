@@ -29,6 +29,9 @@ for seed, n, nsym, decay, base in CASES:
     assert rc == 0 and ZI.huf_decode_literals(info, list(weights)) == src      # the weights are what libzstd encoded
     out["streams"].append({"case": [seed, n, nsym, decay, base], "blob": blob.hex(), "weights": weights.hex(),
                            "table_log": nh.log2, "header_bytes": consumed, "norm": list(nh.table[:nh.table_len])})
+# two small frames with FSE-compressed sequence tables (tests/zstd_interop.py: decode_sequences)
+out["sequence_frames"] = [{"case": [seed, size, level], "frame": ZI.zstd_compress(ZI.wordy_bytes(seed, size), level).hex()}
+                          for seed, size, level in ((9, 9000, 3), (10, 14000, 5))]
 with open(os.path.join(HERE, "zstd_weight_streams.json"), "w") as f:
     json.dump(out, f, indent=1)
 print(len(out["streams"]), "streams from libzstd", out["libzstd"])

@@ -13,11 +13,11 @@ import zstd_interop as ZI
 needs_zstd = pytest.mark.skipif(ZI.zstd() is None, reason="libzstd not available")
 
 
-def _golden():
+def _golden(key="streams"):
     import json
     import os
     with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "zstd_weight_streams.json")) as f:
-        return json.load(f)["streams"]
+        return json.load(f)[key]
 
 
 def test_oracle_decodes_the_committed_libzstd_streams():
@@ -174,3 +174,109 @@ def test_gpu_normalize_zstd_equals_libzstd_on_real_histograms():
         used += 1
     assert used >= 4
     ctx.close()
+
+
+# ------------------------------------------------------------------------------------ sequences sections: tables up to 512 entries
+
+SEQ_CASES = [(5, 60000, 3), (6, 120000, 5), (7, 100000, 1), (8, 30000, 9), (9, 9000, 3)]
+
+
+def _oracle_table_of_header(blob):
+    rc, nh, used = O.ncount_read(blob)
+    assert rc == 0
+    t = O.dec_table(nh)
+    return ([(t.table[i].new_state, t.table[i].symbol, t.table[i].num_bits) for i in range(1 << nh.log2)], nh.log2, used,
+            list(nh.table[:nh.table_len]))
+
+
+def _oracle_table_of_norm(counts, log2):
+    nh = O.norm_from_table(list(counts) + [0] * (256 - len(counts)))
+    assert nh.log2 == log2
+    t = O.dec_table(nh)
+    return [(t.table[i].new_state, t.table[i].symbol, t.table[i].num_bits) for i in range(1 << log2)]
+
+
+def _walk(case, table_of_header, table_of_norm):
+    seed, size, level = case
+    fcs, blk = ZI.single_block(ZI.zstd_compress(ZI.wordy_bytes(seed, size), level))
+    regen, lsz = ZI.literals_section(blk)
+    return ZI.decode_sequences(blk[lsz:], regen, fcs, table_of_header, table_of_norm)
+
+
+@needs_zstd
+def test_oracle_tables_decode_the_sequence_streams_libzstd_writes():
+    """NormHistogram::read + DecodeTable::update (spread with -1 symbols, new_state / num_bits) at table_log 7 .. 9 on the
+    headers FSE_writeNCount wrote for FSE_buildCTable: the three interleaved state streams of thousands of sequences
+    end on the last bit and the lengths add up to the block.  normalize_zstd reproduces every header from the decoded
+    codes, with and without low-probability counts."""
+    fse_tables = low_prob = 0
+    for case in SEQ_CASES:
+        nseq, info, codes = _walk(case, _oracle_table_of_header, _oracle_table_of_norm)
+        assert nseq > 500
+        for name, mode, log2, counts in info:
+            if mode != "fse":
+                continue
+            cnt, total, low = ZI.sequence_code_histogram(codes[name], nseq)
+            rc, nz = O.normalize_zstd(O.hist_from_counts(cnt), log2, use_low_prob_count=low)
+            assert rc == 0 and list(nz.table[:len(counts)]) == counts, (case, name)
+            fse_tables += 1
+            low_prob += -1 in counts
+    assert fse_tables >= 12 and low_prob >= 5
+
+
+@needs_zstd
+@pytest.mark.gpu
+def test_gpu_tables_decode_the_sequence_streams_libzstd_writes():
+    """the same walk with headers parsed and decode tables built by the GPU stage entry points
+    (fse_b200_ncount_read, fse_b200_build_decode_tables), and fse_b200_normalize_zstd on the decoded codes"""
+    import torch
+    import entropy_coders_b200 as E
+    ctx = E.Context(0)
+
+    def table_of_norm_dev(norm, log2, tlen):
+        table, st = ctx.build_decode_tables(norm, log2, tlen, 9)
+        assert int(st.cpu()[0]) == 0
+        t = table.cpu().numpy().view(np.uint32)[0]
+        n = 1 << int(log2.cpu()[0])
+        return [(int(e) & 0xffff, (int(e) >> 16) & 0xff, int(e) >> 24) for e in t[:n]]
+
+    def table_of_header(blob):
+        rows = torch.zeros((1, 640), dtype=torch.uint8, device=ctx.device)
+        rows[0, :len(blob)] = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(ctx.device)
+        lens = torch.tensor([len(blob)], dtype=torch.int32, device=ctx.device)
+        norm, log2, tlen, cons, st = ctx.ncount_read(rows, lens)
+        assert int(st.cpu()[0]) == 0
+        k = int(tlen.cpu()[0])
+        return table_of_norm_dev(norm, log2, tlen), int(log2.cpu()[0]), int(cons.cpu()[0]), norm.cpu().numpy()[0, :k].tolist()
+
+    def table_of_norm(counts, log2):
+        norm = torch.zeros((1, 256), dtype=torch.int32, device=ctx.device)
+        norm[0, :len(counts)] = torch.tensor(counts, dtype=torch.int32)
+        return table_of_norm_dev(norm, torch.tensor([log2], dtype=torch.int32, device=ctx.device),
+                                 torch.tensor([len(counts)], dtype=torch.int32, device=ctx.device))
+    checked = 0
+    for case in SEQ_CASES[:3] + SEQ_CASES[4:]:
+        nseq, info, codes = _walk(case, table_of_header, table_of_norm)
+        for name, mode, log2, counts in info:
+            if mode != "fse":
+                continue
+            cnt, total, low = ZI.sequence_code_histogram(codes[name], nseq)
+            norm, l2, tlen, status = ctx.normalize_zstd(torch.tensor(cnt, dtype=torch.int64, device=ctx.device), log2, use_low_prob_count=low)
+            assert int(status.cpu()[0]) == 0 and norm.cpu().numpy()[0, :len(counts)].tolist() == counts, (case, name)
+            checked += 1
+    assert checked >= 9
+    ctx.close()
+
+
+def test_oracle_tables_decode_the_committed_libzstd_sequence_frames():
+    """the same walk on frames kept under tests/golden (no libzstd needed)"""
+    for v in _golden("sequence_frames"):
+        fcs, blk = ZI.single_block(bytes.fromhex(v["frame"]))
+        regen, lsz = ZI.literals_section(blk)
+        nseq, info, codes = ZI.decode_sequences(blk[lsz:], regen, fcs, _oracle_table_of_header, _oracle_table_of_norm)
+        assert nseq > 300 and any(mode == "fse" for _, mode, _, _ in info)
+        for name, mode, log2, counts in info:
+            if mode == "fse":
+                cnt, total, low = ZI.sequence_code_histogram(codes[name], nseq)
+                rc, nz = O.normalize_zstd(O.hist_from_counts(cnt), log2, use_low_prob_count=low)
+                assert rc == 0 and list(nz.table[:len(counts)]) == counts

@@ -213,3 +213,161 @@ def skewed_bytes(seed, n, nsym, decay, base=0):
     rng = np.random.default_rng(seed)
     p = decay ** np.arange(nsym)
     return (rng.choice(nsym, size=n, p=p / p.sum()).astype(np.uint8) + base).tobytes()
+
+
+# ---------------------------------------------------------------------------------- sequences sections (RFC 8878 3.1.1.3)
+# A compressed block's sequences are three FSE-coded symbol streams (literal-length, offset and match-length codes) over
+# tables of up to 512 entries whose NCount headers libzstd writes with FSE_normalizeCount(.., useLowProbCount = nbSeq >= 2048):
+# larger tables than the Huffman weights reach, and -1 counts written by libzstd itself.  The three states share one
+# backward bit stream with the sequences' extra bits, so decoding it needs exactly right tables: the check is that the
+# stream ends on its last bit and that literal lengths + match lengths + trailing literals make the block size.
+LL_BITS = [0] * 16 + [1, 1, 1, 1, 2, 2, 3, 3, 4, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16]
+LL_BASE = list(range(16)) + [16, 18, 20, 22, 24, 28, 32, 40, 48, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536]
+ML_BITS = [0] * 32 + [1, 1, 1, 1, 2, 2, 3, 3, 4, 4, 5, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16]
+ML_BASE = [i + 3 for i in range(32)] + [35, 37, 39, 41, 43, 47, 51, 59, 67, 83, 99, 131, 259, 515, 1027, 2051, 4099, 8195,
+                                        16387, 32771, 65539]
+PREDEFINED = {      # RFC 8878 3.1.1.3.2.2: (normalised counts, accuracy log)
+    "LL": ([4, 3, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 1, 1, 1, 2, 2, 2, 2, 2, 2, 2, 2, 2, 3, 2, 1, 1, 1, 1, 1, -1, -1, -1, -1], 6),
+    "OF": ([1, 1, 1, 1, 1, 1, 2, 2, 2, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, -1, -1, -1, -1, -1], 5),
+    "ML": ([1, 4, 3, 2, 2, 2, 2, 2, 2, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1,
+            1, 1, 1, 1, -1, -1, -1, -1, -1, -1, -1], 6),
+}
+
+
+def zstd_compress(src, level):
+    z = zstd()
+    cctx = z.ZSTD_createCCtx()
+    assert not z.ZSTD_isError(z.ZSTD_CCtx_setParameter(cctx, 100, level))
+    cap = z.ZSTD_compressBound(len(src))
+    dst = (C.c_uint8 * cap)()
+    n = z.ZSTD_compress2(cctx, dst, cap, src, len(src))
+    z.ZSTD_freeCCtx(cctx)
+    assert not z.ZSTD_isError(n)
+    return bytes(dst[:n])
+
+
+def wordy_bytes(seed, size):
+    """space-separated words drawn (Zipf) from a random dictionary: thousands of matches of many lengths and offsets"""
+    rng = np.random.default_rng(seed)
+    words = [bytes(rng.integers(97, 123, size=int(rng.integers(2, 12))).astype(np.uint8)) for _ in range(3000)]
+    idx = rng.zipf(1.3, size=size // 3 + 16) % len(words)
+    return b" ".join(words[i] for i in idx)[:size]
+
+
+def single_block(frame):
+    """-> (frame content size, the bytes of the first block), which must be the last one and compressed"""
+    assert frame[:4] == MAGIC
+    fhd = frame[4]
+    pos = 5
+    fcs_flag, single, dictid = fhd >> 6, (fhd >> 5) & 1, fhd & 3
+    if not single:
+        pos += 1
+    pos += (0, 1, 2, 4)[dictid]
+    nb = (1 if single else 0, 2, 4, 8)[fcs_flag]
+    fcs = int.from_bytes(frame[pos:pos + nb], "little") + (256 if nb == 2 else 0)
+    pos += nb
+    bh = int.from_bytes(frame[pos:pos + 3], "little")
+    pos += 3
+    assert bh & 1 and (bh >> 1) & 3 == 2
+    return fcs, frame[pos:pos + (bh >> 3)]
+
+
+def literals_section(blk):
+    """-> (regenerated size, bytes of the whole literals section)"""
+    ltype, sf = blk[0] & 3, (blk[0] >> 2) & 3
+    if ltype in (0, 1):
+        if sf in (0, 2):
+            regen, hl = blk[0] >> 3, 1
+        elif sf == 1:
+            regen, hl = int.from_bytes(blk[:2], "little") >> 4, 2
+        else:
+            regen, hl = int.from_bytes(blk[:3], "little") >> 4, 3
+        return regen, hl + (regen if ltype == 0 else 1)
+    if sf in (0, 1):
+        v = int.from_bytes(blk[:3], "little")
+        regen, comp, hl = (v >> 4) & 0x3ff, (v >> 14) & 0x3ff, 3
+    elif sf == 2:
+        v = int.from_bytes(blk[:4], "little")
+        regen, comp, hl = (v >> 4) & 0x3fff, (v >> 18) & 0x3fff, 4
+    else:
+        v = int.from_bytes(blk[:5], "little")
+        regen, comp, hl = (v >> 4) & 0x3ffff, (v >> 22) & 0x3ffff, 5
+    return regen, hl + comp
+
+
+def decode_sequences(seq, lit_count, block_size, table_of_header, table_of_norm):
+    """Walks a sequences section with decode tables supplied by the code under test:
+         table_of_header(bytes) -> (entries [(new_state, symbol, num_bits)], table_log, header bytes used, counts)
+         table_of_norm(counts, table_log) -> entries          (the predefined distributions)
+    -> (number of sequences, [(name, mode, table_log, counts)], {name: codes in sequence order}); asserts that the bit
+    stream is used up exactly and that the lengths add up to the block"""
+    b0 = seq[0]
+    pos = 1
+    assert b0 != 0
+    if b0 < 128:
+        nseq = b0
+    elif b0 < 255:
+        nseq, pos = ((b0 - 128) << 8) + seq[1], 2
+    else:
+        nseq, pos = seq[1] + (seq[2] << 8) + 0x7f00, 3
+    modes = seq[pos]
+    pos += 1
+    tabs, info = [], []
+    for name, mode in (("LL", modes >> 6), ("OF", (modes >> 4) & 3), ("ML", (modes >> 2) & 3)):
+        if mode == 0:
+            counts, log2 = PREDEFINED[name]
+            tabs.append((table_of_norm(counts, log2), log2))
+            info.append((name, "predefined", log2, counts))
+        elif mode == 1:
+            tabs.append(([(0, seq[pos], 0)], 0))
+            info.append((name, "rle", 0, None))
+            pos += 1
+        elif mode == 2:
+            entries, log2, used, counts = table_of_header(bytes(seq[pos:pos + 600]))
+            tabs.append((entries, log2))
+            info.append((name, "fse", log2, counts))
+            pos += used
+        else:
+            raise AssertionError("repeat mode in a first block")
+    data = seq[pos:]
+    assert data and data[-1] != 0
+    v = int.from_bytes(data, "little")
+    nbits = v.bit_length() - 1
+    state = {"n": nbits}
+
+    def read(n):
+        state["n"] -= n
+        assert state["n"] >= 0, "bit stream exhausted"
+        return (v >> state["n"]) & ((1 << n) - 1)
+    (llt, lll), (oft, ofl), (mlt, mll) = tabs
+    sl, so, sm = read(lll), read(ofl), read(mll)
+    tot_ll = tot_ml = 0
+    codes = {"LL": [], "OF": [], "ML": []}
+    for k in range(nseq):
+        llc, ofc, mlc = llt[sl][1], oft[so][1], mlt[sm][1]
+        codes["LL"].append(llc)
+        codes["OF"].append(ofc)
+        codes["ML"].append(mlc)
+        read(ofc)
+        tot_ml += ML_BASE[mlc] + read(ML_BITS[mlc])
+        tot_ll += LL_BASE[llc] + read(LL_BITS[llc])
+        if k + 1 < nseq:
+            sl = llt[sl][0] + read(llt[sl][2])
+            sm = mlt[sm][0] + read(mlt[sm][2])
+            so = oft[so][0] + read(oft[so][2])
+    assert state["n"] == 0, "%d bits left" % state["n"]
+    assert tot_ll <= lit_count and tot_ml + lit_count == block_size, (tot_ll, tot_ml, lit_count, block_size)
+    return nseq, info, codes
+
+
+def sequence_code_histogram(codes, nseq):
+    """what ZSTD_buildCTable hands to FSE_normalizeCount in set_compressed mode: the code counts with the last sequence's
+    code taken out when it is not its only occurrence -> (counts[256], total, useLowProbCount)"""
+    cnt = [0] * 256
+    for c in codes:
+        cnt[c] += 1
+    total = nseq
+    if cnt[codes[-1]] > 1:
+        cnt[codes[-1]] -= 1
+        total -= 1
+    return cnt, total, total >= 2048
