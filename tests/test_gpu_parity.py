@@ -1100,3 +1100,33 @@ def test_many_streams_across_encoder_waves(ctx):
         assert blocks[b] == scratch[b, :int(sizes[b])].tobytes(), "block %d differs" % b
     out, dst_ = ctx.decompress_blocks(d, total, dev(ctx, off), src.size, bs, 0, 2)
     assert not dst_.cpu().numpy().any() and np.array_equal(out.cpu().numpy(), src)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_many_streams_randomised_differential(ctx, seed):
+    """seeded shapes through the thread-per-stream kernels (block size, table_log, data kind, one or two states): every
+    block against the oracle, and the round trip"""
+    rng = np.random.default_rng(900 + seed)
+    n_states = int(rng.choice([1, 2]))
+    bs = int(rng.integers(130, 2600))
+    tl = int(rng.choice([0, 5, 9, 11, 12]))
+    kind = str(rng.choice(["geo", "text", "few", "uniform"]))
+    nb = 4096 + int(rng.integers(1, 300))
+    n = nb * bs - int(rng.integers(0, bs - 1))
+    src = O.generate(kind, 1000 + seed, n)
+    for _ in range(5):                                        # a few degenerate blocks
+        b = int(rng.integers(0, nb - 1))
+        src[b * bs:(b + 1) * bs] = int(rng.choice([0, 7, 255]))
+    blocks, st, (d, off, total) = gpu_blocks(ctx, src, bs, tl, n_states)
+    scratch, sizes, status = O.compress_blocks(src, bs, tl, n_states, threads=8)
+    for b in range(nb):
+        if status[b] == 0:
+            assert st[b] == 0 and blocks[b] == scratch[b, :int(sizes[b])].tobytes(), (seed, b, bs, tl, kind, n_states)
+        else:
+            assert st[b] != 0
+    ok = st >= 0
+    out, dst_ = ctx.decompress_blocks(d, total, dev(ctx, off), n, bs, tl, n_states)
+    outh, dst_ = out.cpu().numpy(), dst_.cpu().numpy()
+    for b in range(nb):
+        if ok[b]:
+            assert dst_[b] >= 0 and np.array_equal(outh[b * bs:(b + 1) * bs], src[b * bs:(b + 1) * bs]), (seed, b)
