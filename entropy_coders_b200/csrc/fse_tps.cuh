@@ -22,7 +22,9 @@ constexpr uint32_t TPS_MIN_BLOCKS = 4096;
 // The two-state encoder takes the blocks in waves of this many: the tables of a wave (6 KiB per block) stay in the L2 while
 // its threads run (c4, 65 536 blocks at once: 158 ms; in waves of 16 384: 109 ms; 8 192: 141; 32 768: 113).  One state: four
 // times as many (a single chain per thread needs the threads more than the L2).  The decoder's tables are 8 KiB per block
-// and a thread takes longer: there one wave of everything is the faster way (measured), its look-ups go to DRAM.
+// and a thread takes longer: there one wave of everything is the faster way (measured), its look-ups go to DRAM.  (Compact
+// 3-byte tables -- transform on the chain, symbol beside it -- in waves of 12 288 were tried for the decoder: 229 ms against
+// 189 ms on c4, two sectors per symbol instead of one.)
 constexpr uint32_t TPS_ENC_WAVE = 16384;
 
 // per block: x = table_log, y = header bytes (encode) / header bytes consumed (decode), z = 1 when the coder has work
