@@ -285,6 +285,8 @@ int fse_b200_create(int device, void *stream, fse_b200_ctx **out)
     cudaFuncSetAttribute(k_build_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
     cudaFuncSetAttribute(k_tps_prepare_enc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
     cudaFuncSetAttribute(k_tps_prepare_dec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
+    cudaFuncSetAttribute(k_tps_decode_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
+    cudaFuncSetAttribute(k_tps_encode_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
     cudaFuncSetAttribute(k_encode_sh_global<16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 64);
     cudaFuncSetAttribute(k_decode_sh_global, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 64);
     cudaFuncSetAttribute(k_encode_sh_blocks<16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 64);
@@ -752,7 +754,15 @@ int fse_b200_compress_blocks_async(fse_b200_ctx *ctx, const uint8_t *d_src, size
             TpsTables g{ctx->tps_enc_tab.as<uint16_t>(), ctx->tps_enc_tt.as<uint2>(), nullptr, ctx->tps_meta.as<uint4>(), (uint32_t)first, count};
             const int pg = (int)std::min<size_t>((count + wpc - 1) / wpc, (size_t)ctx->num_sms);
             k_tps_prepare_enc<<<pg, wpc * 32, (size_t)wpc * per_warp, ctx->stream>>>(a, g);
-            k_tps_encode<<<(count + 31) / 32, 32, 0, ctx->stream>>>(a, g);      // one warp per CTA: few blocks still reach every SM
+            const size_t set_bytes = ((size_t)2 << tlmax) + 2048;
+            const uint32_t lpw = (uint32_t)std::max(1, dev_opt("FSE_B200_TPS_ENC_LPW", 4));
+            // as many table sets as shared memory holds, but no more streams per CTA than leaves every SM one
+            const uint32_t per_cta = (uint32_t)std::min<size_t>(std::min<size_t>(32 * lpw, (ctx->smem_optin - 64) / set_bytes),
+                                                                std::max<size_t>(4, (count + ctx->num_sms - 1) / ctx->num_sms));
+            if (per_cta >= 4 && dev_opt("FSE_B200_TPS_ENC_SMEM", 1))
+                k_tps_encode_smem<<<(count + per_cta - 1) / per_cta, ((per_cta + lpw - 1) / lpw) * 32, per_cta * set_bytes, ctx->stream>>>(a, g, per_cta, lpw);
+            else
+                k_tps_encode<<<(count + 31) / 32, 32, 0, ctx->stream>>>(a, g);  // one warp per CTA: few blocks still reach every SM
             ctx->launches += 2;
         }
         ctx->launches--;                                     // the caller counts one
@@ -905,7 +915,14 @@ int fse_b200_decompress_blocks_async(fse_b200_ctx *ctx, const uint8_t *d_comp, s
             TpsTables g{nullptr, nullptr, ctx->tps_dec_tab.as<uint32_t>(), ctx->tps_meta.as<uint4>(), 0u, (uint32_t)nblocks};
             Timed t(ctx, FSE_B200_K_DECODE);
             k_tps_prepare_dec<<<grid, wpc * 32, (size_t)wpc * lay.total, ctx->stream>>>(a, g);
-            k_tps_decode<<<(unsigned)((nblocks + 31) / 32), 32, 0, ctx->stream>>>(a, g);
+            const uint32_t lpw = (uint32_t)std::max(1, dev_opt("FSE_B200_TPS_LPW", 4));
+            const uint32_t per_cta = (uint32_t)std::min<size_t>(std::min<size_t>(32 * lpw, (ctx->smem_optin - 64) / ((size_t)4 << tlmax)),
+                                                                std::max<size_t>(4, (nblocks + ctx->num_sms - 1) / ctx->num_sms));
+            if (per_cta >= 4 && dev_opt("FSE_B200_TPS_SMEM", 1))
+                k_tps_decode_smem<<<(unsigned)((nblocks + per_cta - 1) / per_cta), ((per_cta + lpw - 1) / lpw) * 32,
+                                    (size_t)per_cta * ((size_t)4 << tlmax), ctx->stream>>>(a, g, per_cta, lpw);
+            else
+                k_tps_decode<<<(unsigned)((nblocks + 31) / 32), 32, 0, ctx->stream>>>(a, g);
             ctx->launches++;
             CK(cudaGetLastError());
             return FSE_B200_OK;

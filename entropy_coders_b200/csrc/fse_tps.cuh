@@ -15,6 +15,7 @@
 // dependent look-up per symbol pair), until the tables outgrow the L2 (decode: 8 KiB per block) and the look-ups go to DRAM.
 #pragma once
 #include "fse_kernels.cuh"
+#include "fse_kernels64.cuh"
 
 namespace fsed {
 
@@ -103,20 +104,22 @@ __global__ void __launch_bounds__(512) k_tps_prepare_enc(EncArgs a, TpsTables g)
 
 // one thread per block: Encoder::new_first_symbol for the highest symbol of each state, encode_raw downwards, finish
 // (fse.rs:210-250), marker bit (lib.rs:141,181); BitStackWriter as a 64-bit accumulator flushed in 32-bit words
-__global__ void __launch_bounds__(32) k_tps_encode(EncArgs a, TpsTables g)
+__device__ __forceinline__ void tps_encode_stream(const EncArgs &a, uint32_t b, uint4 m, const uint16_t *__restrict__ tab,
+                                                  const uint2 *__restrict__ tt)
 {
-    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= g.count) return;
-    const uint32_t b = g.first + r;
-    const uint4 m = g.meta[r];
-    if (!m.z) return;
     const uint32_t log2 = m.x, N = a.n_states;
     const size_t off = (size_t)b * a.block_size;
     const uint32_t bn = (uint32_t)min((size_t)a.block_size, a.n - off);
     const uint8_t *__restrict__ src = a.src + off;
-    const uint16_t *__restrict__ tab = g.enc_tab + ((size_t)r << a.tlmax);
-    const uint2 *__restrict__ tt = g.enc_tt + (size_t)r * 256;
     asm volatile("" : "+l"(tab), "+l"(tt), "+l"(src));        // one base register each: a look-up address is one IMAD.WIDE
+    auto ld_tt = [&](uint32_t sym) -> uint2 { return __ldg(tt + sym); };
+    auto ld_tab = [&](int32_t idx) -> uint32_t { return (uint32_t)__ldg(tab + idx); };
+    auto first = [&](uint32_t sym) -> uint32_t {              // Encoder::new_first_symbol, fse.rs:210-218
+        const uint2 t = ld_tt(sym);
+        const uint32_t bo = (t.x + (1u << 15)) >> 16;
+        const uint32_t value = (bo << 16) - t.x;
+        return ld_tab((int32_t)(value >> bo) + (int32_t)t.y);
+    };
     uint32_t *pay = reinterpret_cast<uint32_t *>(a.scratch + (size_t)b * a.stride + HDR_RESERVE);
     const uint32_t cap = a.pay_cap_words;
     unsigned long long acc = 0;
@@ -132,31 +135,31 @@ __global__ void __launch_bounds__(32) k_tps_encode(EncArgs a, TpsTables g)
         }
     };
     auto step = [&](uint32_t &s, uint32_t sym) {              // fse.rs:227-239
-        const uint2 t = __ldg(tt + sym);
+        const uint2 t = ld_tt(sym);
         const uint32_t nb = (t.x + s) >> 16;
         put(s & ((1u << nb) - 1u), nb);
-        s = __ldg(tab + ((int32_t)(s >> nb) + (int32_t)t.y));
+        s = ld_tab((int32_t)(s >> nb) + (int32_t)t.y);
     };
     int32_t i = (int32_t)bn - 1;
     if (N == 2) {
         // state i & 1 codes symbol i; the two highest symbols initialise the states
-        uint32_t sa = enc_first(tab, tt, __ldg(src + i));     // parity of bn - 1
-        uint32_t sb = enc_first(tab, tt, __ldg(src + i - 1));
+        uint32_t sa = first(__ldg(src + i));                  // parity of bn - 1
+        uint32_t sb = first(__ldg(src + i - 1));
         i -= 2;
         // Two independent chains.  Only the next-state look-up depends on the state: the symbols are fetched two pairs
         // ahead and their transforms one pair ahead, so that a pair costs one memory latency, not three.
         uint32_t ya = 0, yb = 0, ya2 = 0, yb2 = 0;
         uint2 ta = make_uint2(0u, 0u), tb = ta;
-        if (i >= 1) { ya = __ldg(src + i); yb = __ldg(src + i - 1); ta = __ldg(tt + ya); tb = __ldg(tt + yb); }
+        if (i >= 1) { ya = __ldg(src + i); yb = __ldg(src + i - 1); ta = ld_tt(ya); tb = ld_tt(yb); }
         if (i >= 3) { ya2 = __ldg(src + i - 2); yb2 = __ldg(src + i - 3); }
         for (; i >= 1; i -= 2) {
             const uint2 ca = ta, cb = tb;
-            if (i >= 3) { ta = __ldg(tt + ya2); tb = __ldg(tt + yb2); }
+            if (i >= 3) { ta = ld_tt(ya2); tb = ld_tt(yb2); }
             if (i >= 5) { ya2 = __ldg(src + i - 4); yb2 = __ldg(src + i - 5); }
             const uint32_t na = (ca.x + sa) >> 16, nb = (cb.x + sb) >> 16;
             const uint32_t va = sa & ((1u << na) - 1u), vb = sb & ((1u << nb) - 1u);
-            sa = __ldg(tab + ((int32_t)(sa >> na) + (int32_t)ca.y));
-            sb = __ldg(tab + ((int32_t)(sb >> nb) + (int32_t)cb.y));
+            sa = ld_tab((int32_t)(sa >> na) + (int32_t)ca.y);
+            sb = ld_tab((int32_t)(sb >> nb) + (int32_t)cb.y);
             put(va, na);
             put(vb, nb);
         }
@@ -167,19 +170,19 @@ __global__ void __launch_bounds__(32) k_tps_encode(EncArgs a, TpsTables g)
         put(s1 & mask, log2);
         put(s0 & mask, log2);
     } else {
-        uint32_t s = enc_first(tab, tt, __ldg(src + i));
+        uint32_t s = first(__ldg(src + i));
         i--;
         uint32_t y2 = 0;                                      // the same prefetch for the single chain
         uint2 t = make_uint2(0u, 0u);
-        if (i >= 0) t = __ldg(tt + __ldg(src + i));
+        if (i >= 0) t = ld_tt(__ldg(src + i));
         if (i >= 1) y2 = __ldg(src + i - 1);
         for (; i >= 0; i--) {
             const uint2 c = t;
-            if (i >= 1) t = __ldg(tt + y2);
+            if (i >= 1) t = ld_tt(y2);
             if (i >= 2) y2 = __ldg(src + i - 2);
             const uint32_t nb = (c.x + s) >> 16;
             put(s & ((1u << nb) - 1u), nb);
-            s = __ldg(tab + ((int32_t)(s >> nb) + (int32_t)c.y));
+            s = ld_tab((int32_t)(s >> nb) + (int32_t)c.y);
         }
         put(s & ((1u << log2) - 1u), log2);
     }
@@ -188,6 +191,162 @@ __global__ void __launch_bounds__(32) k_tps_encode(EncArgs a, TpsTables g)
     if (cnt) { if (wp < cap) pay[wp] = (uint32_t)acc; wp++; }
     if (wp > cap) { a.hlen[b] = 0; a.plen[b] = 0; a.status[b] = ST_CAPACITY; return; }
     a.plen[b] = (bits + 7) >> 3;
+}
+
+__global__ void __launch_bounds__(32) k_tps_encode(EncArgs a, TpsTables g)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= g.count) return;
+    const uint4 m = g.meta[r];
+    if (!m.z) return;
+    tps_encode_stream(a, g.first + r, m, g.enc_tab + ((size_t)r << a.tlmax), g.enc_tt + (size_t)r * 256);
+}
+
+// ---- the shared-memory form of the same encoder (k_tps_encode_smem).  The state chain is s -> nb -> s >> nb -> look-up
+// (fse.rs:227-239); everything else is arranged to stay off it and to cost few instructions:
+//  * the symbol transforms of the shared copy hold the ADDRESS of their first next-state cell (tab_s + 2 * find_state), so
+//    the look-up address is one LEA;
+//  * BitStackWriter (writer.rs:140-149) as a 64-bit window {hi, lo} filled from the TOP: emitting the low nb bits of the
+//    state is two funnel shifts (lo = {hi, lo} >> nb, hi = {s, hi} >> nb), nothing is masked or OR-ed; the valid bits are
+//    the top `cnt` bits, a full word is cut out with one more funnel shift.  Two symbols emit <= 24 bits (table_log <= 12),
+//    so the window is flushed once per pair;
+//  * the source is read as aligned 32-bit words (four symbols), one word ahead, from sectors prefetched into the L1.
+// ~13 instructions per symbol instead of 46.
+__device__ __forceinline__ void tps_encode_stream_smem(const EncArgs &a, uint32_t b, uint4 m, uint32_t tt_s)
+{
+    const uint32_t log2 = m.x, N = a.n_states;
+    const size_t off = (size_t)b * a.block_size;
+    const uint32_t bn = (uint32_t)min((size_t)a.block_size, a.n - off);
+    const uint8_t *__restrict__ src = a.src + off;
+    uint32_t *pay = reinterpret_cast<uint32_t *>(a.scratch + (size_t)b * a.stride + HDR_RESERVE);
+    const uint32_t cap = a.pay_cap_words;
+    uint32_t lo = 0, hi = 0, cnt = 0, wp = 0;
+    auto push = [&](uint32_t v, uint32_t n) {                 // the low n & 31 bits of v on top of the window
+        lo = __funnelshift_r(lo, hi, n);
+        hi = __funnelshift_r(hi, v, n);
+    };
+    auto flush = [&]() {                                      // cnt < 64
+        if (cnt >= 32) {
+            const uint32_t w = __funnelshift_rc(lo, hi, 64 - cnt);
+            if (wp < cap) __stcs(pay + wp, w);
+            wp++;
+            cnt -= 32;
+        }
+    };
+    auto ld_t = [&](uint32_t sym) -> uint2 { return lds_v2(tt_s + sym * 8); };
+    auto first = [&](uint32_t sym) -> uint32_t {              // Encoder::new_first_symbol, fse.rs:210-218
+        const uint2 t = ld_t(sym);
+        const uint32_t bo = (t.x + (1u << 15)) >> 16;
+        const uint32_t value = (bo << 16) - t.x;
+        return lds_u16(t.y + ((value >> bo) << 1));
+    };
+    auto enc = [&](uint32_t &st, uint2 t) -> uint32_t {       // fse.rs:227-239; returns the bits emitted
+        const uint32_t nb = (t.x + st) >> 16;
+        push(st, nb);
+        st = lds_u16(t.y + ((st >> nb) << 1));
+        return nb;
+    };
+    auto word_at = [&](int32_t i) -> uint32_t {               // symbols i - 3 .. i (src + i - 3 is aligned)
+        if ((i & 31) < 4 && i >= 99) asm volatile("prefetch.global.L1 [%0];" ::"l"(src + i - 99));
+        return __ldg(reinterpret_cast<const uint32_t *>(src + i - 3));
+    };
+    int32_t i = (int32_t)bn - 1;
+    if (N == 2) {
+        // sA is the state of the parity of i (the symbol coded next), sB the other one
+        uint32_t sA = first(__ldg(src + i)), sB = first(__ldg(src + i - 1));
+        i -= 2;
+        while (i >= 0 && (((uintptr_t)(src + i + 1)) & 3)) {   // down to a word boundary
+            cnt += enc(sA, ld_t(__ldg(src + i)));
+            flush();
+            const uint32_t x = sA; sA = sB; sB = x;
+            i--;
+        }
+        uint32_t w = i >= 3 ? word_at(i) : 0u;
+        for (; i >= 3; i -= 4) {
+            const uint32_t c = w;
+            if (i >= 7) w = word_at(i - 4);
+            const uint2 t3 = ld_t(c >> 24), t2 = ld_t((c >> 16) & 0xffu), t1 = ld_t((c >> 8) & 0xffu), t0 = ld_t(c & 0xffu);
+            const uint32_t n3 = enc(sA, t3);
+            const uint32_t n2 = enc(sB, t2);
+            cnt += n3 + n2;
+            flush();
+            const uint32_t n1 = enc(sA, t1);
+            const uint32_t n0 = enc(sB, t0);
+            cnt += n1 + n0;
+            flush();
+        }
+        for (; i >= 0; i--) {
+            cnt += enc(sA, ld_t(__ldg(src + i)));
+            flush();
+            const uint32_t x = sA; sA = sB; sB = x;
+        }
+        // i = -1: sA is the state of the odd indices.  Final states 1, 0 (fse.rs:241-250), then the marker (lib.rs:181)
+        push(sA, log2); cnt += log2; flush();
+        push(sB, log2); cnt += log2; flush();
+    } else {
+        uint32_t st = first(__ldg(src + i));
+        i--;
+        while (i >= 0 && (((uintptr_t)(src + i + 1)) & 3)) {
+            cnt += enc(st, ld_t(__ldg(src + i)));
+            flush();
+            i--;
+        }
+        uint32_t w = i >= 3 ? word_at(i) : 0u;
+        for (; i >= 3; i -= 4) {
+            const uint32_t c = w;
+            if (i >= 7) w = word_at(i - 4);
+            const uint2 t3 = ld_t(c >> 24), t2 = ld_t((c >> 16) & 0xffu), t1 = ld_t((c >> 8) & 0xffu), t0 = ld_t(c & 0xffu);
+            const uint32_t n3 = enc(st, t3);
+            const uint32_t n2 = enc(st, t2);
+            cnt += n3 + n2;
+            flush();
+            const uint32_t n1 = enc(st, t1);
+            const uint32_t n0 = enc(st, t0);
+            cnt += n1 + n0;
+            flush();
+        }
+        for (; i >= 0; i--) {
+            cnt += enc(st, ld_t(__ldg(src + i)));
+            flush();
+        }
+        push(st, log2); cnt += log2; flush();
+    }
+    push(1u, 1u); cnt += 1; flush();
+    const uint32_t bits = wp * 32 + cnt;
+    if (cnt) { if (wp < cap) pay[wp] = hi >> (32 - cnt); wp++; }
+    if (wp > cap) { a.hlen[b] = 0; a.plen[b] = 0; a.status[b] = ST_CAPACITY; return; }
+    a.plen[b] = (bits + 7) >> 3;
+}
+
+// The same streams with their tables in SHARED memory: a CTA takes `per_cta` blocks (as many as table sets fit: 37 at
+// table_log 11: 4 KiB of next states + 2 KiB of symbol transforms each), copies their tables in, and lanes
+// 0 .. lanes_per_warp - 1 of its warps run one stream each.
+__global__ void __launch_bounds__(1024) k_tps_encode_smem(EncArgs a, TpsTables g, uint32_t per_cta, uint32_t lanes_per_warp)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const uint32_t first = blockIdx.x * per_cta, tab_bytes = 2u << a.tlmax, set_bytes = tab_bytes + 2048u;
+    const uint32_t sm0 = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    for (uint32_t j = 0; j < per_cta; j++) {
+        const uint32_t r = first + j;
+        if (r >= g.count) break;
+        const uint4 *st = reinterpret_cast<const uint4 *>(g.enc_tab + ((size_t)r << a.tlmax));
+        const uint4 *ss = reinterpret_cast<const uint4 *>(g.enc_tt + (size_t)r * 256);
+        uint4 *dt = reinterpret_cast<uint4 *>(smem_raw + (size_t)j * set_bytes);
+        const uint32_t tab_s = sm0 + j * set_bytes;
+        for (uint32_t i = threadIdx.x; i < tab_bytes / 16; i += blockDim.x) dt[i] = st[i];
+        for (uint32_t i = threadIdx.x; i < 128; i += blockDim.x) {       // two transforms: find_state -> address of its cell
+            const uint4 v = ss[i];
+            dt[tab_bytes / 16 + i] = make_uint4(v.x, tab_s + 2u * v.y, v.z, tab_s + 2u * v.w);
+        }
+    }
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane >= lanes_per_warp) return;
+    const uint32_t j = warp * lanes_per_warp + lane, r = first + j;
+    if (j >= per_cta || r >= g.count) return;
+    const uint4 m = g.meta[r];
+    if (!m.z) return;
+    tps_encode_stream_smem(a, g.first + r, m, sm0 + j * set_bytes + tab_bytes);
 }
 
 // ---------------------------------------------------------------------------------- decode
@@ -244,18 +403,14 @@ __global__ void __launch_bounds__(512) k_tps_prepare_dec(DecArgs a, TpsTables g)
 // one thread per block: BitStackReader::new (marker), Decoder::new for states 0 .. N-1, decode_symbol for the body,
 // finish for the last N symbols (fse.rs:341-386, lib.rs:187-248), length driven.  The stack is read through a 64-bit
 // window of two aligned words, the next lower word is loaded one refill ahead.
-__global__ void __launch_bounds__(32) k_tps_decode(DecArgs a, TpsTables g)
+__device__ __forceinline__ void tps_decode_stream(const DecArgs &a, uint32_t b, uint4 m, const uint32_t *__restrict__ tab)
 {
-    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= a.nblocks) return;
-    const uint4 m = g.meta[b];
-    if (!m.z) return;
     const uint32_t log2 = m.x, consumed = m.y, N = a.n_states;
     const size_t off = (size_t)b * a.block_size;
     const uint32_t bn = (uint32_t)min((size_t)a.block_size, a.n - off);
     uint8_t *out = a.dst + off;
-    const uint32_t *__restrict__ tab = g.dec_tab + ((size_t)b << a.tlmax);
     asm volatile("" : "+l"(tab));                             // one base register: a look-up address is one IMAD.WIDE
+    auto look = [&](uint32_t st_) -> uint32_t { return __ldg(tab + st_); };
     const unsigned long long o0 = a.offsets[b], o1 = a.offsets[b + 1];
     const uint8_t *pay = a.comp + o0 + consumed;
     const uint32_t plen = (uint32_t)(o1 - o0) - consumed;
@@ -293,17 +448,17 @@ __global__ void __launch_bounds__(32) k_tps_decode(DecArgs a, TpsTables g)
     uint32_t i = 0;
     if (N == 2) {
         uint32_t s0 = read(log2), s1 = read(log2);            // Decoder::new, fse.rs:349-352: state 0 first
-        uint32_t e0 = __ldg(tab + s0), e1 = __ldg(tab + s1);
+        uint32_t e0 = look(s0), e1 = look(s1);
         uint32_t word = 0;
         for (; i + 2 <= body && !bad; i += 2) {               // fse.rs:363-373 on the two chains
             const uint32_t b0 = read(e0 >> 24);
             const uint32_t y0 = (e0 >> 16) & 0xffu;
             s0 = (e0 & 0xffffu) + b0;
-            e0 = __ldg(tab + s0);
+            e0 = look(s0);
             const uint32_t b1 = read(e1 >> 24);
             const uint32_t y1 = (e1 >> 16) & 0xffu;
             s1 = (e1 & 0xffffu) + b1;
-            e1 = __ldg(tab + s1);
+            e1 = look(s1);
             if (aligned) {
                 word |= (y0 | (y1 << 8)) << ((i & 2) * 8);
                 if (i & 2) { __stcs(reinterpret_cast<uint32_t *>(out + (i & ~3u)), word); word = 0; }
@@ -317,7 +472,7 @@ __global__ void __launch_bounds__(32) k_tps_decode(DecArgs a, TpsTables g)
             const uint32_t b0 = read(e0 >> 24);
             out[i] = (uint8_t)(e0 >> 16);
             s0 = (e0 & 0xffffu) + b0;
-            e0 = __ldg(tab + s0);
+            e0 = look(s0);
             i++;
         }
         if (!bad) {                                           // Decoder::finish: symbols body, body + 1 from states (i & 1), ...
@@ -326,16 +481,177 @@ __global__ void __launch_bounds__(32) k_tps_decode(DecArgs a, TpsTables g)
         }
     } else {
         uint32_t s = read(log2);
-        uint32_t e = __ldg(tab + s);
+        uint32_t e = look(s);
         for (; i < body && !bad; i++) {
             const uint32_t bits = read(e >> 24);
             out[i] = (uint8_t)(e >> 16);
             s = (e & 0xffffu) + bits;
-            e = __ldg(tab + s);
+            e = look(s);
         }
         if (!bad) out[i] = (uint8_t)(e >> 16);
     }
     a.status[b] = (bad || cur != floor_bits) ? ST_LENGTH : ST_OK;
+}
+
+// ---- the shared-memory form of the same decoder.  A stream is a serial chain (entry -> bits -> next entry), so what
+// counts is the length of that chain and the instructions around it:
+//  * entry of the shared copy: num_bits | symbol << 8 | (4 * new_state base) << 16 (tps_smem_entry): the shift amounts of a
+//    read come straight from the entry (funnel shifts use the low five bits of their shift operand), the look-up address
+//    is one LEA;
+//  * the stack is read through a LEFT-aligned 64-bit window {wh, wl} (the next bits of the stack are wh's top bits): a read
+//    of nb bits is wh >> (32 - nb) and the window moves up by nb, three funnel shifts, nothing masked;
+//  * up to table_log 12 two reads never need more than 24 bits: the window is refilled (one 32-bit word, loaded one
+//    refill ahead from sectors prefetched into the L1) once per pair when 32 bits or fewer are left;
+//  * no test of the stack's depth on the chain: the bits used are counted and compared with the stream's once, at the end
+//    (a stream that runs dry reads zeros -- every look-up stays inside its table -- and is reported as ST_LENGTH as before).
+// Chain per symbol: LDS, SHF, LEA (and SHF + IADD beside the SHF); ~15 instructions per symbol instead of 48.
+__device__ __forceinline__ uint32_t tps_smem_entry(uint32_t e) { return (e >> 24) | ((e >> 8) & 0xff00u) | ((e & 0xffffu) << 18); }
+
+__device__ __forceinline__ void tps_decode_stream_smem(const DecArgs &a, uint32_t b, uint4 m, uint32_t tab_s)
+{
+    const uint32_t log2 = m.x, consumed = m.y, N = a.n_states;
+    const size_t off = (size_t)b * a.block_size;
+    const uint32_t bn = (uint32_t)min((size_t)a.block_size, a.n - off);
+    uint8_t *out = a.dst + off;
+    const unsigned long long o0 = a.offsets[b], o1 = a.offsets[b + 1];
+    const uint8_t *pay = a.comp + o0 + consumed;
+    const uint32_t plen = (uint32_t)(o1 - o0) - consumed;
+    if (plen == 0 || pay[plen - 1] == 0) { a.status[b] = ST_NO_MARKER; return; }       // stack_reader.rs:17-92
+    const uint32_t bias = (uint32_t)((uintptr_t)pay & 3);
+    const uint32_t *__restrict__ origin = reinterpret_cast<const uint32_t *>(pay - bias);
+    const uint32_t cur = (plen - 1) * 8 + ilog2u(pay[plen - 1]) + 8 * bias;             // marker position
+    const uint32_t floor_bits = 8 * bias;
+    if (cur - floor_bits < N * log2) { a.status[b] = ST_LENGTH; return; }               // lib.rs:197,224-225
+    uint32_t left = (cur + 31) >> 5;                          // words not loaded yet: origin[0 .. left)
+    auto next_word = [&]() -> uint32_t {
+        if (!left) return 0u;
+        left--;
+        if (left >= 24) asm volatile("prefetch.global.L1 [%0];" ::"l"(origin + left - 24));
+        return __ldg(origin + left);
+    };
+    const uint32_t top = next_word();
+    const uint32_t r = cur & 31;
+    uint32_t wh = r ? top << (32 - r) : top, wl = 0u;
+    uint32_t cnt = r ? r : 32u;                               // valid bits in the window (zeros below the stack count too)
+    uint32_t nx = next_word();
+    uint32_t used = 0;
+    auto refill = [&]() {                                     // cnt <= 32: wl is empty
+        if (cnt <= 32) {
+            wh |= __funnelshift_rc(nx, 0u, cnt);
+            wl = __funnelshift_rc(0u, nx, cnt);
+            cnt += 32;
+            nx = next_word();
+        }
+    };
+    refill();
+    auto take = [&](uint32_t e) -> uint32_t {                 // e & 31 bits off the top of the window
+        const uint32_t bits = __funnelshift_l(wh, 0u, e);
+        wh = __funnelshift_l(wl, wh, e);
+        wl = __funnelshift_l(0u, wl, e);
+        return bits;
+    };
+    auto step = [&](uint32_t &e) {                            // fse.rs:363-373: new_state + bits, then its entry
+        const uint32_t bits = take(e);
+        e = lds_u32((e >> 16) + tab_s + bits * 4);
+    };
+    const uint32_t body = bn - N;
+    const bool aligned = (((uintptr_t)out) & 3) == 0;
+    uint32_t i = 0;
+    if (N == 2) {
+        const uint32_t s0 = take(log2), s1 = take(log2);      // Decoder::new, fse.rs:349-352: state 0 first
+        cnt -= 2 * log2; used += 2 * log2;
+        refill();
+        uint32_t e0 = lds_u32(tab_s + s0 * 4), e1 = lds_u32(tab_s + s1 * 4);
+        for (; i + 4 <= body; i += 4) {
+            const uint32_t a0 = e0, a1 = e1;
+            step(e0); step(e1);
+            { const uint32_t k = (a0 & 31u) + (a1 & 31u); cnt -= k; used += k; }
+            refill();
+            const uint32_t a2 = e0, a3 = e1;
+            step(e0); step(e1);
+            { const uint32_t k = (a2 & 31u) + (a3 & 31u); cnt -= k; used += k; }
+            refill();
+            const uint32_t word = __byte_perm(__byte_perm(a0, a1, 0x0051), __byte_perm(a2, a3, 0x0051), 0x5410);
+            if (aligned) __stcs(reinterpret_cast<uint32_t *>(out + i), word);
+            else { out[i] = (uint8_t)word; out[i + 1] = (uint8_t)(word >> 8); out[i + 2] = (uint8_t)(word >> 16); out[i + 3] = (uint8_t)(word >> 24); }
+        }
+        for (; i < body; i++) {                               // up to three more body symbols, states in turn
+            const uint32_t e = (i & 1) ? e1 : e0;
+            out[i] = (uint8_t)(e >> 8);
+            uint32_t en = e;
+            step(en);
+            cnt -= e & 31u; used += e & 31u;
+            refill();
+            if (i & 1) e1 = en; else e0 = en;
+        }
+        out[i] = (uint8_t)(((i & 1) ? e1 : e0) >> 8);         // Decoder::finish: symbols body, body + 1 from states (i & 1), ...
+        out[i + 1] = (uint8_t)(((i & 1) ? e0 : e1) >> 8);
+    } else {
+        const uint32_t s = take(log2);
+        cnt -= log2; used += log2;
+        refill();
+        uint32_t e = lds_u32(tab_s + s * 4);
+        for (; i + 4 <= body; i += 4) {
+            const uint32_t a0 = e; step(e);
+            const uint32_t a1 = e; step(e);
+            { const uint32_t k = (a0 & 31u) + (a1 & 31u); cnt -= k; used += k; }
+            refill();
+            const uint32_t a2 = e; step(e);
+            const uint32_t a3 = e; step(e);
+            { const uint32_t k = (a2 & 31u) + (a3 & 31u); cnt -= k; used += k; }
+            refill();
+            const uint32_t word = __byte_perm(__byte_perm(a0, a1, 0x0051), __byte_perm(a2, a3, 0x0051), 0x5410);
+            if (aligned) __stcs(reinterpret_cast<uint32_t *>(out + i), word);
+            else { out[i] = (uint8_t)word; out[i + 1] = (uint8_t)(word >> 8); out[i + 2] = (uint8_t)(word >> 16); out[i + 3] = (uint8_t)(word >> 24); }
+        }
+        for (; i < body; i++) {
+            out[i] = (uint8_t)(e >> 8);
+            const uint32_t k = e & 31u;
+            step(e);
+            cnt -= k; used += k;
+            refill();
+        }
+        out[i] = (uint8_t)(e >> 8);
+    }
+    a.status[b] = (used != cur - floor_bits) ? ST_LENGTH : ST_OK;   // ran dry, or bits left over (lib.rs:205,245)
+}
+
+__global__ void __launch_bounds__(32) k_tps_decode(DecArgs a, TpsTables g)
+{
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.nblocks) return;
+    const uint4 m = g.meta[b];
+    if (!m.z) return;
+    tps_decode_stream(a, b, m, g.dec_tab + ((size_t)b << a.tlmax));
+}
+
+// The same streams with their tables in SHARED memory: a CTA takes `per_cta` blocks (as many as tables fit: 28 at
+// table_log 11), copies their tables in, and lanes 0 .. lanes_per_warp - 1 of its per_cta / lanes_per_warp warps run one
+// stream each.  A stream is a long dependent instruction sequence, so what counts is how many warps a scheduler can
+// alternate between: one stream per warp (28 warps, 7 per scheduler) issues an instruction nearly every cycle.
+__global__ void __launch_bounds__(1024) k_tps_decode_smem(DecArgs a, TpsTables g, uint32_t per_cta, uint32_t lanes_per_warp)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint32_t *sm = reinterpret_cast<uint32_t *>(smem_raw);
+    const uint32_t first = blockIdx.x * per_cta, size = 1u << a.tlmax;
+    for (uint32_t j = 0; j < per_cta; j++) {
+        const uint32_t b = first + j;
+        if (b >= a.nblocks) break;
+        const uint4 *src = reinterpret_cast<const uint4 *>(g.dec_tab + ((size_t)b << a.tlmax));
+        uint4 *dst = reinterpret_cast<uint4 *>(sm + (size_t)j * size);
+        for (uint32_t i = threadIdx.x; i < size / 4; i += blockDim.x) {
+            const uint4 v = src[i];
+            dst[i] = make_uint4(tps_smem_entry(v.x), tps_smem_entry(v.y), tps_smem_entry(v.z), tps_smem_entry(v.w));
+        }
+    }
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane >= lanes_per_warp) return;
+    const uint32_t j = warp * lanes_per_warp + lane, b = first + j;
+    if (j >= per_cta || b >= a.nblocks) return;
+    const uint4 m = g.meta[b];
+    if (!m.z) return;
+    tps_decode_stream_smem(a, b, m, (uint32_t)__cvta_generic_to_shared(sm + (size_t)j * size));
 }
 
 }  // namespace fsed

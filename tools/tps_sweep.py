@@ -9,7 +9,10 @@ def timed(fn, reps=3):
     for _ in range(reps): fn()
     b.record(); torch.cuda.synchronize()
     return a.elapsed_time(b) / reps
-for bs, mib in ((131072, 512), (131072, 1024), (131072, 2048), (65536, 1024), (16384, 512), (4096, 256)):
+SIZES = ((131072, 512), (131072, 1024), (131072, 2048), (65536, 1024), (16384, 512), (4096, 256))
+if len(sys.argv) > 1:                                    # tps_sweep.py 131072:8192 65536:1024 ...
+    SIZES = tuple(tuple(int(v) for v in a.split(":")) for a in sys.argv[1:])
+for bs, mib in SIZES:
     n = mib << 20
     src = ctx.generate("geo", 0xC0FFEE04, n)
     for ns in (2, 1):
