@@ -74,8 +74,8 @@ def kernel_names(tmode, seg, tlog=0, nblocks=0, num_sms=148, smem_per_sm=233472,
     elif n == 64:
         enc, dec = "k_encode64_blocks", ("k_decode64c_blocks" if tl <= 12 else "k_decode64_blocks")
     elif n <= 2 and tmode == 0 and tl <= 12 and nblocks >= 4096:
-        enc = "k_tps_encode"                                           # one thread per stream (fse_tps.cuh)
-        dec = "k_tps_decode"
+        enc = "k_tps_prepare_enc + k_tps_encode_smem"                  # one thread per stream, tables in shared memory (fse_tps.cuh)
+        dec = "k_tps_prepare_dec + k_tps_decode_smem"
     else:
         enc, dec = "k_encode_blocks", "k_decode_blocks"
     return {"hist": "k_hist_blocks16", "encode": enc, "decode": dec, "scan": "k_scan_sizes", "gather": "k_gather"}
@@ -751,6 +751,28 @@ def run_ours(args, wl):
             except Exception as ex:
                 configs[key] = {"error": repr(ex)}
                 barrier(env)
+        # c4 in the reference's OWN stream formats (fse_compress2 / fse_compress: two states / one state per block, the
+        # bytes a user of the crate has): one thread per stream, tables in shared memory (fse_tps.cuh)
+        global N_STATES
+        keep = N_STATES
+        for ns in (2, 1):
+            key = "c4_reference_format_%dstate" % ns
+            try:
+                N_STATES = ns
+                j = Job(env, "c4")
+                r = measure(env, j, 3, 3)
+                configs[key] = {"workload": "c4: " + j.w["desc"] + "; block format = the crate's fse_compress%s" % ("2" if ns == 2 else ""),
+                                "scaling": j.w["scaling"], "total_bytes": j.total_bytes, "block_size": j.w["bs"], "n_states": ns,
+                                "value": r["value"], "unit": "GB/s", "ms_per_step": r["ms_per_step"],
+                                "encode_GBps_per_gpu": r["encode_GBps"], "decode_GBps_per_gpu": r["decode_GBps"],
+                                "compressed_ratio": r["compressed_ratio"], "kernel_ms_per_step": r["kernel_ms_per_step"],
+                                "roofline_frac": r["roofline"]["frac"], "roofline_kernel": r["roofline"]["kernel"]}
+                j.release()
+            except Exception as ex:
+                configs[key] = {"error": repr(ex)}
+                barrier(env)
+            finally:
+                N_STATES = keep
 
     if rank == 0:
         line = {

@@ -134,6 +134,17 @@ struct Timed {
 
 bool pow2(uint32_t v) { return v && !(v & (v - 1)); }
 
+// Streams per CTA of the shared-memory thread-per-stream kernels (one CTA per SM at a time): `fit` table sets fit in shared
+// memory; the streams are spread evenly over the fewest rounds of num_sms CTAs, so that the last round is as full as the
+// others (8 192 blocks, 37 sets fit: 2 rounds of 28 instead of one of 37 and half a round)
+uint32_t tps_streams_per_cta(size_t streams, size_t num_sms, size_t fit)
+{
+    if (fit < 1) return 0;
+    const size_t rounds = (streams + num_sms * fit - 1) / (num_sms * fit);
+    const size_t per = (streams + num_sms * rounds - 1) / (num_sms * std::max<size_t>(rounds, 1));
+    return (uint32_t)std::max<size_t>(1, std::min(per, fit));
+}
+
 // development overrides (variant builds under tools/bin only): the release library ignores the environment
 int dev_opt(const char *name, int dflt)
 {
@@ -755,11 +766,9 @@ int fse_b200_compress_blocks_async(fse_b200_ctx *ctx, const uint8_t *d_src, size
             const int pg = (int)std::min<size_t>((count + wpc - 1) / wpc, (size_t)ctx->num_sms);
             k_tps_prepare_enc<<<pg, wpc * 32, (size_t)wpc * per_warp, ctx->stream>>>(a, g);
             const size_t set_bytes = ((size_t)2 << tlmax) + 2048;
-            const uint32_t lpw = (uint32_t)std::max(1, dev_opt("FSE_B200_TPS_ENC_LPW", 4));
-            // as many table sets as shared memory holds, but no more streams per CTA than leaves every SM one
-            const uint32_t per_cta = (uint32_t)std::min<size_t>(std::min<size_t>(32 * lpw, (ctx->smem_optin - 64) / set_bytes),
-                                                                std::max<size_t>(4, (count + ctx->num_sms - 1) / ctx->num_sms));
-            if (per_cta >= 4 && dev_opt("FSE_B200_TPS_ENC_SMEM", 1))
+            const uint32_t lpw = (uint32_t)std::max(1, dev_opt("FSE_B200_TPS_ENC_LPW", 8));
+            const uint32_t per_cta = tps_streams_per_cta(count, (size_t)ctx->num_sms, std::min<size_t>(32 * lpw, (ctx->smem_optin - 64) / set_bytes));
+            if (per_cta >= 1 && set_bytes * 4 <= ctx->smem_optin - 64 && dev_opt("FSE_B200_TPS_ENC_SMEM", 1))
                 k_tps_encode_smem<<<(count + per_cta - 1) / per_cta, ((per_cta + lpw - 1) / lpw) * 32, per_cta * set_bytes, ctx->stream>>>(a, g, per_cta, lpw);
             else
                 k_tps_encode<<<(count + 31) / 32, 32, 0, ctx->stream>>>(a, g);  // one warp per CTA: few blocks still reach every SM
@@ -916,9 +925,8 @@ int fse_b200_decompress_blocks_async(fse_b200_ctx *ctx, const uint8_t *d_comp, s
             Timed t(ctx, FSE_B200_K_DECODE);
             k_tps_prepare_dec<<<grid, wpc * 32, (size_t)wpc * lay.total, ctx->stream>>>(a, g);
             const uint32_t lpw = (uint32_t)std::max(1, dev_opt("FSE_B200_TPS_LPW", 4));
-            const uint32_t per_cta = (uint32_t)std::min<size_t>(std::min<size_t>(32 * lpw, (ctx->smem_optin - 64) / ((size_t)4 << tlmax)),
-                                                                std::max<size_t>(4, (nblocks + ctx->num_sms - 1) / ctx->num_sms));
-            if (per_cta >= 4 && dev_opt("FSE_B200_TPS_SMEM", 1))
+            const uint32_t per_cta = tps_streams_per_cta(nblocks, (size_t)ctx->num_sms, std::min<size_t>(32 * lpw, (ctx->smem_optin - 64) / ((size_t)4 << tlmax)));
+            if (per_cta >= 1 && ((size_t)16 << tlmax) <= ctx->smem_optin - 64 && dev_opt("FSE_B200_TPS_SMEM", 1))
                 k_tps_decode_smem<<<(unsigned)((nblocks + per_cta - 1) / per_cta), ((per_cta + lpw - 1) / lpw) * 32,
                                     (size_t)per_cta * ((size_t)4 << tlmax), ctx->stream>>>(a, g, per_cta, lpw);
             else

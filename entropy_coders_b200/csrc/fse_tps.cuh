@@ -225,13 +225,12 @@ __device__ __forceinline__ void tps_encode_stream_smem(const EncArgs &a, uint32_
         lo = __funnelshift_r(lo, hi, n);
         hi = __funnelshift_r(hi, v, n);
     };
-    auto flush = [&]() {                                      // cnt < 64
-        if (cnt >= 32) {
-            const uint32_t w = __funnelshift_rc(lo, hi, 64 - cnt);
-            if (wp < cap) __stcs(pay + wp, w);
-            wp++;
-            cnt -= 32;
-        }
+    auto flush = [&]() {                                      // cnt < 64; a full word leaves the window (no branch: see tps_ld_if)
+        const uint32_t w = __funnelshift_rc(lo, hi, 64 - cnt);
+        asm volatile("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q st.global.cs.u32 [%0], %1; }" ::"l"(pay + wp), "r"(w),
+                     "r"((uint32_t)(cnt >= 32 && wp < cap)) : "memory");
+        wp += cnt >> 5;
+        cnt &= 31u;
     };
     auto ld_t = [&](uint32_t sym) -> uint2 { return lds_v2(tt_s + sym * 8); };
     auto first = [&](uint32_t sym) -> uint32_t {              // Encoder::new_first_symbol, fse.rs:210-218
@@ -507,6 +506,17 @@ __device__ __forceinline__ void tps_decode_stream(const DecArgs &a, uint32_t b, 
 // Chain per symbol: LDS, SHF, LEA (and SHF + IADD beside the SHF); ~15 instructions per symbol instead of 48.
 __device__ __forceinline__ uint32_t tps_smem_entry(uint32_t e) { return (e >> 24) | ((e >> 8) & 0xff00u) | ((e & 0xffffu) << 18); }
 
+// predicated global load / L1 prefetch (no branch: the lanes of a warp run different streams, and a divergent branch with
+// its reconvergence costs more than the handful of instructions it would skip)
+__device__ __forceinline__ void tps_ld_if(uint32_t &v, const uint32_t *p, bool c)
+{
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q ld.global.nc.u32 %0, [%1]; }" : "+r"(v) : "l"(p), "r"((uint32_t)c));
+}
+__device__ __forceinline__ void tps_prefetch_if(const void *p, bool c)
+{
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %1, 0; @q prefetch.global.L1 [%0]; }" ::"l"(p), "r"((uint32_t)c));
+}
+
 __device__ __forceinline__ void tps_decode_stream_smem(const DecArgs &a, uint32_t b, uint4 m, uint32_t tab_s)
 {
     const uint32_t log2 = m.x, consumed = m.y, N = a.n_states;
@@ -522,26 +532,25 @@ __device__ __forceinline__ void tps_decode_stream_smem(const DecArgs &a, uint32_
     const uint32_t cur = (plen - 1) * 8 + ilog2u(pay[plen - 1]) + 8 * bias;             // marker position
     const uint32_t floor_bits = 8 * bias;
     if (cur - floor_bits < N * log2) { a.status[b] = ST_LENGTH; return; }               // lib.rs:197,224-225
-    uint32_t left = (cur + 31) >> 5;                          // words not loaded yet: origin[0 .. left)
-    auto next_word = [&]() -> uint32_t {
-        if (!left) return 0u;
-        left--;
-        if (left >= 24) asm volatile("prefetch.global.L1 [%0];" ::"l"(origin + left - 24));
-        return __ldg(origin + left);
-    };
-    const uint32_t top = next_word();
+    const uint32_t words = (cur + 31) >> 5;                   // origin[0 .. words) hold the stack
+    const uint32_t top = words ? __ldg(origin + words - 1) : 0u;
+    int32_t k = (int32_t)words - 2;                           // nx = origin[k], zeros below the stack
+    uint32_t nx = k >= 0 ? __ldg(origin + k) : 0u;
     const uint32_t r = cur & 31;
     uint32_t wh = r ? top << (32 - r) : top, wl = 0u;
-    uint32_t cnt = r ? r : 32u;                               // valid bits in the window (zeros below the stack count too)
-    uint32_t nx = next_word();
+    uint32_t cnt = r ? r : 32u;                               // valid bits in the window (the zeros below the stack count too)
     uint32_t used = 0;
-    auto refill = [&]() {                                     // cnt <= 32: wl is empty
-        if (cnt <= 32) {
-            wh |= __funnelshift_rc(nx, 0u, cnt);
-            wl = __funnelshift_rc(0u, nx, cnt);
-            cnt += 32;
-            nx = next_word();
-        }
+    auto refill = [&]() {                                     // when 32 bits or fewer are left: wl is empty, nx goes in
+        const bool need = cnt <= 32;
+        wh |= __funnelshift_rc(nx, 0u, cnt);                  // nx >> cnt: nothing when cnt > 32 (the shift is clamped)
+        const uint32_t t = __funnelshift_rc(0u, nx, cnt);
+        wl = need ? t : wl;
+        cnt = need ? cnt + 32 : cnt;
+        k = need ? k - 1 : k;
+        nx = need ? 0u : nx;
+        const uint32_t *q = origin + k;
+        tps_ld_if(nx, q, need && k >= 0);
+        tps_prefetch_if(q - 24, need && (k & 7) == 7 && k >= 24);       // a new sector: fetch the third one below it
     };
     refill();
     auto take = [&](uint32_t e) -> uint32_t {                 // e & 31 bits off the top of the window
@@ -554,63 +563,81 @@ __device__ __forceinline__ void tps_decode_stream_smem(const DecArgs &a, uint32_
         const uint32_t bits = take(e);
         e = lds_u32((e >> 16) + tab_s + bits * 4);
     };
+    auto account = [&](uint32_t e0_, uint32_t e1_) {
+        const uint32_t kb = (e0_ & 31u) + (e1_ & 31u);
+        cnt -= kb;
+        used += kb;
+    };
     const uint32_t body = bn - N;
-    const bool aligned = (((uintptr_t)out) & 3) == 0;
     uint32_t i = 0;
     if (N == 2) {
-        const uint32_t s0 = take(log2), s1 = take(log2);      // Decoder::new, fse.rs:349-352: state 0 first
+        // eA: entry of the state whose turn it is (state i & 1 decodes symbol i: Decoder::new reads state 0 first, fse.rs:349-352)
+        const uint32_t s0 = take(log2), s1 = take(log2);
         cnt -= 2 * log2; used += 2 * log2;
         refill();
-        uint32_t e0 = lds_u32(tab_s + s0 * 4), e1 = lds_u32(tab_s + s1 * 4);
-        for (; i + 4 <= body; i += 4) {
-            const uint32_t a0 = e0, a1 = e1;
-            step(e0); step(e1);
-            { const uint32_t k = (a0 & 31u) + (a1 & 31u); cnt -= k; used += k; }
+        uint32_t eA = lds_u32(tab_s + s0 * 4), eB = lds_u32(tab_s + s1 * 4);
+        auto single = [&]() {                                 // one symbol, then the other state's turn
+            out[i] = (uint8_t)(eA >> 8);
+            const uint32_t kb = eA & 31u;
+            step(eA);
+            cnt -= kb; used += kb;
             refill();
-            const uint32_t a2 = e0, a3 = e1;
-            step(e0); step(e1);
-            { const uint32_t k = (a2 & 31u) + (a3 & 31u); cnt -= k; used += k; }
+            const uint32_t x = eA; eA = eB; eB = x;
+            i++;
+        };
+        while (i < body && (((uintptr_t)(out + i)) & 3)) single();      // up to an aligned output word
+        auto quad = [&]() -> uint32_t {
+            const uint32_t a0 = eA, a1 = eB;
+            step(eA); step(eB);
+            account(a0, a1);
             refill();
-            const uint32_t word = __byte_perm(__byte_perm(a0, a1, 0x0051), __byte_perm(a2, a3, 0x0051), 0x5410);
-            if (aligned) __stcs(reinterpret_cast<uint32_t *>(out + i), word);
-            else { out[i] = (uint8_t)word; out[i + 1] = (uint8_t)(word >> 8); out[i + 2] = (uint8_t)(word >> 16); out[i + 3] = (uint8_t)(word >> 24); }
+            const uint32_t a2 = eA, a3 = eB;
+            step(eA); step(eB);
+            account(a2, a3);
+            refill();
+            return __byte_perm(__byte_perm(a0, a1, 0x0051), __byte_perm(a2, a3, 0x0051), 0x5410);
+        };
+        for (; i + 8 <= body; i += 8) {
+            const uint32_t w0 = quad();
+            const uint32_t w1 = quad();
+            __stcs(reinterpret_cast<uint32_t *>(out + i), w0);
+            __stcs(reinterpret_cast<uint32_t *>(out + i + 4), w1);
         }
-        for (; i < body; i++) {                               // up to three more body symbols, states in turn
-            const uint32_t e = (i & 1) ? e1 : e0;
-            out[i] = (uint8_t)(e >> 8);
-            uint32_t en = e;
-            step(en);
-            cnt -= e & 31u; used += e & 31u;
-            refill();
-            if (i & 1) e1 = en; else e0 = en;
-        }
-        out[i] = (uint8_t)(((i & 1) ? e1 : e0) >> 8);         // Decoder::finish: symbols body, body + 1 from states (i & 1), ...
-        out[i + 1] = (uint8_t)(((i & 1) ? e0 : e1) >> 8);
+        while (i < body) single();
+        out[i] = (uint8_t)(eA >> 8);                          // Decoder::finish: symbols body, body + 1 from the states in turn
+        out[i + 1] = (uint8_t)(eB >> 8);
     } else {
         const uint32_t s = take(log2);
         cnt -= log2; used += log2;
         refill();
         uint32_t e = lds_u32(tab_s + s * 4);
-        for (; i + 4 <= body; i += 4) {
+        auto single = [&]() {
+            out[i] = (uint8_t)(e >> 8);
+            const uint32_t kb = e & 31u;
+            step(e);
+            cnt -= kb; used += kb;
+            refill();
+            i++;
+        };
+        while (i < body && (((uintptr_t)(out + i)) & 3)) single();
+        auto quad = [&]() -> uint32_t {
             const uint32_t a0 = e; step(e);
             const uint32_t a1 = e; step(e);
-            { const uint32_t k = (a0 & 31u) + (a1 & 31u); cnt -= k; used += k; }
+            account(a0, a1);
             refill();
             const uint32_t a2 = e; step(e);
             const uint32_t a3 = e; step(e);
-            { const uint32_t k = (a2 & 31u) + (a3 & 31u); cnt -= k; used += k; }
+            account(a2, a3);
             refill();
-            const uint32_t word = __byte_perm(__byte_perm(a0, a1, 0x0051), __byte_perm(a2, a3, 0x0051), 0x5410);
-            if (aligned) __stcs(reinterpret_cast<uint32_t *>(out + i), word);
-            else { out[i] = (uint8_t)word; out[i + 1] = (uint8_t)(word >> 8); out[i + 2] = (uint8_t)(word >> 16); out[i + 3] = (uint8_t)(word >> 24); }
+            return __byte_perm(__byte_perm(a0, a1, 0x0051), __byte_perm(a2, a3, 0x0051), 0x5410);
+        };
+        for (; i + 8 <= body; i += 8) {
+            const uint32_t w0 = quad();
+            const uint32_t w1 = quad();
+            __stcs(reinterpret_cast<uint32_t *>(out + i), w0);
+            __stcs(reinterpret_cast<uint32_t *>(out + i + 4), w1);
         }
-        for (; i < body; i++) {
-            out[i] = (uint8_t)(e >> 8);
-            const uint32_t k = e & 31u;
-            step(e);
-            cnt -= k; used += k;
-            refill();
-        }
+        while (i < body) single();
         out[i] = (uint8_t)(e >> 8);
     }
     a.status[b] = (used != cur - floor_bits) ? ST_LENGTH : ST_OK;   // ran dry, or bits left over (lib.rs:205,245)

@@ -1,4 +1,9 @@
-# development run: per-kernel times of c4 in the reference's formats, then an ncu capture of the thread-per-stream kernels
-bash tools/quick.sh "--workload c4 --n-states 2" "--workload c4 --n-states 1" "--workload c2 --n-states 2" > gpurun_out/tps_quick.log 2>&1
-timeout 600 ncu --set full --import-source on --clock-control none --kernel-name regex:k_tps -c 8 -o gpurun_out/r2_tps -f python tools/tps_profile.py > gpurun_out/tps_ncu.log 2>&1
-tail -3 gpurun_out/tps_ncu.log
+# development run: the shared-memory thread-per-stream kernels (tests, then lanes-per-warp sweep with the FSE_DEV build)
+timeout 900 python -m pytest tests -m gpu -x -q -k "many_streams or reference_formats" > gpurun_out/t_smem.log 2>&1
+tail -3 gpurun_out/t_smem.log
+export FSE_B200_LIB=$PWD/tools/bin/libdev.so
+for cfg in "4 4" "8 8" "2 2"; do
+  set -- $cfg
+  echo "== TPS_LPW(dec)=$1 ENC_LPW=$2"
+  FSE_B200_TPS_LPW=$1 FSE_B200_TPS_ENC_LPW=$2 timeout 300 python tools/tps_sweep.py 131072:8192 131072:1024 16384:512
+done > gpurun_out/tps_smem2.log 2>&1
