@@ -707,6 +707,7 @@ def run_probe(args, wl):
 
 
 def run_ours(args, wl):
+    global N_STATES
     import torch
     env = make_env()
     world, rank = env["world"], env["rank"]
@@ -753,7 +754,6 @@ def run_ours(args, wl):
                 barrier(env)
         # c4 in the reference's OWN stream formats (fse_compress2 / fse_compress: two states / one state per block, the
         # bytes a user of the crate has): one thread per stream, tables in shared memory (fse_tps.cuh)
-        global N_STATES
         keep = N_STATES
         for ns in (2, 1):
             key = "c4_reference_format_%dstate" % ns

@@ -296,7 +296,8 @@ int fse_b200_create(int device, void *stream, fse_b200_ctx **out)
     cudaFuncSetAttribute(k_build_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
     cudaFuncSetAttribute(k_tps_prepare_enc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
     cudaFuncSetAttribute(k_tps_prepare_dec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
-    cudaFuncSetAttribute(k_tps_decode_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
+    cudaFuncSetAttribute(k_tps_decode_smem<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
+    cudaFuncSetAttribute(k_tps_decode_smem<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
     cudaFuncSetAttribute(k_tps_encode_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
     cudaFuncSetAttribute(k_encode_sh_global<16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 64);
     cudaFuncSetAttribute(k_decode_sh_global, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 64);
@@ -766,8 +767,8 @@ int fse_b200_compress_blocks_async(fse_b200_ctx *ctx, const uint8_t *d_src, size
             const int pg = (int)std::min<size_t>((count + wpc - 1) / wpc, (size_t)ctx->num_sms);
             k_tps_prepare_enc<<<pg, wpc * 32, (size_t)wpc * per_warp, ctx->stream>>>(a, g);
             const size_t set_bytes = ((size_t)2 << tlmax) + 2048;
-            const uint32_t lpw = (uint32_t)std::max(1, dev_opt("FSE_B200_TPS_ENC_LPW", 8));
-            const uint32_t per_cta = tps_streams_per_cta(count, (size_t)ctx->num_sms, std::min<size_t>(32 * lpw, (ctx->smem_optin - 64) / set_bytes));
+            const uint32_t per_cta = tps_streams_per_cta(count, (size_t)ctx->num_sms, std::min<size_t>(256, (ctx->smem_optin - 64) / set_bytes));
+            const uint32_t lpw = (uint32_t)std::max(1, std::min(32, dev_opt("FSE_B200_TPS_ENC_LPW", (int)((per_cta + 4) / 5))));   // ~five warps (measured 2 .. 16 lanes)
             if (per_cta >= 1 && set_bytes * 4 <= ctx->smem_optin - 64 && dev_opt("FSE_B200_TPS_ENC_SMEM", 1))
                 k_tps_encode_smem<<<(count + per_cta - 1) / per_cta, ((per_cta + lpw - 1) / lpw) * 32, per_cta * set_bytes, ctx->stream>>>(a, g, per_cta, lpw);
             else
@@ -924,11 +925,21 @@ int fse_b200_decompress_blocks_async(fse_b200_ctx *ctx, const uint8_t *d_comp, s
             TpsTables g{nullptr, nullptr, ctx->tps_dec_tab.as<uint32_t>(), ctx->tps_meta.as<uint4>(), 0u, (uint32_t)nblocks};
             Timed t(ctx, FSE_B200_K_DECODE);
             k_tps_prepare_dec<<<grid, wpc * 32, (size_t)wpc * lay.total, ctx->stream>>>(a, g);
-            const uint32_t lpw = (uint32_t)std::max(1, dev_opt("FSE_B200_TPS_LPW", 4));
-            const uint32_t per_cta = tps_streams_per_cta(nblocks, (size_t)ctx->num_sms, std::min<size_t>(32 * lpw, (ctx->smem_optin - 64) / ((size_t)4 << tlmax)));
-            if (per_cta >= 1 && ((size_t)16 << tlmax) <= ctx->smem_optin - 64 && dev_opt("FSE_B200_TPS_SMEM", 1))
-                k_tps_decode_smem<<<(unsigned)((nblocks + per_cta - 1) / per_cta), ((per_cta + lpw - 1) / lpw) * 32,
-                                    (size_t)per_cta * ((size_t)4 << tlmax), ctx->stream>>>(a, g, per_cta, lpw);
+            // 16-bit entries + symbol bytes (3 bytes per cell, table_log <= 11) when the smaller sets save a round of CTAs
+            // (c4: 37 streams per SM instead of 28, 12 rounds instead of 16: 83 -> 72 ms); the 32-bit DecodeTransform
+            // otherwise (fewer instructions per symbol).  Lanes per warp: about eight warps per CTA (measured 2 .. 8).
+            const size_t fit_w = std::min<size_t>(256, (ctx->smem_optin - 64) / ((size_t)4 << tlmax));
+            const size_t fit_c = std::min<size_t>(256, (ctx->smem_optin - 64) / ((size_t)3 << tlmax));
+            auto rounds = [&](size_t fit) { return fit ? (nblocks + ctx->num_sms * fit - 1) / (ctx->num_sms * fit) : (size_t)-1; };
+            const bool compact = dev_opt("FSE_B200_TPS_COMPACT", tlmax <= 11 && rounds(fit_c) < rounds(fit_w));
+            const size_t set_bytes = (size_t)(compact ? 3 : 4) << tlmax;
+            const uint32_t per_cta = tps_streams_per_cta(nblocks, (size_t)ctx->num_sms, compact ? fit_c : fit_w);
+            const uint32_t lpw = (uint32_t)std::max(1, std::min(32, dev_opt("FSE_B200_TPS_LPW", (int)((per_cta + 7) / 8))));
+            const unsigned dgrid = (unsigned)((nblocks + per_cta - 1) / std::max(per_cta, 1u)), dthreads = ((per_cta + lpw - 1) / lpw) * 32;
+            if (per_cta >= 1 && 4 * set_bytes <= ctx->smem_optin - 64 && dev_opt("FSE_B200_TPS_SMEM", 1)) {
+                if (compact) k_tps_decode_smem<true><<<dgrid, dthreads, per_cta * set_bytes, ctx->stream>>>(a, g, per_cta, lpw);
+                else k_tps_decode_smem<false><<<dgrid, dthreads, per_cta * set_bytes, ctx->stream>>>(a, g, per_cta, lpw);
+            }
             else
                 k_tps_decode<<<(unsigned)((nblocks + 31) / 32), 32, 0, ctx->stream>>>(a, g);
             ctx->launches++;

@@ -16,6 +16,7 @@
 #pragma once
 #include "fse_kernels.cuh"
 #include "fse_kernels64.cuh"
+#include "fse_decode128c.cuh"
 
 namespace fsed {
 
@@ -517,7 +518,11 @@ __device__ __forceinline__ void tps_prefetch_if(const void *p, bool c)
     asm volatile("{ .reg .pred q; setp.ne.u32 q, %1, 0; @q prefetch.global.L1 [%0]; }" ::"l"(p), "r"((uint32_t)c));
 }
 
-__device__ __forceinline__ void tps_decode_stream_smem(const DecArgs &a, uint32_t b, uint4 m, uint32_t tab_s)
+// COMPACT (table_log <= 11): 16-bit entries `num_bits | new_state base << 5` and the symbols as bytes beside them (3 bytes per
+// cell instead of 4: 37 streams per SM instead of 28 at table_log 11); the state is the entry's shared ADDRESS, the symbol
+// of a state is loaded with its entry from sym_c + address / 2.
+template <bool COMPACT>
+__device__ __forceinline__ void tps_decode_stream_smem(const DecArgs &a, uint32_t b, uint4 m, uint32_t tab_s, uint32_t sym_c)
 {
     const uint32_t log2 = m.x, consumed = m.y, N = a.n_states;
     const size_t off = (size_t)b * a.block_size;
@@ -549,7 +554,7 @@ __device__ __forceinline__ void tps_decode_stream_smem(const DecArgs &a, uint32_
         k = need ? k - 1 : k;
         nx = need ? 0u : nx;
         const uint32_t *q = origin + k;
-        tps_ld_if(nx, q, need && k >= 0);
+        tps_ld_if(nx, q, need && k >= 0);                     // (a second word in flight was measured: no gain)
         tps_prefetch_if(q - 24, need && (k & 7) == 7 && k >= 24);       // a new sector: fetch the third one below it
     };
     refill();
@@ -559,9 +564,26 @@ __device__ __forceinline__ void tps_decode_stream_smem(const DecArgs &a, uint32_
         wl = __funnelshift_l(0u, wl, e);
         return bits;
     };
-    auto step = [&](uint32_t &e) {                            // fse.rs:363-373: new_state + bits, then its entry
+    auto look = [&](uint32_t &e, uint32_t &y, uint32_t state) {               // entry (and symbol) of a state
+        if (COMPACT) { const uint32_t ad = tab_s + state * 2; e = lds_u16(ad); y = lds_u8((ad >> 1) + sym_c); }
+        else { e = lds_u32(tab_s + state * 4); y = e; }
+    };
+    auto step = [&](uint32_t &e, uint32_t &y) {               // fse.rs:363-373: new_state + bits, then its entry
         const uint32_t bits = take(e);
-        e = lds_u32((e >> 16) + tab_s + bits * 4);
+        if (COMPACT) {
+            const uint32_t ad = (e >> 4) + tab_s + bits * 2;  // bit 4 of an entry is 0: e >> 4 = 2 * base
+            e = lds_u16(ad);
+            y = lds_u8((ad >> 1) + sym_c);
+        } else {
+            e = lds_u32((e >> 16) + tab_s + bits * 4);
+            y = e;
+        }
+    };
+    auto sym_of = [&](uint32_t y) -> uint8_t { return (uint8_t)(COMPACT ? y : y >> 8); };
+    // four symbols -> one word: the symbol is byte 1 of a wide entry, byte 0 of y in the compact form
+    auto word_of = [&](uint32_t y0, uint32_t y1, uint32_t y2, uint32_t y3) -> uint32_t {
+        return COMPACT ? __byte_perm(__byte_perm(y0, y1, 0x0040), __byte_perm(y2, y3, 0x0040), 0x5410)
+                       : __byte_perm(__byte_perm(y0, y1, 0x0051), __byte_perm(y2, y3, 0x0051), 0x5410);
     };
     auto account = [&](uint32_t e0_, uint32_t e1_) {
         const uint32_t kb = (e0_ & 31u) + (e1_ & 31u);
@@ -575,27 +597,30 @@ __device__ __forceinline__ void tps_decode_stream_smem(const DecArgs &a, uint32_
         const uint32_t s0 = take(log2), s1 = take(log2);
         cnt -= 2 * log2; used += 2 * log2;
         refill();
-        uint32_t eA = lds_u32(tab_s + s0 * 4), eB = lds_u32(tab_s + s1 * 4);
+        uint32_t eA, eB, yA, yB;
+        look(eA, yA, s0);
+        look(eB, yB, s1);
         auto single = [&]() {                                 // one symbol, then the other state's turn
-            out[i] = (uint8_t)(eA >> 8);
+            out[i] = sym_of(yA);
             const uint32_t kb = eA & 31u;
-            step(eA);
+            step(eA, yA);
             cnt -= kb; used += kb;
             refill();
-            const uint32_t x = eA; eA = eB; eB = x;
+            uint32_t x = eA; eA = eB; eB = x;
+            x = yA; yA = yB; yB = x;
             i++;
         };
         while (i < body && (((uintptr_t)(out + i)) & 3)) single();      // up to an aligned output word
         auto quad = [&]() -> uint32_t {
-            const uint32_t a0 = eA, a1 = eB;
-            step(eA); step(eB);
+            const uint32_t a0 = eA, a1 = eB, y0 = yA, y1 = yB;
+            step(eA, yA); step(eB, yB);
             account(a0, a1);
             refill();
-            const uint32_t a2 = eA, a3 = eB;
-            step(eA); step(eB);
+            const uint32_t a2 = eA, a3 = eB, y2 = yA, y3 = yB;
+            step(eA, yA); step(eB, yB);
             account(a2, a3);
             refill();
-            return __byte_perm(__byte_perm(a0, a1, 0x0051), __byte_perm(a2, a3, 0x0051), 0x5410);
+            return word_of(y0, y1, y2, y3);
         };
         for (; i + 8 <= body; i += 8) {
             const uint32_t w0 = quad();
@@ -604,32 +629,33 @@ __device__ __forceinline__ void tps_decode_stream_smem(const DecArgs &a, uint32_
             __stcs(reinterpret_cast<uint32_t *>(out + i + 4), w1);
         }
         while (i < body) single();
-        out[i] = (uint8_t)(eA >> 8);                          // Decoder::finish: symbols body, body + 1 from the states in turn
-        out[i + 1] = (uint8_t)(eB >> 8);
+        out[i] = sym_of(yA);                                 // Decoder::finish: symbols body, body + 1 from the states in turn
+        out[i + 1] = sym_of(yB);
     } else {
         const uint32_t s = take(log2);
         cnt -= log2; used += log2;
         refill();
-        uint32_t e = lds_u32(tab_s + s * 4);
+        uint32_t e, y;
+        look(e, y, s);
         auto single = [&]() {
-            out[i] = (uint8_t)(e >> 8);
+            out[i] = sym_of(y);
             const uint32_t kb = e & 31u;
-            step(e);
+            step(e, y);
             cnt -= kb; used += kb;
             refill();
             i++;
         };
         while (i < body && (((uintptr_t)(out + i)) & 3)) single();
         auto quad = [&]() -> uint32_t {
-            const uint32_t a0 = e; step(e);
-            const uint32_t a1 = e; step(e);
+            const uint32_t a0 = e, y0 = y; step(e, y);
+            const uint32_t a1 = e, y1 = y; step(e, y);
             account(a0, a1);
             refill();
-            const uint32_t a2 = e; step(e);
-            const uint32_t a3 = e; step(e);
+            const uint32_t a2 = e, y2 = y; step(e, y);
+            const uint32_t a3 = e, y3 = y; step(e, y);
             account(a2, a3);
             refill();
-            return __byte_perm(__byte_perm(a0, a1, 0x0051), __byte_perm(a2, a3, 0x0051), 0x5410);
+            return word_of(y0, y1, y2, y3);
         };
         for (; i + 8 <= body; i += 8) {
             const uint32_t w0 = quad();
@@ -638,7 +664,7 @@ __device__ __forceinline__ void tps_decode_stream_smem(const DecArgs &a, uint32_
             __stcs(reinterpret_cast<uint32_t *>(out + i + 4), w1);
         }
         while (i < body) single();
-        out[i] = (uint8_t)(e >> 8);
+        out[i] = sym_of(y);
     }
     a.status[b] = (used != cur - floor_bits) ? ST_LENGTH : ST_OK;   // ran dry, or bits left over (lib.rs:205,245)
 }
@@ -653,22 +679,29 @@ __global__ void __launch_bounds__(32) k_tps_decode(DecArgs a, TpsTables g)
 }
 
 // The same streams with their tables in SHARED memory: a CTA takes `per_cta` blocks (as many as tables fit: 28 at
-// table_log 11), copies their tables in, and lanes 0 .. lanes_per_warp - 1 of its per_cta / lanes_per_warp warps run one
-// stream each.  A stream is a long dependent instruction sequence, so what counts is how many warps a scheduler can
-// alternate between: one stream per warp (28 warps, 7 per scheduler) issues an instruction nearly every cycle.
+// table_log 11, 37 in the compact form), copies their tables in, and lanes 0 .. lanes_per_warp - 1 of its warps run one
+// stream each.
+template <bool COMPACT>
 __global__ void __launch_bounds__(1024) k_tps_decode_smem(DecArgs a, TpsTables g, uint32_t per_cta, uint32_t lanes_per_warp)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    uint32_t *sm = reinterpret_cast<uint32_t *>(smem_raw);
     const uint32_t first = blockIdx.x * per_cta, size = 1u << a.tlmax;
+    const uint32_t set_bytes = COMPACT ? 3u * size : 4u * size;
     for (uint32_t j = 0; j < per_cta; j++) {
         const uint32_t b = first + j;
         if (b >= a.nblocks) break;
         const uint4 *src = reinterpret_cast<const uint4 *>(g.dec_tab + ((size_t)b << a.tlmax));
-        uint4 *dst = reinterpret_cast<uint4 *>(sm + (size_t)j * size);
+        uint8_t *set = smem_raw + (size_t)j * set_bytes;
         for (uint32_t i = threadIdx.x; i < size / 4; i += blockDim.x) {
-            const uint4 v = src[i];
-            dst[i] = make_uint4(tps_smem_entry(v.x), tps_smem_entry(v.y), tps_smem_entry(v.z), tps_smem_entry(v.w));
+            const uint4 v = src[i];                           // DecodeTransform: new_state base | symbol << 16 | num_bits << 24
+            if (COMPACT) {
+                auto c16 = [](uint32_t e) -> uint32_t { return (e >> 24) | ((e & 0xffffu) << 5); };
+                reinterpret_cast<uint2 *>(set)[i] = make_uint2(c16(v.x) | c16(v.y) << 16, c16(v.z) | c16(v.w) << 16);
+                reinterpret_cast<uint32_t *>(set + 2u * size)[i] =
+                    ((v.x >> 16) & 0xffu) | ((v.y >> 8) & 0xff00u) | (v.z & 0xff0000u) | ((v.w << 8) & 0xff000000u);
+            } else {
+                reinterpret_cast<uint4 *>(set)[i] = make_uint4(tps_smem_entry(v.x), tps_smem_entry(v.y), tps_smem_entry(v.z), tps_smem_entry(v.w));
+            }
         }
     }
     __syncthreads();
@@ -678,7 +711,8 @@ __global__ void __launch_bounds__(1024) k_tps_decode_smem(DecArgs a, TpsTables g
     if (j >= per_cta || b >= a.nblocks) return;
     const uint4 m = g.meta[b];
     if (!m.z) return;
-    tps_decode_stream_smem(a, b, m, (uint32_t)__cvta_generic_to_shared(sm + (size_t)j * size));
+    const uint32_t tab_s = (uint32_t)__cvta_generic_to_shared(smem_raw + (size_t)j * set_bytes);
+    tps_decode_stream_smem<COMPACT>(a, b, m, tab_s, COMPACT ? tab_s + 2u * size - (tab_s >> 1) : 0u);
 }
 
 }  // namespace fsed
