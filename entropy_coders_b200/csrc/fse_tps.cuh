@@ -203,6 +203,17 @@ __global__ void __launch_bounds__(32) k_tps_encode(EncArgs a, TpsTables g)
     tps_encode_stream(a, g.first + r, m, g.enc_tab + ((size_t)r << a.tlmax), g.enc_tt + (size_t)r * 256);
 }
 
+// predicated global load / L1 prefetch (no branch: the lanes of a warp run different streams, and a divergent branch with
+// its reconvergence costs more than the handful of instructions it would skip)
+__device__ __forceinline__ void tps_ld_if(uint32_t &v, const uint32_t *p, bool c)
+{
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q ld.global.nc.u32 %0, [%1]; }" : "+r"(v) : "l"(p), "r"((uint32_t)c));
+}
+__device__ __forceinline__ void tps_prefetch_if(const void *p, bool c)
+{
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %1, 0; @q prefetch.global.L1 [%0]; }" ::"l"(p), "r"((uint32_t)c));
+}
+
 // ---- the shared-memory form of the same encoder (k_tps_encode_smem).  The state chain is s -> nb -> s >> nb -> look-up
 // (fse.rs:227-239); everything else is arranged to stay off it and to cost few instructions:
 //  * the symbol transforms of the shared copy hold the ADDRESS of their first next-state cell (tab_s + 2 * find_state), so
@@ -246,10 +257,12 @@ __device__ __forceinline__ void tps_encode_stream_smem(const EncArgs &a, uint32_
         st = lds_u16(t.y + ((st >> nb) << 1));
         return nb;
     };
-    auto word_at = [&](int32_t i) -> uint32_t {               // symbols i - 3 .. i (src + i - 3 is aligned)
-        if ((i & 31) < 4 && i >= 99) asm volatile("prefetch.global.L1 [%0];" ::"l"(src + i - 99));
-        return __ldg(reinterpret_cast<const uint32_t *>(src + i - 3));
+    auto word_at = [&](uint32_t &w, int32_t i, bool c) {      // if c: symbols i - 3 .. i (src + i - 3 is aligned); no branch
+        const uint8_t *q = src + i - 3;
+        tps_ld_if(w, reinterpret_cast<const uint32_t *>(q), c);
+        tps_prefetch_if(q - 96, c && (i & 31) < 4 && i >= 99);
     };
+    auto sym = [&](uint32_t c, uint32_t sel) -> uint32_t { return __byte_perm(c, 0u, sel); };    // one byte of the word
     int32_t i = (int32_t)bn - 1;
     if (N == 2) {
         // sA is the state of the parity of i (the symbol coded next), sB the other one
@@ -261,11 +274,12 @@ __device__ __forceinline__ void tps_encode_stream_smem(const EncArgs &a, uint32_
             const uint32_t x = sA; sA = sB; sB = x;
             i--;
         }
-        uint32_t w = i >= 3 ? word_at(i) : 0u;
+        uint32_t w = 0u;
+        word_at(w, i, i >= 3);
         for (; i >= 3; i -= 4) {
             const uint32_t c = w;
-            if (i >= 7) w = word_at(i - 4);
-            const uint2 t3 = ld_t(c >> 24), t2 = ld_t((c >> 16) & 0xffu), t1 = ld_t((c >> 8) & 0xffu), t0 = ld_t(c & 0xffu);
+            word_at(w, i - 4, i >= 7);
+            const uint2 t3 = ld_t(sym(c, 0x4443)), t2 = ld_t(sym(c, 0x4442)), t1 = ld_t(sym(c, 0x4441)), t0 = ld_t(sym(c, 0x4440));
             const uint32_t n3 = enc(sA, t3);
             const uint32_t n2 = enc(sB, t2);
             cnt += n3 + n2;
@@ -291,11 +305,12 @@ __device__ __forceinline__ void tps_encode_stream_smem(const EncArgs &a, uint32_
             flush();
             i--;
         }
-        uint32_t w = i >= 3 ? word_at(i) : 0u;
+        uint32_t w = 0u;
+        word_at(w, i, i >= 3);
         for (; i >= 3; i -= 4) {
             const uint32_t c = w;
-            if (i >= 7) w = word_at(i - 4);
-            const uint2 t3 = ld_t(c >> 24), t2 = ld_t((c >> 16) & 0xffu), t1 = ld_t((c >> 8) & 0xffu), t0 = ld_t(c & 0xffu);
+            word_at(w, i - 4, i >= 7);
+            const uint2 t3 = ld_t(sym(c, 0x4443)), t2 = ld_t(sym(c, 0x4442)), t1 = ld_t(sym(c, 0x4441)), t0 = ld_t(sym(c, 0x4440));
             const uint32_t n3 = enc(st, t3);
             const uint32_t n2 = enc(st, t2);
             cnt += n3 + n2;
@@ -506,17 +521,6 @@ __device__ __forceinline__ void tps_decode_stream(const DecArgs &a, uint32_t b, 
 //    (a stream that runs dry reads zeros -- every look-up stays inside its table -- and is reported as ST_LENGTH as before).
 // Chain per symbol: LDS, SHF, LEA (and SHF + IADD beside the SHF); ~15 instructions per symbol instead of 48.
 __device__ __forceinline__ uint32_t tps_smem_entry(uint32_t e) { return (e >> 24) | ((e >> 8) & 0xff00u) | ((e & 0xffffu) << 18); }
-
-// predicated global load / L1 prefetch (no branch: the lanes of a warp run different streams, and a divergent branch with
-// its reconvergence costs more than the handful of instructions it would skip)
-__device__ __forceinline__ void tps_ld_if(uint32_t &v, const uint32_t *p, bool c)
-{
-    asm volatile("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q ld.global.nc.u32 %0, [%1]; }" : "+r"(v) : "l"(p), "r"((uint32_t)c));
-}
-__device__ __forceinline__ void tps_prefetch_if(const void *p, bool c)
-{
-    asm volatile("{ .reg .pred q; setp.ne.u32 q, %1, 0; @q prefetch.global.L1 [%0]; }" ::"l"(p), "r"((uint32_t)c));
-}
 
 // COMPACT (table_log <= 11): 16-bit entries `num_bits | new_state base << 5` and the symbols as bytes beside them (3 bytes per
 // cell instead of 4: 37 streams per SM instead of 28 at table_log 11); the state is the entry's shared ADDRESS, the symbol
