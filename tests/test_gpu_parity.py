@@ -1102,6 +1102,59 @@ def test_many_streams_across_encoder_waves(ctx):
     assert not dst_.cpu().numpy().any() and np.array_equal(out.cpu().numpy(), src)
 
 
+@pytest.mark.parametrize("n_states,bs,tl,nb", [(2, 301, 0, 4200), (1, 256, 0, 4500), (2, 200, 12, 4100), (1, 333, 9, 4097)])
+def test_many_streams_stay_inside_their_buffers(ctx, n_states, bs, tl, nb):
+    """the thread-per-stream kernels (wide and compact shared-memory tables, unaligned block sizes) between guard bytes: the
+    compressed stream, the output and the status array sit inside larger buffers whose margins must come back untouched,
+    for good streams and for damaged ones (the decoder then runs past the end of its stack and decodes what it finds)"""
+    import torch
+    G = 4096
+    n = nb * bs - 17
+    src = O.generate("geo" if n_states == 2 else "text", 40 + n_states + tl, n)
+    p = ctx.params(bs, tl, n_states, 0)
+    assert ctx.num_streams(n, p) == nb
+    cap = ctx.bound(n, p)
+
+    def guarded(nbytes, dtype=torch.uint8, fill=0xA5):
+        big = torch.full((nbytes + 2 * G,), fill, dtype=dtype, device=ctx.device)
+        return big, big[G:G + nbytes]
+
+    def margins_ok(big, nbytes, fill=0xA5):
+        return bool((big[:G] == fill).all()) and bool((big[G + nbytes:] == fill).all())
+    big_c, comp = guarded(cap)
+    big_o, off = guarded(nb + 1, torch.int64, 0x5A5A)
+    big_s, st = guarded(nb, torch.int32, 0x5A5A)
+    ctx.compress_blocks_async(dev(ctx, src), p, comp, off, st)
+    ctx.sync()
+    assert margins_ok(big_c, cap) and margins_ok(big_o, nb + 1, 0x5A5A) and margins_ok(big_s, nb, 0x5A5A)
+    assert (st.cpu().numpy() >= 0).all()
+    total = int(off[nb].item())
+    big_d, out = guarded(n)
+    big_t, st2 = guarded(nb, torch.int32, 0x5A5A)
+    ctx.decompress_blocks_async(comp, total, off, nb, p, out, n, st2)
+    ctx.sync()
+    assert margins_ok(big_d, n) and margins_ok(big_t, nb, 0x5A5A) and margins_ok(big_c, cap)
+    assert np.array_equal(out.cpu().numpy(), src) and (st2.cpu().numpy() >= 0).all()
+    rng = np.random.default_rng(5 + bs)
+    bad = comp[:total].cpu().numpy().copy()
+    offh = off.cpu().numpy().astype(np.int64)
+    for _ in range(400):
+        b = int(rng.integers(0, nb))
+        lo, hi = int(offh[b]), int(offh[b + 1])
+        k = int(rng.integers(1, max(2, hi - lo)))
+        if rng.integers(0, 2):
+            bad[hi - k:hi] = rng.integers(0, 256, k, dtype=np.uint8)
+        else:
+            bad[lo:lo + k] = rng.integers(0, 256, k, dtype=np.uint8)
+    comp[:total] = dev(ctx, bad)
+    out.fill_(0)
+    ctx.decompress_blocks_async(comp, total, off, nb, p, out, n, st2)
+    ctx.sync()
+    st3 = st2.cpu().numpy()
+    assert ((st3 <= 2) & (st3 >= -11)).all()
+    assert margins_ok(big_d, n) and margins_ok(big_t, nb, 0x5A5A) and margins_ok(big_c, cap)
+
+
 @pytest.mark.parametrize("seed", range(6))
 def test_many_streams_randomised_differential(ctx, seed):
     """seeded shapes through the thread-per-stream kernels (block size, table_log, data kind, one or two states): every
