@@ -768,7 +768,7 @@ int fse_b200_compress_blocks_async(fse_b200_ctx *ctx, const uint8_t *d_src, size
             k_tps_prepare_enc<<<pg, wpc * 32, (size_t)wpc * per_warp, ctx->stream>>>(a, g);
             const size_t set_bytes = ((size_t)2 << tlmax) + 2048;
             const uint32_t per_cta = tps_streams_per_cta(count, (size_t)ctx->num_sms, std::min<size_t>(256, (ctx->smem_optin - 64) / set_bytes));
-            const uint32_t lpw = (uint32_t)std::max(1, std::min(32, dev_opt("FSE_B200_TPS_ENC_LPW", (int)((per_cta + 4) / 5))));   // ~five warps (measured 2 .. 16 lanes)
+            const uint32_t lpw = (uint32_t)std::max(1, std::min(32, dev_opt("FSE_B200_TPS_ENC_LPW", (int)((per_cta + 3) / 4))));   // four warps (c4, 37 streams: 5 / 6 / 8 / 10 / 13 lanes: 65.9 / 66.6 / 67.5 / 63.0 / 64.9 ms)
             if (per_cta >= 1 && set_bytes * 4 <= ctx->smem_optin - 64 && dev_opt("FSE_B200_TPS_ENC_SMEM", 1))
                 k_tps_encode_smem<<<(count + per_cta - 1) / per_cta, ((per_cta + lpw - 1) / lpw) * 32, per_cta * set_bytes, ctx->stream>>>(a, g, per_cta, lpw);
             else
