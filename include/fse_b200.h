@@ -32,6 +32,13 @@
  *  stored with an escape byte that no valid header can start with (low nibble > 10 means
  *  table_log > 15, rejected at src/histogram.rs:439-441):  0x0F = raw bytes follow,
  *  0x0E = one byte follows, repeated.  status[b] reports 1 / 2 for those.
+ *
+ * Which kernels a call takes (same bytes whichever it is)
+ *  n_states 128 / 64: one warp per block, four / two states per lane (the fast formats: ~570 / 1 020 GB/s encode / decode
+ *  on one B200, 8 GiB in 128 KiB blocks).  n_states 1 and 2 -- the crate's own fse_compress / fse_compress2 block
+ *  format -- are one or two serial state chains per block: from 4 096 blocks per call on every block is coded by ONE
+ *  THREAD with the block's tables in shared memory (~125-135 GB/s each way), below that by one warp per block
+ *  (~15-25 GB/s): hand such data over in calls of at least 4 096 blocks (the host-buffer entry points chunk that way).
  */
 #ifndef FSE_B200_H
 #define FSE_B200_H
