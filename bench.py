@@ -73,7 +73,7 @@ def kernel_names(tmode, seg, tlog=0, nblocks=0, num_sms=148, smem_per_sm=233472,
         dec = "k_decode128_blocks" if wide else "k_decode128c_blocks"  # 32-bit entries / compact tables
     elif n == 64:
         enc, dec = "k_encode64_blocks", ("k_decode64c_blocks" if tl <= 12 else "k_decode64_blocks")
-    elif n <= 2 and tmode == 0 and tl <= 12 and nblocks >= 4096:
+    elif n <= 2 and tmode == 0 and tl <= 12:
         enc = "k_tps_prepare_enc + k_tps_encode_smem"                  # one thread per stream, tables in shared memory (fse_tps.cuh)
         dec = "k_tps_prepare_dec + k_tps_decode_smem"
     else:

@@ -1008,11 +1008,11 @@ static int worst_status(const int32_t *st, size_t nb)
 
 static const size_t PIPE_CHUNK_BYTES = 32u << 20;
 
-// blocks a chunk must hold: one- and two-state streams are coded one thread per stream from 4 096 blocks per state on
-// (fse_tps.cuh), so their chunks are that large
+// blocks a chunk must hold: one- and two-state streams are coded one thread per stream (fse_tps.cuh), whose throughput
+// grows with the streams per call until a round of CTAs is full, so their chunks are that large
 static size_t pipe_min_blocks(const fse_b200_params *p)
 {
-    return (p->n_states <= 2 && p->table_mode == FSE_B200_TABLE_PER_BLOCK && !p->flags) ? (size_t)TPS_MIN_BLOCKS * 2 : 1;
+    return (p->n_states <= 2 && p->table_mode == FSE_B200_TABLE_PER_BLOCK && !p->flags) ? (size_t)TPS_PIPE_BLOCKS : 1;
 }
 
 static int pipe_setup(fse_b200_ctx *ctx, size_t nchunks)

@@ -8,7 +8,7 @@
 // GLOBAL memory: a look-up costs L1 / L2 / DRAM latency instead of shared-memory latency, and thousands of chains hide
 // it.  The tables are built by one warp per block with the code of the warp-per-block kernels (k_tps_prepare_*), which
 // also settles every block that needs no coder (escapes, errors).  Same bytes as k_encode_blocks / k_decode_blocks
-// (tests/test_gpu_parity.py::test_many_streams_*); chosen by the dispatcher from TPS_MIN_BLOCKS blocks on.
+// (tests/test_gpu_parity.py::test_many_streams_*); chosen by the dispatcher for every call with one or two states (TPS_MIN_BLOCKS).
 // Measured (tools/tps_sweep.py, 128 KiB geometric blocks, two states; warp per block in brackets): 4 096 blocks encode
 // 41 (29) GB/s, decode 18 (16); 8 192: 58 (29) / 34 (16); 16 384: 71 (32) / 29 (18); c4's 65 536: 51 (26) / 44 (14),
 // one state 48 (13) / 43 (7).  A thread takes the same ~13 / 30 ms for its 128 KiB whatever the block count is (one
@@ -20,7 +20,12 @@
 
 namespace fsed {
 
-constexpr uint32_t TPS_MIN_BLOCKS = 4096;
+// With the tables in shared memory one thread per stream beats one warp per stream at every block count measured (256 blocks
+// of 128 KiB, two states: 3.7 / 3.4 ms against 8.6 / 16.2 ms; a lone stream takes the same time as 256): the one or two
+// lanes a warp-per-block kernel keeps busy run the same chain with more instructions around it.
+constexpr uint32_t TPS_MIN_BLOCKS = 1;
+// the host-buffer paths hand over chunks of at least this many blocks: a round of CTAs holds 148 x 28..37 streams
+constexpr uint32_t TPS_PIPE_BLOCKS = 8192;
 // The two-state encoder takes the blocks in waves of this many: the tables of a wave (6 KiB per block) stay in the L2 while
 // its threads run (c4, 65 536 blocks at once: 158 ms; in waves of 16 384: 109 ms; 8 192: 141; 32 768: 113).  One state: four
 // times as many (a single chain per thread needs the threads more than the L2).  The decoder's tables are 8 KiB per block
