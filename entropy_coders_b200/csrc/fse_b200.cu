@@ -754,7 +754,8 @@ int fse_b200_compress_blocks_async(fse_b200_ctx *ctx, const uint8_t *d_src, size
         const int g = (int)std::min<size_t>(nb, (size_t)ctx->num_sms);
         Timed t(ctx, FSE_B200_K_ENCODE);
         k_encode_sh_global<16, 16><<<g, w * 32, fixed + w * pw, ctx->stream>>>(a);
-    } else if (!global && p->n_states <= 2 && !p->flags && tlmax <= 12 && nb >= (size_t)dev_opt("FSE_B200_TPS_MIN", (int)TPS_MIN_BLOCKS)) {
+    } else if (!global && p->n_states <= 2 && !p->flags && tlmax <= 12 && nb >= (size_t)dev_opt("FSE_B200_TPS_MIN", (int)TPS_MIN_BLOCKS) &&
+               ((size_t)2 << tlmax) + 2048 <= ctx->smem_optin - 64) {
         // the reference's own one- / two-state streams, many of them: one thread per stream (fse_tps.cuh)
         const size_t wave = std::min<size_t>(nb, (size_t)dev_opt("FSE_B200_TPS_WAVE", (int)(p->n_states == 2 ? TPS_ENC_WAVE : 4 * TPS_ENC_WAVE)));
         CK(ctx->tps_enc_tab.reserve((wave << tlmax) * sizeof(uint16_t)));
@@ -769,10 +770,7 @@ int fse_b200_compress_blocks_async(fse_b200_ctx *ctx, const uint8_t *d_src, size
             const size_t set_bytes = ((size_t)2 << tlmax) + 2048;
             const uint32_t per_cta = tps_streams_per_cta(count, (size_t)ctx->num_sms, std::min<size_t>(256, (ctx->smem_optin - 64) / set_bytes));
             const uint32_t lpw = (uint32_t)std::max(1, std::min(32, dev_opt("FSE_B200_TPS_ENC_LPW", (int)((per_cta + 3) / 4))));   // four warps (c4, 37 streams: 5 / 6 / 8 / 10 / 13 lanes: 65.9 / 66.6 / 67.5 / 63.0 / 64.9 ms)
-            if (per_cta >= 1 && set_bytes * 4 <= ctx->smem_optin - 64 && dev_opt("FSE_B200_TPS_ENC_SMEM", 1))
-                k_tps_encode_smem<<<(count + per_cta - 1) / per_cta, ((per_cta + lpw - 1) / lpw) * 32, per_cta * set_bytes, ctx->stream>>>(a, g, per_cta, lpw);
-            else
-                k_tps_encode<<<(count + 31) / 32, 32, 0, ctx->stream>>>(a, g);  // one warp per CTA: few blocks still reach every SM
+            k_tps_encode_smem<<<(count + per_cta - 1) / per_cta, ((per_cta + lpw - 1) / lpw) * 32, per_cta * set_bytes, ctx->stream>>>(a, g, per_cta, lpw);
             ctx->launches += 2;
         }
         ctx->launches--;                                     // the caller counts one
@@ -918,7 +916,7 @@ int fse_b200_decompress_blocks_async(fse_b200_ctx *ctx, const uint8_t *d_comp, s
         if (wpc < 1) return fail(ctx, FSE_B200_ERR_UNSUPPORTED, "table_log too large for shared memory");
         int grid = (int)std::min<size_t>((nblocks + wpc - 1) / wpc, (size_t)ctx->num_sms);
         if (!global && !a.exhaust && p->n_states <= 2 && tlmax <= 12 &&
-            nblocks >= (size_t)dev_opt("FSE_B200_TPS_MIN", (int)TPS_MIN_BLOCKS)) {
+            nblocks >= (size_t)dev_opt("FSE_B200_TPS_MIN", (int)TPS_MIN_BLOCKS) && ((size_t)4 << tlmax) <= ctx->smem_optin - 64) {
             // the reference's own one- / two-state streams, many of them: one thread per stream (fse_tps.cuh)
             CK(ctx->tps_dec_tab.reserve((nblocks << tlmax) * sizeof(uint32_t)));
             CK(ctx->tps_meta.reserve(nblocks * sizeof(uint4)));
@@ -936,12 +934,8 @@ int fse_b200_decompress_blocks_async(fse_b200_ctx *ctx, const uint8_t *d_comp, s
             const uint32_t per_cta = tps_streams_per_cta(nblocks, (size_t)ctx->num_sms, compact ? fit_c : fit_w);
             const uint32_t lpw = (uint32_t)std::max(1, std::min(32, dev_opt("FSE_B200_TPS_LPW", (int)((per_cta + 7) / 8))));
             const unsigned dgrid = (unsigned)((nblocks + per_cta - 1) / std::max(per_cta, 1u)), dthreads = ((per_cta + lpw - 1) / lpw) * 32;
-            if (per_cta >= 1 && 4 * set_bytes <= ctx->smem_optin - 64 && dev_opt("FSE_B200_TPS_SMEM", 1)) {
-                if (compact) k_tps_decode_smem<true><<<dgrid, dthreads, per_cta * set_bytes, ctx->stream>>>(a, g, per_cta, lpw);
-                else k_tps_decode_smem<false><<<dgrid, dthreads, per_cta * set_bytes, ctx->stream>>>(a, g, per_cta, lpw);
-            }
-            else
-                k_tps_decode<<<(unsigned)((nblocks + 31) / 32), 32, 0, ctx->stream>>>(a, g);
+            if (compact) k_tps_decode_smem<true><<<dgrid, dthreads, per_cta * set_bytes, ctx->stream>>>(a, g, per_cta, lpw);
+            else k_tps_decode_smem<false><<<dgrid, dthreads, per_cta * set_bytes, ctx->stream>>>(a, g, per_cta, lpw);
             ctx->launches++;
             CK(cudaGetLastError());
             return FSE_B200_OK;

@@ -1,18 +1,15 @@
 // fse_tps.cuh -- the reference's OWN stream formats (one or two states per stream: fse_compress / fse_compress2,
-// src/lib.rs:112-248) when there are many streams: one THREAD per stream.
+// src/lib.rs:112-248): one THREAD per stream.
 //
 // A stream with one or two states is one or two serial chains (fse.rs:227-239, :363-373): a warp per block has one or two
-// lanes at work (c4, 65 536 blocks: 26 GB/s encode, 14 GB/s decode at two states).  With thousands of blocks the
-// parallelism is across streams, so here every lane runs its own block exactly as the CPU does -- states and the 64-bit bit
-// accumulator (writer.rs:140-149) / the stack window (stack_reader.rs:97-172) in registers -- against that block's tables in
-// GLOBAL memory: a look-up costs L1 / L2 / DRAM latency instead of shared-memory latency, and thousands of chains hide
-// it.  The tables are built by one warp per block with the code of the warp-per-block kernels (k_tps_prepare_*), which
-// also settles every block that needs no coder (escapes, errors).  Same bytes as k_encode_blocks / k_decode_blocks
-// (tests/test_gpu_parity.py::test_many_streams_*); chosen by the dispatcher for every call with one or two states (TPS_MIN_BLOCKS).
-// Measured (tools/tps_sweep.py, 128 KiB geometric blocks, two states; warp per block in brackets): 4 096 blocks encode
-// 41 (29) GB/s, decode 18 (16); 8 192: 58 (29) / 34 (16); 16 384: 71 (32) / 29 (18); c4's 65 536: 51 (26) / 44 (14),
-// one state 48 (13) / 43 (7).  A thread takes the same ~13 / 30 ms for its 128 KiB whatever the block count is (one
-// dependent look-up per symbol pair), until the tables outgrow the L2 (decode: 8 KiB per block) and the look-ups go to DRAM.
+// lanes at work (c4, 65 536 blocks: 26 GB/s encode, 14 GB/s decode at two states).  The parallelism is across streams, so
+// here every lane runs its own block exactly as the CPU does -- states, the bit window of BitStackWriter (writer.rs:140-149)
+// / BitStackReader (stack_reader.rs:97-172) in registers -- against that block's tables in SHARED memory.  The tables are
+// built by one warp per block with the code of the warp-per-block kernels (k_tps_prepare_*), which also settles every block
+// that needs no coder (escapes, errors), and pass through global memory to the CTA that codes the block.  Same bytes as
+// k_encode_blocks / k_decode_blocks (tests/test_gpu_parity.py::test_many_streams_* and every one- / two-state test).
+// History: the first form read the tables from global memory (c4 two states 75 / 45 GB/s: every look-up an
+// L2 / DRAM round trip); in shared memory 136 / 125 GB/s.
 #pragma once
 #include "fse_kernels.cuh"
 #include "fse_kernels64.cuh"
@@ -26,12 +23,8 @@ namespace fsed {
 constexpr uint32_t TPS_MIN_BLOCKS = 1;
 // the host-buffer paths hand over chunks of at least this many blocks: a round of CTAs holds 148 x 28..37 streams
 constexpr uint32_t TPS_PIPE_BLOCKS = 8192;
-// The two-state encoder takes the blocks in waves of this many: the tables of a wave (6 KiB per block) stay in the L2 while
-// its threads run (c4, 65 536 blocks at once: 158 ms; in waves of 16 384: 109 ms; 8 192: 141; 32 768: 113).  One state: four
-// times as many (a single chain per thread needs the threads more than the L2).  The decoder's tables are 8 KiB per block
-// and a thread takes longer: there one wave of everything is the faster way (measured), its look-ups go to DRAM.  (Compact
-// 3-byte tables -- transform on the chain, symbol beside it -- in waves of 12 288 were tried for the decoder: 229 ms against
-// 189 ms on c4, two sectors per symbol instead of one.)
+// The encoder takes the blocks in waves of this many (two states; four times as many with one): the table scratch in global
+// memory (6 KiB per block) stays in the L2 between the kernel that builds a wave's tables and the one that copies them in.
 constexpr uint32_t TPS_ENC_WAVE = 16384;
 
 // per block: x = table_log, y = header bytes (encode) / header bytes consumed (decode), z = 1 when the coder has work
@@ -106,106 +99,6 @@ __global__ void __launch_bounds__(512) k_tps_prepare_enc(EncArgs a, TpsTables g)
             a.status[b] = st;
         }
     }
-}
-
-// one thread per block: Encoder::new_first_symbol for the highest symbol of each state, encode_raw downwards, finish
-// (fse.rs:210-250), marker bit (lib.rs:141,181); BitStackWriter as a 64-bit accumulator flushed in 32-bit words
-__device__ __forceinline__ void tps_encode_stream(const EncArgs &a, uint32_t b, uint4 m, const uint16_t *__restrict__ tab,
-                                                  const uint2 *__restrict__ tt)
-{
-    const uint32_t log2 = m.x, N = a.n_states;
-    const size_t off = (size_t)b * a.block_size;
-    const uint32_t bn = (uint32_t)min((size_t)a.block_size, a.n - off);
-    const uint8_t *__restrict__ src = a.src + off;
-    asm volatile("" : "+l"(tab), "+l"(tt), "+l"(src));        // one base register each: a look-up address is one IMAD.WIDE
-    auto ld_tt = [&](uint32_t sym) -> uint2 { return __ldg(tt + sym); };
-    auto ld_tab = [&](int32_t idx) -> uint32_t { return (uint32_t)__ldg(tab + idx); };
-    auto first = [&](uint32_t sym) -> uint32_t {              // Encoder::new_first_symbol, fse.rs:210-218
-        const uint2 t = ld_tt(sym);
-        const uint32_t bo = (t.x + (1u << 15)) >> 16;
-        const uint32_t value = (bo << 16) - t.x;
-        return ld_tab((int32_t)(value >> bo) + (int32_t)t.y);
-    };
-    uint32_t *pay = reinterpret_cast<uint32_t *>(a.scratch + (size_t)b * a.stride + HDR_RESERVE);
-    const uint32_t cap = a.pay_cap_words;
-    unsigned long long acc = 0;
-    uint32_t cnt = 0, wp = 0;
-    auto put = [&](uint32_t v, uint32_t nb) {                 // v < 2^nb, nb <= 16, cnt < 32
-        acc |= (unsigned long long)v << cnt;
-        cnt += nb;
-        if (cnt >= 32) {
-            if (wp < cap) __stcs(pay + wp, (uint32_t)acc);
-            wp++;
-            acc >>= 32;
-            cnt -= 32;
-        }
-    };
-    auto step = [&](uint32_t &s, uint32_t sym) {              // fse.rs:227-239
-        const uint2 t = ld_tt(sym);
-        const uint32_t nb = (t.x + s) >> 16;
-        put(s & ((1u << nb) - 1u), nb);
-        s = ld_tab((int32_t)(s >> nb) + (int32_t)t.y);
-    };
-    int32_t i = (int32_t)bn - 1;
-    if (N == 2) {
-        // state i & 1 codes symbol i; the two highest symbols initialise the states
-        uint32_t sa = first(__ldg(src + i));                  // parity of bn - 1
-        uint32_t sb = first(__ldg(src + i - 1));
-        i -= 2;
-        // Two independent chains.  Only the next-state look-up depends on the state: the symbols are fetched two pairs
-        // ahead and their transforms one pair ahead, so that a pair costs one memory latency, not three.
-        uint32_t ya = 0, yb = 0, ya2 = 0, yb2 = 0;
-        uint2 ta = make_uint2(0u, 0u), tb = ta;
-        if (i >= 1) { ya = __ldg(src + i); yb = __ldg(src + i - 1); ta = ld_tt(ya); tb = ld_tt(yb); }
-        if (i >= 3) { ya2 = __ldg(src + i - 2); yb2 = __ldg(src + i - 3); }
-        for (; i >= 1; i -= 2) {
-            const uint2 ca = ta, cb = tb;
-            if (i >= 3) { ta = ld_tt(ya2); tb = ld_tt(yb2); }
-            if (i >= 5) { ya2 = __ldg(src + i - 4); yb2 = __ldg(src + i - 5); }
-            const uint32_t na = (ca.x + sa) >> 16, nb = (cb.x + sb) >> 16;
-            const uint32_t va = sa & ((1u << na) - 1u), vb = sb & ((1u << nb) - 1u);
-            sa = ld_tab((int32_t)(sa >> na) + (int32_t)ca.y);
-            sb = ld_tab((int32_t)(sb >> nb) + (int32_t)cb.y);
-            put(va, na);
-            put(vb, nb);
-        }
-        if (i == 0) step(sa, __ldg(src));                     // sa is the state of symbol 0's parity here
-        // final states 1, 0: state of parity 1 first.  sa belongs to parity (bn - 1) & 1.
-        const uint32_t mask = (1u << log2) - 1u;
-        const uint32_t s1 = ((bn - 1) & 1) ? sa : sb, s0 = ((bn - 1) & 1) ? sb : sa;
-        put(s1 & mask, log2);
-        put(s0 & mask, log2);
-    } else {
-        uint32_t s = first(__ldg(src + i));
-        i--;
-        uint32_t y2 = 0;                                      // the same prefetch for the single chain
-        uint2 t = make_uint2(0u, 0u);
-        if (i >= 0) t = ld_tt(__ldg(src + i));
-        if (i >= 1) y2 = __ldg(src + i - 1);
-        for (; i >= 0; i--) {
-            const uint2 c = t;
-            if (i >= 1) t = ld_tt(y2);
-            if (i >= 2) y2 = __ldg(src + i - 2);
-            const uint32_t nb = (c.x + s) >> 16;
-            put(s & ((1u << nb) - 1u), nb);
-            s = ld_tab((int32_t)(s >> nb) + (int32_t)c.y);
-        }
-        put(s & ((1u << log2) - 1u), log2);
-    }
-    put(1u, 1u);
-    const uint32_t bits = wp * 32 + cnt;
-    if (cnt) { if (wp < cap) pay[wp] = (uint32_t)acc; wp++; }
-    if (wp > cap) { a.hlen[b] = 0; a.plen[b] = 0; a.status[b] = ST_CAPACITY; return; }
-    a.plen[b] = (bits + 7) >> 3;
-}
-
-__global__ void __launch_bounds__(32) k_tps_encode(EncArgs a, TpsTables g)
-{
-    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= g.count) return;
-    const uint4 m = g.meta[r];
-    if (!m.z) return;
-    tps_encode_stream(a, g.first + r, m, g.enc_tab + ((size_t)r << a.tlmax), g.enc_tt + (size_t)r * 256);
 }
 
 // predicated global load / L1 prefetch (no branch: the lanes of a warp run different streams, and a divergent branch with
@@ -420,99 +313,6 @@ __global__ void __launch_bounds__(512) k_tps_prepare_dec(DecArgs a, TpsTables g)
     }
 }
 
-// one thread per block: BitStackReader::new (marker), Decoder::new for states 0 .. N-1, decode_symbol for the body,
-// finish for the last N symbols (fse.rs:341-386, lib.rs:187-248), length driven.  The stack is read through a 64-bit
-// window of two aligned words, the next lower word is loaded one refill ahead.
-__device__ __forceinline__ void tps_decode_stream(const DecArgs &a, uint32_t b, uint4 m, const uint32_t *__restrict__ tab)
-{
-    const uint32_t log2 = m.x, consumed = m.y, N = a.n_states;
-    const size_t off = (size_t)b * a.block_size;
-    const uint32_t bn = (uint32_t)min((size_t)a.block_size, a.n - off);
-    uint8_t *out = a.dst + off;
-    asm volatile("" : "+l"(tab));                             // one base register: a look-up address is one IMAD.WIDE
-    auto look = [&](uint32_t st_) -> uint32_t { return __ldg(tab + st_); };
-    const unsigned long long o0 = a.offsets[b], o1 = a.offsets[b + 1];
-    const uint8_t *pay = a.comp + o0 + consumed;
-    const uint32_t plen = (uint32_t)(o1 - o0) - consumed;
-    if (plen == 0 || pay[plen - 1] == 0) { a.status[b] = ST_NO_MARKER; return; }       // stack_reader.rs:17-92
-    const uint32_t bias = (uint32_t)((uintptr_t)pay & 3);
-    const uint32_t *__restrict__ origin = reinterpret_cast<const uint32_t *>(pay - bias);
-    uint32_t cur = (plen - 1) * 8 + ilog2u(pay[plen - 1]) + 8 * bias;                   // marker position
-    const uint32_t floor_bits = 8 * bias;
-    if (cur - floor_bits < N * log2) { a.status[b] = ST_LENGTH; return; }               // lib.rs:197,224-225
-    // window: lo = word q0, hi = word q0 + 1, nx = word q0 - 1; bits at and above the marker are never used
-    // Every lane runs a different stream: whatever is conditional here is written as selects (a branch would diverge on
-    // nearly every read).  qbit = bit index of lo's first bit; pw points at lo's word.
-    const uint32_t *pw = origin + (cur >> 5);
-    uint32_t qbit = cur & ~31u;
-    // the payload and the output are touched once: streaming loads / stores, so that the tables keep their place in the caches
-    uint32_t lo = __ldcs(pw), hi = 0u, nx = qbit ? __ldcs(pw - 1) : 0u;
-    uint32_t bad = 0;
-    auto read = [&](uint32_t n) -> uint32_t {                 // n <= 16
-        const bool ok = cur - floor_bits >= n;
-        bad |= ok ? 0u : 1u;
-        n = ok ? n : 0u;
-        cur -= n;
-        const bool need = cur < qbit;                         // one word down at most
-        hi = need ? lo : hi;
-        lo = need ? nx : lo;
-        if (need) {
-            qbit -= 32;
-            pw--;
-            nx = qbit ? __ldcs(pw - 1) : 0u;
-        }
-        return __funnelshift_r(lo, hi, cur & 31) & ~(0xffffffffu << n);
-    };
-    const uint32_t body = bn - N;
-    const bool aligned = (((uintptr_t)out) & 3) == 0;
-    uint32_t i = 0;
-    if (N == 2) {
-        uint32_t s0 = read(log2), s1 = read(log2);            // Decoder::new, fse.rs:349-352: state 0 first
-        uint32_t e0 = look(s0), e1 = look(s1);
-        uint32_t word = 0;
-        for (; i + 2 <= body && !bad; i += 2) {               // fse.rs:363-373 on the two chains
-            const uint32_t b0 = read(e0 >> 24);
-            const uint32_t y0 = (e0 >> 16) & 0xffu;
-            s0 = (e0 & 0xffffu) + b0;
-            e0 = look(s0);
-            const uint32_t b1 = read(e1 >> 24);
-            const uint32_t y1 = (e1 >> 16) & 0xffu;
-            s1 = (e1 & 0xffffu) + b1;
-            e1 = look(s1);
-            if (aligned) {
-                word |= (y0 | (y1 << 8)) << ((i & 2) * 8);
-                if (i & 2) { __stcs(reinterpret_cast<uint32_t *>(out + (i & ~3u)), word); word = 0; }
-            } else {
-                out[i] = (uint8_t)y0;
-                out[i + 1] = (uint8_t)y1;
-            }
-        }
-        if (aligned && (i & 2) && !bad) { out[i - 2] = (uint8_t)word; out[i - 1] = (uint8_t)(word >> 8); }   // half a word pending
-        if (!bad && i < body) {                               // one more body symbol: state 0's turn (i is even)
-            const uint32_t b0 = read(e0 >> 24);
-            out[i] = (uint8_t)(e0 >> 16);
-            s0 = (e0 & 0xffffu) + b0;
-            e0 = look(s0);
-            i++;
-        }
-        if (!bad) {                                           // Decoder::finish: symbols body, body + 1 from states (i & 1), ...
-            out[i] = (uint8_t)(((i & 1) ? e1 : e0) >> 16);
-            out[i + 1] = (uint8_t)(((i & 1) ? e0 : e1) >> 16);
-        }
-    } else {
-        uint32_t s = read(log2);
-        uint32_t e = look(s);
-        for (; i < body && !bad; i++) {
-            const uint32_t bits = read(e >> 24);
-            out[i] = (uint8_t)(e >> 16);
-            s = (e & 0xffffu) + bits;
-            e = look(s);
-        }
-        if (!bad) out[i] = (uint8_t)(e >> 16);
-    }
-    a.status[b] = (bad || cur != floor_bits) ? ST_LENGTH : ST_OK;
-}
-
 // ---- the shared-memory form of the same decoder.  A stream is a serial chain (entry -> bits -> next entry), so what
 // counts is the length of that chain and the instructions around it:
 //  * entry of the shared copy: num_bits | symbol << 8 | (4 * new_state base) << 16 (tps_smem_entry): the shift amounts of a
@@ -678,15 +478,6 @@ __device__ __forceinline__ void tps_decode_stream_smem(const DecArgs &a, uint32_
     }
     const uint32_t used = entered0 - 32u * (uint32_t)k - cnt;
     a.status[b] = (used != cur - floor_bits) ? ST_LENGTH : ST_OK;   // ran dry, or bits left over (lib.rs:205,245)
-}
-
-__global__ void __launch_bounds__(32) k_tps_decode(DecArgs a, TpsTables g)
-{
-    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= a.nblocks) return;
-    const uint4 m = g.meta[b];
-    if (!m.z) return;
-    tps_decode_stream(a, b, m, g.dec_tab + ((size_t)b << a.tlmax));
 }
 
 // The same streams with their tables in SHARED memory: a CTA takes `per_cta` blocks (as many as tables fit: 28 at
