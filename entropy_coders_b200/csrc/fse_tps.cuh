@@ -160,6 +160,14 @@ __device__ __forceinline__ void tps_encode_stream_smem(const EncArgs &a, uint32_
         tps_ld_if(w, reinterpret_cast<const uint32_t *>(q), c);
         tps_prefetch_if(q - 96, c && (i & 31) < 4 && i >= 99);
     };
+    // inside the loop (i >= 3): the word below the current one, or the current one again when there is none (then it is not
+    // used): the address is arithmetic, the load unconditional (a predicate set by ISETP is usable 13 cycles later)
+    auto next_word = [&](uint32_t &w, int32_t i) {
+        const uint32_t down = min(4u, (uint32_t)i - 3u) & 4u;                   // 4 when i >= 7
+        const uint8_t *q = src + i - 3 - down;
+        w = __ldg(reinterpret_cast<const uint32_t *>(q));
+        tps_prefetch_if(q - 96, (i & 31) >= 4 && (i & 31) < 8 && i >= 103);
+    };
     auto sym = [&](uint32_t c, uint32_t sel) -> uint32_t { return __byte_perm(c, 0u, sel); };    // one byte of the word
     int32_t i = (int32_t)bn - 1;
     if (N == 2) {
@@ -176,7 +184,7 @@ __device__ __forceinline__ void tps_encode_stream_smem(const EncArgs &a, uint32_
         word_at(w, i, i >= 3);
         for (; i >= 3; i -= 4) {
             const uint32_t c = w;
-            word_at(w, i - 4, i >= 7);
+            next_word(w, i);
             const uint2 t3 = ld_t(sym(c, 0x4443)), t2 = ld_t(sym(c, 0x4442)), t1 = ld_t(sym(c, 0x4441)), t0 = ld_t(sym(c, 0x4440));
             const uint32_t n3 = enc(sA, t3);
             const uint32_t n2 = enc(sB, t2);
@@ -207,7 +215,7 @@ __device__ __forceinline__ void tps_encode_stream_smem(const EncArgs &a, uint32_
         word_at(w, i, i >= 3);
         for (; i >= 3; i -= 4) {
             const uint32_t c = w;
-            word_at(w, i - 4, i >= 7);
+            next_word(w, i);
             const uint2 t3 = ld_t(sym(c, 0x4443)), t2 = ld_t(sym(c, 0x4442)), t1 = ld_t(sym(c, 0x4441)), t0 = ld_t(sym(c, 0x4440));
             const uint32_t n3 = enc(st, t3);
             const uint32_t n2 = enc(st, t2);
