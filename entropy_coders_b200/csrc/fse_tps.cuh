@@ -9,7 +9,7 @@
 // that needs no coder (escapes, errors), and pass through global memory to the CTA that codes the block.  Same bytes as
 // k_encode_blocks / k_decode_blocks (tests/test_gpu_parity.py::test_many_streams_* and every one- / two-state test).
 // History: the first form read the tables from global memory (c4 two states 75 / 45 GB/s: every look-up an
-// L2 / DRAM round trip); in shared memory 136 / 125 GB/s.
+// L2 / DRAM round trip); in shared memory 148 / 125 GB/s.
 #pragma once
 #include "fse_kernels.cuh"
 #include "fse_kernels64.cuh"

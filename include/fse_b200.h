@@ -37,7 +37,7 @@
  *  n_states 128 / 64: one warp per block, four / two states per lane (the fast formats: ~570 / 1 020 GB/s encode / decode
  *  on one B200, 8 GiB in 128 KiB blocks).  n_states 1 and 2 -- the crate's own fse_compress / fse_compress2 block
  *  format -- are one or two serial state chains per block: every block is coded by ONE THREAD with the block's tables in
- *  shared memory (a 128 KiB block takes ~4 ms however many there are, up to ~5 000 blocks at a time: 125-135 GB/s each
+ *  shared memory (a 128 KiB block takes ~4 ms however many there are, up to ~5 000 blocks at a time: 125-148 GB/s each
  *  way from 8 192 blocks per call on, 33 GB/s at 1 024, 9 GB/s at 256): hand such data over in calls of many blocks (the
  *  host-buffer entry points take chunks of 8 192).
  */
